@@ -1,0 +1,83 @@
+/* mjt.h -- C ABI of libmjt_b200: the B200-native batched physics step.
+ *
+ * The reference (vmoens/mujoco-torch) is pure Python and has no FFI layer; its boundary for this path is
+ *   mujoco_torch.device_put(MjModel)            reference mujoco_torch/_src/device.py:1029
+ *   mujoco_torch.make_data(model)               reference mujoco_torch/_src/io.py:100
+ *   mujoco_torch.step(model, data)              reference mujoco_torch/_src/forward.py:463
+ *   mujoco_torch.forward(model, data)           reference mujoco_torch/_src/forward.py:373
+ * The functions below are what a Python binding of those four calls needs (INTEGRATION.md shows the ctypes
+ * stub): plain pointers and sizes, no torch types, no exceptions across the boundary (0 = ok, else see
+ * mjt_last_error()), caller-owned buffers, stream-ordered and asynchronous.
+ *
+ * Memory convention ("env-minor"): every per-environment array of n words for a batch of nenv environments is an
+ * (n, nenv) array -- word k of environment e at base[k * nenv + e] -- in the model's compute dtype (float or
+ * double, fixed when the blob was packed).
+ */
+#ifndef MJT_H_
+#define MJT_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mjtModel mjtModel;
+
+/* Input state of one step / forward call: device pointers, env-minor.  Replaces the Data fields the reference's
+ * step reads (reference types.Data :1091-1261): qpos (nq), qvel (nv), act (na), time (1), qacc_warmstart (nv),
+ * ctrl (nu), qfrc_applied (nv), xfrc_applied (6*nbody), mocap_pos (3*nmocap), mocap_quat (4*nmocap),
+ * sensordata (nsensordata; slots of sensor types without an implementation pass through), qfrc_constraint (nv;
+ * only read when the model has no constraint rows), eq_active (neq, int32).  qacc is accepted for symmetry with
+ * the reference's _check_state but never influences the result. */
+typedef struct mjtStateIn {
+  const void* qpos;
+  const void* qvel;
+  const void* act;
+  const void* time;
+  const void* qacc;
+  const void* qacc_warmstart;
+  const void* ctrl;
+  const void* qfrc_applied;
+  const void* xfrc_applied;
+  const void* mocap_pos;
+  const void* mocap_quat;
+  const void* sensordata;
+  const void* qfrc_constraint;
+  const int* eq_active;
+} mjtStateIn;
+
+/* Library / ABI version (major * 1000 + minor). */
+int mjt_version(void);
+
+/* Last error message of the calling thread ("" if none). */
+const char* mjt_last_error(void);
+
+/* device_put(MjModel): copies a packed ModelBlob (mujoco_torch_b200/layout.py) to `device`.
+ * Replaces reference device.device_put :1029-1112 for MjModel inputs. */
+int mjt_model_create(const void* blob_host, size_t nbytes, int device, mjtModel** out);
+void mjt_model_destroy(mjtModel* m);
+
+/* Sizes a caller needs to allocate buffers: words per env of the output Data buffer, of the scratch buffer
+ * (RK4 stage buffer + accumulators; 0 for the other integrators) and sizeof(compute dtype). */
+int mjt_model_data_words(const mjtModel* m);
+int mjt_model_scratch_words(const mjtModel* m);
+int mjt_model_dtype_size(const mjtModel* m);
+/* Word offset and word count of a named Data field inside the output buffer; -1 if unknown. */
+int mjt_model_field(const mjtModel* m, const char* name, int* offset, int* words);
+
+/* step(model, data): reference forward.step :463-496.  `out` is a (data_words, nenv) device buffer that receives
+ * the complete new Data (state + every derived field); `scratch` is (scratch_words, nenv) or NULL when
+ * scratch_words == 0.  The input is never modified.  Launches on `stream` (a cudaStream_t) and returns immediately. */
+int mjt_step(const mjtModel* m, const mjtStateIn* in, void* out, void* scratch, int nenv, void* stream);
+
+/* forward(model, data): reference forward.forward :373-401 (no integration). */
+int mjt_forward(const mjtModel* m, const mjtStateIn* in, void* out, int nenv, void* stream);
+
+/* Number of kernel launches mjt_step issues for this model (used by bench.py's gpu_launches claim). */
+int mjt_step_launches(const mjtModel* m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MJT_H_ */

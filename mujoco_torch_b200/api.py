@@ -1,0 +1,174 @@
+"""Public API mirroring ``mujoco_torch`` for the batched physics step.
+
+    mx = device_put(mj_model).to("cuda")          reference device.py:1029
+    dx = make_data(mx)                            reference io.py:100
+    d_batch = dx.expand(B).clone()                reference benchmarks/_helpers.py:25-42
+    d_batch = step(mx, d_batch)                   reference forward.py:463
+    d_batch = torch.vmap(lambda d: step(mx, d))(d_batch)
+
+``step`` never mutates its input; unchanged fields are shared with the input Data, everything the step writes is a
+view of one freshly allocated env-minor buffer.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import layout as L
+from . import ops
+from .data import Contact, Data
+from .mjmodel import ConeType, MjModelLite
+from .model import Model, device_put_model
+
+_OUT_FIELDS = tuple(n for n, _ in L.D_FIELDS if n not in L.HIDDEN_FIELDS and not n.startswith("contact_"))
+
+
+def device_put(value, *, dtype: torch.dtype | None = None):
+    """Place a compiled model (``mujoco.MjModel`` or ``MjModelLite``: any object with MjModel attribute names) on
+    the device-side representation.  Mirrors reference ``device_put`` (device.py:1029-1112) for models."""
+    if isinstance(value, Model):
+        return value
+    if not hasattr(value, "nq") or not hasattr(value, "opt"):
+        raise NotImplementedError(f"{type(value)} is not supported for device_put.")
+    return device_put_model(value, dtype)
+
+
+def _contact_static(m: Model, lead, device):
+    c = m.con
+    ft = lambda a: torch.as_tensor(np.ascontiguousarray(a)).to(m.dtype).to(device)
+    it = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a).astype(np.int64)).to(dt).to(device)
+    ex = lambda t: t.expand(*lead, *t.shape) if lead else t
+    g1, g2 = it(c["g1"], torch.int64), it(c["g2"], torch.int64)
+    return dict(
+        includemargin=ex(ft(c["include"])), friction=ex(ft(c["friction"])), solref=ex(ft(c["solref"])),
+        solreffriction=ex(ft(c["solreffriction"])), solimp=ex(ft(c["solimp"])), contact_dim=ex(it(c["dim"], torch.int32)),
+        geom1=ex(g1), geom2=ex(g2), geom=ex(torch.stack([g1, g2], dim=-1)), efc_address=ex(it(m.con_efcadr, torch.int64)),
+    )
+
+
+def make_data(m: Model) -> Data:
+    """Zero-initialised unbatched Data with static contact / efc sizes (reference io.make_data :100-221)."""
+    if not isinstance(m, Model):
+        m = device_put(m)
+    dev, dt = m.device, m.dtype
+    z = lambda *s: torch.zeros(s, dtype=dt, device=dev)
+    f = {}
+    for name, _ in L.D_FIELDS:
+        if name in L.HIDDEN_FIELDS or name.startswith("contact_"):
+            continue
+        f[name] = z(*m.field_shape[name])
+    f["qpos"] = torch.as_tensor(np.asarray(m.mj.qpos0, dtype=np.float64)).to(dt).to(dev)
+    f.update(ctrl=z(m.nu), qfrc_applied=z(m.nv), xfrc_applied=z(m.nbody, 6), mocap_pos=z(m.nmocap, 3), mocap_quat=z(m.nmocap, 4),
+             eq_active=torch.as_tensor(np.asarray(m.mj.eq_active0).astype(np.int32)).to(dev), userdata=z(0),
+             qLDiagInv=z(m.nv), qfrc_fluid=z(m.nv), qfrc_inverse=z(m.nv), cacc=z(m.nbody, 6), cfrc_int=z(m.nbody, 6),
+             cfrc_ext=z(m.nbody, 6), subtree_linvel=z(m.nbody, 3), subtree_angmom=z(m.nbody, 3), efc_pos=z(m.nefc), efc_margin=z(m.nefc),
+             efc_type=torch.zeros(m.nefc, dtype=torch.int32, device=dev), solver_niter=torch.zeros((), dtype=torch.int32, device=dev))
+    for b in range(m.nbody):
+        mid = int(m.mj.body_mocapid[b])
+        if mid >= 0:
+            f["mocap_pos"][mid] = torch.as_tensor(np.asarray(m.mj.body_pos[b])).to(dt)
+            f["mocap_quat"][mid] = torch.as_tensor(np.asarray(m.mj.body_quat[b])).to(dt)
+    contact = Contact(dict(dist=z(m.ncon), pos=z(m.ncon, 3), frame=z(m.ncon, 3, 3), **_contact_static(m, (), dev)))
+    f["contact"] = contact
+    return Data(f, dict(ne=m.ne, nf=m.nf, nl=m.nl, ncon=m.ncon, nefc=m.nefc))
+
+
+def _run(m: Model, d: Data, mode: int) -> Data:
+    if not isinstance(m, Model):
+        raise TypeError("first argument must be a mujoco_torch_b200 Model (see device_put)")
+    lead = tuple(d.qpos.shape[:-1])
+    flat = len(lead) > 1
+    args = []
+    for name in ops._STATE_ARGS:
+        t = getattr(d, name)
+        if name == "time":
+            t = t.unsqueeze(-1)
+        ne = {"xfrc_applied": 2, "mocap_pos": 2, "mocap_quat": 2}.get(name, 1)
+        t = t.reshape(*t.shape[: t.dim() - ne], -1)
+        if flat:
+            t = t.reshape(-1, t.shape[-1])
+        args.append(t)
+    out = torch.ops.mjt.run(m._id, mode, *args)
+    if flat:
+        out = out.reshape(*lead, out.shape[-1])
+    new = dict(d._fields)
+    sl = lambda name: out[..., m.field_off[name]: m.field_off[name] + int(np.prod(m.field_shape[name]) if m.field_shape[name] else 1)]
+    for name in _OUT_FIELDS:
+        shp = m.field_shape[name]
+        v = sl(name)
+        new[name] = v.reshape(*lead, *shp) if shp else v.reshape(*lead)
+    # model-constant contact fields (reference collision_driver._compute_static_contact_dict :691-793); efc_address is
+    # re-derived cone-aware every step by the reference (constraint.py:636-646), so it always comes from the model
+    key = (lead, str(out.device))
+    cache = m.__dict__.setdefault("_static_contact_cache", {})
+    if key not in cache:
+        cache[key] = _contact_static(m, lead, out.device)
+    static = cache[key]
+    new["contact"] = Contact(dict(dist=sl("contact_dist").reshape(*lead, m.ncon), pos=sl("contact_pos").reshape(*lead, m.ncon, 3),
+                                  frame=sl("contact_frame").reshape(*lead, m.ncon, 3, 3), **static))
+    meta = dict(d._meta)
+    meta.update(ne=m.ne, nf=m.nf, nl=m.nl, ncon=m.ncon, nefc=m.nefc)
+    return Data(new, meta)
+
+
+def step(m: Model, d: Data, fixed_iterations: bool = False) -> Data:
+    """Advance the simulation by one timestep (reference forward.step :463-496).
+
+    ``fixed_iterations`` exists for signature compatibility; the kernels always implement true per-env early exit,
+    which is what the reference computes in eager mode.
+    """
+    if fixed_iterations:
+        raise NotImplementedError("fixed_iterations=True (static-graph mode of the reference) is not needed by the CUDA path")
+    return _run(m, d, ops.MODE_STEP)
+
+
+def forward(m: Model, d: Data, fixed_iterations: bool = False) -> Data:
+    """Forward dynamics without integration (reference forward.forward :373-401)."""
+    if fixed_iterations:
+        raise NotImplementedError("fixed_iterations=True is not supported")
+    return _run(m, d, ops.MODE_FORWARD)
+
+
+# ---- stage-level API (reference __init__.py:41-108): each stage returns `d` with that stage's write-set refreshed
+# (SURVEY.md Appendix D).  All stages are evaluated by the fused forward kernels from the state in `d`.
+_STAGE_FIELDS = {
+    "kinematics": ("qpos", "xanchor", "xaxis", "xpos", "xquat", "xmat", "xipos", "ximat", "geom_xpos", "geom_xmat", "site_xpos", "site_xmat"),
+    "com_pos": ("subtree_com", "cinert", "cdof"),
+    "crb": ("crb", "qM"),
+    "factor_m": ("qLD",),
+    "tendon": ("ten_length", "ten_J"),
+    "transmission": ("actuator_length", "actuator_moment"),
+    "com_vel": ("cvel", "cdof_dot"),
+    "rne": ("qfrc_bias",),
+    "passive": ("qfrc_passive", "qfrc_gravcomp"),
+    "collision": ("contact",),
+    "make_constraint": ("efc_J", "efc_D", "efc_aref", "efc_frictionloss", "contact"),
+    "fwd_position": ("qpos", "xanchor", "xaxis", "xpos", "xquat", "xmat", "xipos", "ximat", "geom_xpos", "geom_xmat", "site_xpos",
+                     "site_xmat", "subtree_com", "cinert", "cdof", "crb", "qM", "qLD", "ten_length", "ten_J", "actuator_length",
+                     "actuator_moment", "contact", "efc_J", "efc_D", "efc_aref", "efc_frictionloss"),
+    "fwd_velocity": ("actuator_velocity", "ten_velocity", "cvel", "cdof_dot", "qfrc_passive", "qfrc_gravcomp", "qfrc_bias"),
+    "fwd_actuation": ("act_dot", "qfrc_actuator", "actuator_force"),
+    "fwd_acceleration": ("qfrc_smooth", "qacc_smooth"),
+    "solve": ("qacc", "qacc_warmstart", "qfrc_constraint", "efc_force"),
+    "sensor_pos": ("sensordata",), "sensor_vel": ("sensordata",), "sensor_acc": ("sensordata",),
+}
+
+
+def _make_stage(name):
+    def stage(m: Model, d: Data) -> Data:
+        full = forward(m, d)
+        return d.replace(**{k: full._fields[k] for k in _STAGE_FIELDS[name]})
+
+    stage.__name__ = name
+    stage.__doc__ = f"Stage ``{name}``: refreshes {_STAGE_FIELDS[name]} from the state in ``d``."
+    return stage
+
+
+for _n in _STAGE_FIELDS:
+    globals()[_n] = _make_stage(_n)
+
+
+def constraint_sizes(m: Model):
+    """(ne, nf, nl, ncon, nefc) -- reference collision_driver.constraint_sizes :681-688."""
+    return m.constraint_sizes_py

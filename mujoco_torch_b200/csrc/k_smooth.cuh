@@ -1,0 +1,599 @@
+// k_smooth: one thread per environment, env-minor coalesced access.
+// Fuses the reference's _check_state -> kinematics -> com_pos -> tendon -> crb/make_m -> transmission ->
+// com_vel -> passive -> rne -> actuation -> qfrc_smooth (reference forward.py:44-59,73-99,102-228;
+// smooth.py:34-308,385-591; passive.py:80-200; support.py:50-80,138-194).
+// The reference's tree scans become loops in body order (parents precede children).
+#pragma once
+#include "mjt_common.cuh"
+
+template <typename T>
+__device__ __forceinline__ void ld3(const EnvBuf<T>& d, int off, V3<T>& v) { v.x = d.get(off); v.y = d.get(off + 1); v.z = d.get(off + 2); }
+template <typename T>
+__device__ __forceinline__ void st3(const EnvBuf<T>& d, int off, const V3<T>& v) { d.set(off, v.x); d.set(off + 1, v.y); d.set(off + 2, v.z); }
+template <typename T>
+__device__ __forceinline__ V3<T> f3(const T* p) { return V3<T>(p[0], p[1], p[2]); }
+template <typename T>
+__device__ __forceinline__ Q4<T> f4(const T* p) { return Q4<T>(p[0], p[1], p[2], p[3]); }
+
+// Jacobian-transpose application of a force/torque at a world point on body b:
+// qfrc[i] += jacp_i . force + jacr_i . torque over ancestor dofs (reference support.apply_ft :169-181).
+template <typename T, typename F>
+__device__ __forceinline__ void for_ancestor_dofs(const ModelView<T>& m, int b, F fn) {
+  const int* bdofadr = m.I(I_body_dofadr);
+  const int* bdofnum = m.I(I_body_dofnum);
+  const int* dparent = m.I(I_dof_parentid);
+  const int* bparent = m.I(I_body_parentid);
+  while (b > 0 && bdofnum[b] == 0) b = bparent[b];
+  if (b <= 0) return;
+  for (int i = bdofadr[b] + bdofnum[b] - 1; i >= 0; i = dparent[i]) fn(i);
+}
+
+template <typename T>
+__device__ void smooth_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T>& d, size_t B, int env) {
+  const int nq = m.h(H_nq), nv = m.h(H_nv), nu = m.h(H_nu), na = m.h(H_na), nbody = m.h(H_nbody), njnt = m.h(H_njnt);
+  const int ngeom = m.h(H_ngeom), nsite = m.h(H_nsite), ntendon = m.h(H_ntendon), flags = m.h(H_disableflags);
+  const int oQpos = m.D(D_qpos), oQvel = m.D(D_qvel), oXpos = m.D(D_xpos), oXquat = m.D(D_xquat), oXmat = m.D(D_xmat);
+  const int oXipos = m.D(D_xipos), oXimat = m.D(D_ximat), oAnchor = m.D(D_xanchor), oAxis = m.D(D_xaxis);
+  const int oCom = m.D(D_subtree_com), oCinert = m.D(D_cinert), oCrb = m.D(D_crb), oCdof = m.D(D_cdof), oCdofdot = m.D(D_cdof_dot);
+  const int oCvel = m.D(D_cvel), oM = m.D(D_qM);
+  const int* body_parent = m.I(I_body_parentid);
+  const int* body_root = m.I(I_body_rootid);
+  const int* body_jntadr = m.I(I_body_jntadr);
+  const int* body_jntnum = m.I(I_body_jntnum);
+  const int* body_dofadr = m.I(I_body_dofadr);
+  const int* body_dofnum = m.I(I_body_dofnum);
+  const int* jnt_type = m.I(I_jnt_type);
+  const int* jnt_qposadr = m.I(I_jnt_qposadr);
+  const int* jnt_dofadr = m.I(I_jnt_dofadr);
+  const int* jnt_bodyid = m.I(I_jnt_bodyid);
+  const int* dof_bodyid = m.I(I_dof_bodyid);
+  const int* dof_parent = m.I(I_dof_parentid);
+  const T* qpos0 = m.F(F_qpos0);
+
+  // ---- _check_state (forward.py:44-59) + copy of pass-through state
+  for (int i = 0; i < nq; ++i) {
+    T q = in_get<T>(in.qpos, B, env, i);
+    if (!t_finite(q) || t_abs(q) > T(MJT_MAXVAL)) q = qpos0[i];
+    d.set(oQpos + i, q);
+  }
+  for (int i = 0; i < nv; ++i) {
+    T v = in_get<T>(in.qvel, B, env, i);
+    if (!t_finite(v) || t_abs(v) > T(MJT_MAXVAL)) v = T(0);
+    d.set(oQvel + i, v);
+  }
+  for (int i = 0; i < na; ++i) d.set(m.D(D_act) + i, in_get<T>(in.act, B, env, i));
+  d.set(m.D(D_time), in_get<T>(in.time, B, env, 0));
+
+  // ---- kinematics (smooth.py:34-207)
+  for (int b = 0; b < nbody; ++b) {
+    V3<T> pos = f3(m.F(F_body_pos) + 3 * b);
+    Q4<T> quat = f4(m.F(F_body_quat) + 4 * b);
+    if (b > 0) {
+      const int p = body_parent[b];
+      V3<T> ppos;
+      ld3(d, oXpos + 3 * p, ppos);
+      Q4<T> pq(d.get(oXquat + 4 * p), d.get(oXquat + 4 * p + 1), d.get(oXquat + 4 * p + 2), d.get(oXquat + 4 * p + 3));
+      pos = ppos + qrot(pos, pq);
+      quat = qmul(pq, quat);
+    }
+    for (int j = body_jntadr[b], je = j + body_jntnum[b]; j < je; ++j) {
+      const int jt = jnt_type[j], qa = jnt_qposadr[j];
+      const V3<T> jpos = f3(m.F(F_jnt_pos) + 3 * j), jaxis = f3(m.F(F_jnt_axis) + 3 * j);
+      V3<T> anchor, axis;
+      if (jt == JNT_FREE) {
+        ld3(d, oQpos + qa, anchor);
+        axis = V3<T>(0, 0, 1);
+      } else {
+        anchor = qrot(jpos, quat) + pos;
+        axis = qrot(jaxis, quat);
+      }
+      st3(d, oAnchor + 3 * j, anchor);
+      st3(d, oAxis + 3 * j, axis);
+      if (jt == JNT_FREE) {
+        ld3(d, oQpos + qa, pos);
+        quat = qnormalize(Q4<T>(d.get(oQpos + qa + 3), d.get(oQpos + qa + 4), d.get(oQpos + qa + 5), d.get(oQpos + qa + 6)));
+        d.set(oQpos + qa + 3, quat.w); d.set(oQpos + qa + 4, quat.x); d.set(oQpos + qa + 5, quat.y); d.set(oQpos + qa + 6, quat.z);
+      } else if (jt == JNT_BALL) {
+        Q4<T> ql = qnormalize(Q4<T>(d.get(oQpos + qa), d.get(oQpos + qa + 1), d.get(oQpos + qa + 2), d.get(oQpos + qa + 3)));
+        d.set(oQpos + qa, ql.w); d.set(oQpos + qa + 1, ql.x); d.set(oQpos + qa + 2, ql.y); d.set(oQpos + qa + 3, ql.z);
+        quat = qmul(quat, ql);
+        pos = anchor - qrot(jpos, quat);
+      } else if (jt == JNT_HINGE) {
+        const T angle = d.get(oQpos + qa) - qpos0[qa];
+        quat = qmul(quat, axis_angle_q(jaxis, angle));
+        pos = anchor - qrot(jpos, quat);
+      } else {
+        pos = pos + axis * (d.get(oQpos + qa) - qpos0[qa]);
+      }
+    }
+    st3(d, oXpos + 3 * b, pos);
+    d.set(oXquat + 4 * b, quat.w); d.set(oXquat + 4 * b + 1, quat.x); d.set(oXquat + 4 * b + 2, quat.y); d.set(oXquat + 4 * b + 3, quat.z);
+  }
+  // mocap overrides are applied after the tree pass, as in the reference (smooth.py:105-113)
+  for (int b = 0; b < nbody; ++b) {
+    const int mid = m.I(I_body_mocapid)[b];
+    V3<T> pos;
+    Q4<T> quat;
+    if (mid >= 0) {
+      pos = V3<T>(in_get<T>(in.mocap_pos, B, env, 3 * mid), in_get<T>(in.mocap_pos, B, env, 3 * mid + 1), in_get<T>(in.mocap_pos, B, env, 3 * mid + 2));
+      quat = qnormalize(Q4<T>(in_get<T>(in.mocap_quat, B, env, 4 * mid), in_get<T>(in.mocap_quat, B, env, 4 * mid + 1),
+                              in_get<T>(in.mocap_quat, B, env, 4 * mid + 2), in_get<T>(in.mocap_quat, B, env, 4 * mid + 3)));
+      st3(d, oXpos + 3 * b, pos);
+      d.set(oXquat + 4 * b, quat.w); d.set(oXquat + 4 * b + 1, quat.x); d.set(oXquat + 4 * b + 2, quat.y); d.set(oXquat + 4 * b + 3, quat.z);
+    } else {
+      ld3(d, oXpos + 3 * b, pos);
+      quat = Q4<T>(d.get(oXquat + 4 * b), d.get(oXquat + 4 * b + 1), d.get(oXquat + 4 * b + 2), d.get(oXquat + 4 * b + 3));
+    }
+    T mat[9];
+    q2mat(quat, mat);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) d.set(oXmat + 9 * b + k, mat[k]);
+    // inertial frame
+    V3<T> ipos = pos + qrot(f3(m.F(F_body_ipos) + 3 * b), quat);
+    st3(d, oXipos + 3 * b, ipos);
+    q2mat(qmul(quat, f4(m.F(F_body_iquat) + 4 * b)), mat);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) d.set(oXimat + 9 * b + k, mat[k]);
+  }
+  // geoms and sites (local_to_global, support.py:99-108)
+  for (int pass = 0; pass < 2; ++pass) {
+    const int n = pass == 0 ? ngeom : nsite;
+    const int* bid = m.I(pass == 0 ? I_geom_bodyid : I_site_bodyid);
+    const T* lpos = m.F(pass == 0 ? F_geom_pos : F_site_pos);
+    const T* lquat = m.F(pass == 0 ? F_geom_quat : F_site_quat);
+    const int oP = m.D(pass == 0 ? D_geom_xpos : D_site_xpos), oR = m.D(pass == 0 ? D_geom_xmat : D_site_xmat);
+    for (int g = 0; g < n; ++g) {
+      const int b = bid[g];
+      V3<T> bp;
+      ld3(d, oXpos + 3 * b, bp);
+      Q4<T> bq(d.get(oXquat + 4 * b), d.get(oXquat + 4 * b + 1), d.get(oXquat + 4 * b + 2), d.get(oXquat + 4 * b + 3));
+      st3(d, oP + 3 * g, bp + qrot(f3(lpos + 3 * g), bq));
+      T mat[9];
+      q2mat(qmul(bq, f4(lquat + 4 * g)), mat);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) d.set(oR + 9 * g + k, mat[k]);
+    }
+  }
+
+  // ---- com_pos (smooth.py:210-288)
+  const T* body_mass = m.F(F_body_mass);
+  const T* body_submass = m.F(F_body_subtreemass);
+  for (int b = 0; b < nbody; ++b) {
+    V3<T> ip;
+    ld3(d, oXipos + 3 * b, ip);
+    st3(d, oCom + 3 * b, ip * body_mass[b]);
+  }
+  for (int b = nbody - 1; b > 0; --b) {
+    const int p = body_parent[b];
+    V3<T> a, c;
+    ld3(d, oCom + 3 * p, a);
+    ld3(d, oCom + 3 * b, c);
+    st3(d, oCom + 3 * p, a + c);
+  }
+  for (int b = 0; b < nbody; ++b) {
+    V3<T> s, ip;
+    ld3(d, oCom + 3 * b, s);
+    const T ms = body_submass[b];
+    if (ms < T(MJT_MINVAL)) {
+      ld3(d, oXipos + 3 * b, ip);
+      s = ip;
+    } else {
+      const T dm = t_max(ms, T(MJT_MINVAL));
+      s = V3<T>(s.x / dm, s.y / dm, s.z / dm);
+    }
+    st3(d, oCom + 3 * b, s);
+  }
+  for (int b = 0; b < nbody; ++b) {
+    V3<T> ip, rc;
+    ld3(d, oXipos + 3 * b, ip);
+    ld3(d, oCom + 3 * body_root[b], rc);
+    const V3<T> off = ip - rc;
+    T R[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) R[k] = d.get(oXimat + 9 * b + k);
+    const T* I3 = m.F(F_body_inertia) + 3 * b;
+    const T ms = body_mass[b];
+    // inert = R diag(I) R^T + m (|o|^2 E - o o^T)
+    T in6[6];
+    const int ti[6] = {0, 1, 2, 0, 0, 1}, tj[6] = {0, 1, 2, 1, 2, 2};
+    const T o[3] = {off.x, off.y, off.z};
+    const T oo = dot(off, off);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const int a = ti[k], c = tj[k];
+      T v = R[3 * a] * I3[0] * R[3 * c] + R[3 * a + 1] * I3[1] * R[3 * c + 1] + R[3 * a + 2] * I3[2] * R[3 * c + 2];
+      v += ((a == c ? oo : T(0)) - o[a] * o[c]) * ms;
+      in6[k] = v;
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) d.set(oCinert + 10 * b + k, in6[k]);
+    d.set(oCinert + 10 * b + 6, off.x * ms); d.set(oCinert + 10 * b + 7, off.y * ms); d.set(oCinert + 10 * b + 8, off.z * ms);
+    d.set(oCinert + 10 * b + 9, ms);
+  }
+  for (int j = 0; j < njnt; ++j) {
+    const int jt = jnt_type[j], da = jnt_dofadr[j], b = jnt_bodyid[j];
+    V3<T> rc, an;
+    ld3(d, oCom + 3 * body_root[b], rc);
+    ld3(d, oAnchor + 3 * j, an);
+    const V3<T> off = rc - an;
+    if (jt == JNT_FREE || jt == JNT_BALL) {
+      int base = da;
+      if (jt == JNT_FREE) {
+        for (int k = 0; k < 3; ++k)
+          for (int c = 0; c < 6; ++c) d.set(oCdof + 6 * (da + k) + c, (c == 3 + k) ? T(1) : T(0));
+        base = da + 3;
+      }
+      for (int k = 0; k < 3; ++k) {  // body axes = columns of xmat
+        V3<T> a(d.get(oXmat + 9 * b + k), d.get(oXmat + 9 * b + 3 + k), d.get(oXmat + 9 * b + 6 + k));
+        st3(d, oCdof + 6 * (base + k), a);
+        st3(d, oCdof + 6 * (base + k) + 3, cross(a, off));
+      }
+    } else if (jt == JNT_HINGE) {
+      V3<T> a;
+      ld3(d, oAxis + 3 * j, a);
+      st3(d, oCdof + 6 * da, a);
+      st3(d, oCdof + 6 * da + 3, cross(a, off));
+    } else {
+      V3<T> a;
+      ld3(d, oAxis + 3 * j, a);
+      st3(d, oCdof + 6 * da, V3<T>(0, 0, 0));
+      st3(d, oCdof + 6 * da + 3, a);
+    }
+  }
+
+  // ---- tendon (smooth.py:470-497), fixed tendons only
+  if (ntendon) {
+    const int oL = m.D(D_ten_length), oJ = m.D(D_ten_J);
+    for (int t = 0; t < ntendon; ++t) {
+      for (int i = 0; i < nv; ++i) d.set(oJ + t * nv + i, T(0));
+      T len = 0;
+      for (int w = m.I(I_ten_adr)[t], we = w + m.I(I_ten_num)[t]; w < we; ++w) {
+        const int j = m.I(I_wrap_jnt)[w];
+        if (j < 0) continue;
+        const T c = m.F(F_wrap_prm)[w];
+        len += c * d.get(oQpos + jnt_qposadr[j]);
+        d.set(oJ + t * nv + jnt_dofadr[j], c);
+      }
+      d.set(oL + t, len);
+    }
+  }
+
+  // ---- crb + dense M (smooth.py:291-308, support.make_m :50-69)
+  for (int b = 0; b < nbody; ++b)
+    for (int k = 0; k < 10; ++k) d.set(oCrb + 10 * b + k, d.get(oCinert + 10 * b + k));
+  for (int b = nbody - 1; b > 0; --b) {
+    const int p = body_parent[b];
+    for (int k = 0; k < 10; ++k) d.set(oCrb + 10 * p + k, d.get(oCrb + 10 * p + k) + d.get(oCrb + 10 * b + k));
+  }
+  for (int k = 0; k < 10; ++k) d.set(oCrb + k, T(0));
+  for (int i = 0; i < nv * nv; ++i) d.set(oM + i, T(0));
+  for (int i = 0; i < nv; ++i) {
+    T c[10], v[6], f[6];
+    const int b = dof_bodyid[i];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) c[k] = d.get(oCrb + 10 * b + k);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) v[k] = d.get(oCdof + 6 * i + k);
+    inert_mul(c, v, f);
+    for (int j = i; j >= 0; j = dof_parent[j]) {
+      T s = 0;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) s += f[k] * d.get(oCdof + 6 * j + k);
+      if (j == i) s += m.F(F_dof_armature)[i];
+      d.set(oM + i * nv + j, s);
+      d.set(oM + j * nv + i, s);
+    }
+  }
+  // tendon_armature (smooth.py:500-521): M += J^T diag(armature) J
+  if (ntendon) {
+    const int oJ = m.D(D_ten_J);
+    for (int t = 0; t < ntendon; ++t) {
+      const T arm = m.F(F_ten_armature)[t];
+      if (arm == T(0)) continue;
+      for (int i = 0; i < nv; ++i) {
+        const T ji = d.get(oJ + t * nv + i);
+        if (ji == T(0)) continue;
+        for (int j = 0; j < nv; ++j) d.set(oM + i * nv + j, d.get(oM + i * nv + j) + ji * arm * d.get(oJ + t * nv + j));
+      }
+    }
+  }
+
+  // ---- transmission (smooth.py:535-591) and actuator_velocity (forward.py:87-95)
+  const int oAlen = m.D(D_actuator_length), oAmom = m.D(D_actuator_moment), oAvel = m.D(D_actuator_velocity);
+  for (int u = 0; u < nu; ++u) {
+    const int trn = m.I(I_act_trntype)[u], id = m.I(I_act_trnid)[u];
+    const T* gear = m.F(F_act_gear) + 6 * u;
+    for (int i = 0; i < nv; ++i) d.set(oAmom + u * nv + i, T(0));
+    T len = 0, vel = 0;
+    if (trn == TRN_TENDON) {
+      len = d.get(m.D(D_ten_length) + id) * gear[0];
+      for (int i = 0; i < nv; ++i) {
+        const T mm = d.get(m.D(D_ten_J) + id * nv + i) * gear[0];
+        d.set(oAmom + u * nv + i, mm);
+        vel += mm * d.get(oQvel + i);
+      }
+    } else {
+      const int jt = jnt_type[id], da = jnt_dofadr[id], qa = jnt_qposadr[id];
+      if (jt == JNT_FREE) {
+        T g6[6] = {gear[0], gear[1], gear[2], gear[3], gear[4], gear[5]};
+        if (trn == TRN_JOINTINPARENT) {
+          Q4<T> q(d.get(oQpos + qa + 3), d.get(oQpos + qa + 4), d.get(oQpos + qa + 5), d.get(oQpos + qa + 6));
+          V3<T> ga = qrot(V3<T>(gear[3], gear[4], gear[5]), qconj(q));
+          g6[3] = ga.x; g6[4] = ga.y; g6[5] = ga.z;
+        }
+        for (int k = 0; k < 6; ++k) { d.set(oAmom + u * nv + da + k, g6[k]); vel += g6[k] * d.get(oQvel + da + k); }
+      } else if (jt == JNT_BALL) {
+        Q4<T> q(d.get(oQpos + qa), d.get(oQpos + qa + 1), d.get(oQpos + qa + 2), d.get(oQpos + qa + 3));
+        V3<T> ga(gear[0], gear[1], gear[2]);
+        if (trn == TRN_JOINTINPARENT) ga = qrot(ga, qconj(q));
+        len = dot(q2axisangle(q), ga);
+        d.set(oAmom + u * nv + da, ga.x); d.set(oAmom + u * nv + da + 1, ga.y); d.set(oAmom + u * nv + da + 2, ga.z);
+        vel = ga.x * d.get(oQvel + da) + ga.y * d.get(oQvel + da + 1) + ga.z * d.get(oQvel + da + 2);
+      } else {
+        len = d.get(oQpos + qa) * gear[0];
+        d.set(oAmom + u * nv + da, gear[0]);
+        vel = gear[0] * d.get(oQvel + da);
+      }
+    }
+    d.set(oAlen + u, len);
+    d.set(oAvel + u, vel);
+  }
+  if (ntendon) {
+    for (int t = 0; t < ntendon; ++t) {
+      T v = 0;
+      for (int i = 0; i < nv; ++i) v += d.get(m.D(D_ten_J) + t * nv + i) * d.get(oQvel + i);
+      d.set(m.D(D_ten_velocity) + t, v);
+    }
+  }
+
+  // ---- com_vel (smooth.py:385-424)
+  for (int k = 0; k < 6; ++k) d.set(oCvel + k, T(0));
+  for (int b = 1; b < nbody; ++b) {
+    T v[6];
+    const int p = body_parent[b];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) v[k] = d.get(oCvel + 6 * p + k);
+    for (int j = body_jntadr[b], je = j + body_jntnum[b]; j < je; ++j) {
+      const int jt = jnt_type[j], da = jnt_dofadr[j];
+      int first = da, cnt = (jt == JNT_BALL) ? 3 : 1;
+      if (jt == JNT_FREE) {
+        for (int k = 0; k < 3; ++k) {
+          const T qv = d.get(oQvel + da + k);
+          for (int c = 0; c < 6; ++c) {
+            v[c] += d.get(oCdof + 6 * (da + k) + c) * qv;
+            d.set(oCdofdot + 6 * (da + k) + c, T(0));
+          }
+        }
+        first = da + 3;
+        cnt = 3;
+      }
+      T cd[3][6];
+      for (int k = 0; k < cnt; ++k) {
+        T out[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) cd[k][c] = d.get(oCdof + 6 * (first + k) + c);
+        motion_cross(v, cd[k], out);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) d.set(oCdofdot + 6 * (first + k) + c, out[c]);
+      }
+      for (int k = 0; k < cnt; ++k) {
+        const T qv = d.get(oQvel + first + k);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) v[c] += cd[k][c] * qv;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) d.set(oCvel + 6 * b + k, v[k]);
+  }
+
+  // ---- passive (passive.py:80-200)
+  const int oPassive = m.D(D_qfrc_passive), oGravcomp = m.D(D_qfrc_gravcomp);
+  for (int i = 0; i < nv; ++i) { d.set(oPassive + i, T(0)); d.set(oGravcomp + i, T(0)); }
+  if (!(flags & (DSBL_SPRING | DSBL_DAMPER))) {
+    if (!(flags & DSBL_SPRING)) {
+      const T* qs = m.F(F_qpos_spring);
+      for (int j = 0; j < njnt; ++j) {
+        const int jt = jnt_type[j], qa = jnt_qposadr[j], da = jnt_dofadr[j];
+        const T k = m.F(F_jnt_stiffness)[j];
+        if (jt == JNT_FREE || jt == JNT_BALL) {
+          int qq = qa, dd = da;
+          if (jt == JNT_FREE) {
+            for (int c = 0; c < 3; ++c) d.set(oPassive + da + c, -k * (d.get(oQpos + qa + c) - qs[qa + c]));
+            qq = qa + 3;
+            dd = da + 3;
+          }
+          Q4<T> q(d.get(oQpos + qq), d.get(oQpos + qq + 1), d.get(oQpos + qq + 2), d.get(oQpos + qq + 3));
+          Q4<T> s(qs[qq], qs[qq + 1], qs[qq + 2], qs[qq + 3]);
+          V3<T> r = q2axisangle(qmul(qconj(s), q));  // quat_sub(q, s)
+          d.set(oPassive + dd, -k * r.x); d.set(oPassive + dd + 1, -k * r.y); d.set(oPassive + dd + 2, -k * r.z);
+        } else {
+          d.set(oPassive + da, -k * (d.get(oQpos + qa) - qs[qa]));
+        }
+      }
+    }
+    if (!(flags & DSBL_DAMPER))
+      for (int i = 0; i < nv; ++i) d.set(oPassive + i, d.get(oPassive + i) - m.F(F_dof_damping)[i] * d.get(oQvel + i));
+    for (int t = 0; t < ntendon; ++t) {
+      T frc = 0;
+      const T len = d.get(m.D(D_ten_length) + t);
+      if (!(flags & DSBL_SPRING)) {
+        const T below = m.F(F_ten_lengthspring)[2 * t] - len, above = m.F(F_ten_lengthspring)[2 * t + 1] - len;
+        const T ks = m.F(F_ten_stiffness)[t];
+        if (below > T(0)) frc = ks * below;
+        if (above < T(0)) frc = ks * above;
+      }
+      if (!(flags & DSBL_DAMPER)) frc += -m.F(F_ten_damping)[t] * d.get(m.D(D_ten_velocity) + t);
+      for (int i = 0; i < nv; ++i) d.set(oPassive + i, d.get(oPassive + i) + d.get(m.D(D_ten_J) + t * nv + i) * frc);
+    }
+    // gravity compensation (passive.py:148-155,187-189)
+    if (m.h(H_has_gravcomp) && !(flags & DSBL_GRAVITY)) {
+      for (int b = 1; b < nbody; ++b) {
+        const T gc = m.F(F_body_gravcomp)[b] * body_mass[b];
+        if (gc == T(0)) continue;
+        const V3<T> force(-m.opt(OPT_gravity0) * gc, -m.opt(OPT_gravity1) * gc, -m.opt(OPT_gravity2) * gc);
+        V3<T> pt, rc;
+        ld3(d, oXipos + 3 * b, pt);
+        ld3(d, oCom + 3 * body_root[b], rc);
+        const V3<T> off = pt - rc;
+        for_ancestor_dofs(m, b, [&](int i) {
+          V3<T> a, l;
+          ld3(d, oCdof + 6 * i, a);
+          ld3(d, oCdof + 6 * i + 3, l);
+          d.set(oGravcomp + i, d.get(oGravcomp + i) + dot(l + cross(a, off), force));
+        });
+      }
+      for (int i = 0; i < nv; ++i) {
+        const T agc = T(m.I(I_jnt_actgravcomp)[m.I(I_dof_jntid)[i]]);
+        d.set(oPassive + i, d.get(oPassive + i) + d.get(oGravcomp + i) * (T(1) - agc));
+      }
+    }
+  }
+
+  // ---- rne (smooth.py:427-467)
+  const int oCacc = m.D(D_scr_cacc), oCfrc = m.D(D_scr_cfrc), oBias = m.D(D_qfrc_bias);
+  {
+    const bool nograv = flags & DSBL_GRAVITY;
+    d.set(oCacc, T(0)); d.set(oCacc + 1, T(0)); d.set(oCacc + 2, T(0));
+    d.set(oCacc + 3, nograv ? T(0) : -m.opt(OPT_gravity0));
+    d.set(oCacc + 4, nograv ? T(0) : -m.opt(OPT_gravity1));
+    d.set(oCacc + 5, nograv ? T(0) : -m.opt(OPT_gravity2));
+  }
+  for (int b = 0; b < nbody; ++b) {
+    T a[6], ci[10], cv[6], f1[6], f2[6], f3v[6];
+    if (b > 0) {
+      const int p = body_parent[b];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) a[k] = d.get(oCacc + 6 * p + k);
+      for (int i = body_dofadr[b], ie = i + body_dofnum[b]; i < ie; ++i) {
+        const T qv = d.get(oQvel + i);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) a[k] += d.get(oCdofdot + 6 * i + k) * qv;
+      }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) d.set(oCacc + 6 * b + k, a[k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) a[k] = d.get(oCacc + k);
+    }
+#pragma unroll
+    for (int k = 0; k < 10; ++k) ci[k] = d.get(oCinert + 10 * b + k);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) cv[k] = d.get(oCvel + 6 * b + k);
+    inert_mul(ci, a, f1);
+    inert_mul(ci, cv, f2);
+    motion_cross_force(cv, f2, f3v);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) d.set(oCfrc + 6 * b + k, f1[k] + f3v[k]);
+  }
+  for (int b = nbody - 1; b > 0; --b) {
+    const int p = body_parent[b];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) d.set(oCfrc + 6 * p + k, d.get(oCfrc + 6 * p + k) + d.get(oCfrc + 6 * b + k));
+  }
+  for (int i = 0; i < nv; ++i) {
+    const int b = dof_bodyid[i];
+    T s = 0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) s += d.get(oCdof + 6 * i + k) * d.get(oCfrc + 6 * b + k);
+    d.set(oBias + i, s);
+  }
+
+  // ---- actuation (forward.py:102-219)
+  const int oAct = m.D(D_act), oActdot = m.D(D_act_dot), oQfa = m.D(D_qfrc_actuator), oForce = m.D(D_actuator_force);
+  for (int i = 0; i < nv; ++i) d.set(oQfa + i, T(0));
+  for (int i = 0; i < na; ++i) d.set(oActdot + i, T(0));
+  if (nu && !(flags & DSBL_ACTUATION)) {
+    for (int u = 0; u < nu; ++u) {
+      T ctrl = in_get<T>(in.ctrl, B, env, u);
+      if (!(flags & DSBL_CLAMPCTRL) && m.I(I_act_ctrllimited)[u])
+        ctrl = t_min(t_max(ctrl, m.F(F_act_ctrlrange)[2 * u]), m.F(F_act_ctrlrange)[2 * u + 1]);
+      T ctrl_act = ctrl;
+      const int adr = m.I(I_act_actadr)[u];
+      if (adr >= 0) {
+        const int dyn = m.I(I_act_dyntype)[u];
+        const T* prm = m.F(F_act_dynprm) + 10 * u;
+        const T act = d.get(oAct + adr);
+        T ad = 0;
+        if (dyn == DYN_INTEGRATOR) ad = ctrl;
+        else if (dyn == DYN_FILTER || dyn == DYN_FILTEREXACT) ad = (ctrl - act) / t_max(prm[0], T(MJT_MINVAL));
+        else if (dyn == DYN_MUSCLE) {
+          // support.muscle_dynamics :217-228
+          const T cc = t_clamp(ctrl, T(0), T(1)), ac = t_clamp(act, T(0), T(1));
+          const T tau_act = prm[0] * (T(0.5) + T(1.5) * ac), tau_deact = prm[1] / (T(0.5) + T(1.5) * ac);
+          const T dctrl = cc - act;
+          T tau;
+          if (prm[2] < T(MJT_MINVAL)) tau = dctrl > T(0) ? tau_act : tau_deact;
+          else {
+            T x = dctrl / (prm[2] + (prm[2] == T(0) ? T(MJT_MINVAL) : T(0))) + T(0.5);
+            T sg = x * x * x * (T(3) * x * (T(2) * x - T(5)) + T(10));
+            if (x <= T(0)) sg = T(0);
+            if (x >= T(1)) sg = T(1);
+            tau = tau_deact + (tau_act - tau_deact) * sg;
+          }
+          ad = dctrl / t_max(tau, T(MJT_MINVAL));
+        }
+        d.set(oActdot + adr, ad);
+        ctrl_act = d.get(oAct + adr + m.I(I_act_actnum)[u] - 1);
+      }
+      const int gt = m.I(I_act_gaintype)[u], bt = m.I(I_act_biastype)[u];
+      const T* gp = m.F(F_act_gainprm) + 10 * u;
+      const T* bp = m.F(F_act_biasprm) + 10 * u;
+      const T len = d.get(oAlen + u), vel = d.get(oAvel + u);
+      T gain = gp[0], bias = 0;
+      if (gt == GAIN_AFFINE) gain = gp[0] + gp[1] * len + gp[2] * vel;
+      // TODO(muscle gain/bias): refused at device_put
+      if (bt == BIAS_AFFINE) bias = bp[0] + bp[1] * len + bp[2] * vel;
+      T force = gain * ctrl_act + bias;
+      if (m.I(I_act_forcelimited)[u]) force = t_min(t_max(force, m.F(F_act_forcerange)[2 * u]), m.F(F_act_forcerange)[2 * u + 1]);
+      d.set(oForce + u, force);
+      if (force != T(0))
+        for (int i = 0; i < nv; ++i) {
+          const T mm = d.get(oAmom + u * nv + i);
+          if (mm != T(0)) d.set(oQfa + i, d.get(oQfa + i) + mm * force);
+        }
+    }
+    for (int i = 0; i < nv; ++i) {
+      const int j = m.I(I_dof_jntid)[i];
+      T q = d.get(oQfa + i);
+      if (m.h(H_has_gravcomp)) q += d.get(oGravcomp + i) * T(m.I(I_jnt_actgravcomp)[j]);
+      if (m.I(I_jnt_actfrclimited)[j]) q = t_min(t_max(q, m.F(F_jnt_actfrcrange)[2 * j]), m.F(F_jnt_actfrcrange)[2 * j + 1]);
+      d.set(oQfa + i, q);
+    }
+  } else {
+    for (int u = 0; u < nu; ++u) d.set(oForce + u, T(0));
+  }
+
+  // ---- qfrc_smooth (forward.py:222-228; qacc_smooth is solved in k_solve where M is factorised)
+  const int oSmooth = m.D(D_qfrc_smooth);
+  for (int i = 0; i < nv; ++i)
+    d.set(oSmooth + i, d.get(oPassive + i) - d.get(oBias + i) + d.get(oQfa + i) + in_get<T>(in.qfrc_applied, B, env, i));
+  for (int b = 1; b < nbody; ++b) {  // support.xfrc_accumulate :184-194 (exact zeros skipped)
+    T x[6];
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { x[k] = in_get<T>(in.xfrc_applied, B, env, 6 * b + k); any |= (x[k] != T(0)); }
+    if (!any) continue;
+    V3<T> pt, rc;
+    ld3(d, oXipos + 3 * b, pt);
+    ld3(d, oCom + 3 * body_root[b], rc);
+    const V3<T> off = pt - rc, force(x[0], x[1], x[2]), torque(x[3], x[4], x[5]);
+    for_ancestor_dofs(m, b, [&](int i) {
+      V3<T> a, l;
+      ld3(d, oCdof + 6 * i, a);
+      ld3(d, oCdof + 6 * i + 3, l);
+      d.set(oSmooth + i, d.get(oSmooth + i) + dot(l + cross(a, off), force) + dot(a, torque));
+    });
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) k_smooth(const int* __restrict__ gblob, int blob_words, MjtIn in, T* __restrict__ out, int B) {
+  extern __shared__ __align__(16) int smem_blob[];
+  __shared__ uint64_t bar;
+  stage_blob(smem_blob, &bar, gblob, blob_words);
+  const ModelView<T> m = make_view<T>(smem_blob);
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= B) return;
+  EnvBuf<T> d{out + env, (size_t)B};
+  smooth_env<T>(m, in, d, (size_t)B, env);
+}

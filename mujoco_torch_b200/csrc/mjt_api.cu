@@ -1,0 +1,270 @@
+// C ABI of libmjt_b200 (see include/mjt.h): model upload and kernel sequencing for step / forward.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/mjt.h"
+#include "k_collision.cuh"
+#include "k_constraint.cuh"
+#include "k_convex.cuh"
+#include "k_sensor.cuh"
+#include "k_smooth.cuh"
+#include "k_solve.cuh"
+#include "mjt_common.cuh"
+
+static thread_local std::string g_err;
+
+static int fail(const std::string& msg) {
+  g_err = msg;
+  return 1;
+}
+#define CUDA_OK(expr)                                                                            \
+  do {                                                                                           \
+    cudaError_t e__ = (expr);                                                                    \
+    if (e__ != cudaSuccess) return fail(std::string(#expr) + ": " + cudaGetErrorString(e__));    \
+  } while (0)
+
+struct mjtModel {
+  int device;
+  int* d_blob;
+  std::vector<int> h;  // host copy of the blob
+  int blob_words;
+  bool f64;
+  int sm_count;
+  int max_smem;
+  int solve_envs;  // envs (warps) per CTA in k_solve
+  size_t solve_smem;
+  int hv(int k) const { return h[k]; }
+};
+
+static const char* kFieldNames[] = {
+
+    "qpos", "qvel", "act", "time", "qacc", "qacc_warmstart", "act_dot", "xpos", "xquat", "xmat", "xipos", "ximat", "xanchor", "xaxis",
+    "geom_xpos", "geom_xmat", "site_xpos", "site_xmat", "subtree_com", "cinert", "crb", "cdof", "cdof_dot", "cvel", "qM", "qLD",
+    "ten_length", "ten_J", "ten_velocity", "actuator_length", "actuator_moment", "actuator_velocity", "actuator_force", "qfrc_bias",
+    "qfrc_passive", "qfrc_gravcomp", "qfrc_actuator", "qfrc_smooth", "qacc_smooth", "qfrc_constraint", "contact_dist", "contact_pos",
+    "contact_frame", "efc_J", "efc_D", "efc_aref", "efc_frictionloss", "efc_force", "sensordata", "scr_cacc", "scr_cfrc"
+
+};
+static_assert(sizeof(kFieldNames) / sizeof(kFieldNames[0]) == NUM_D, "field name table out of sync with mjt_layout.h");
+
+extern "C" int mjt_version(void) { return 1000; }
+extern "C" const char* mjt_last_error(void) { return g_err.c_str(); }
+
+extern "C" int mjt_model_create(const void* blob_host, size_t nbytes, int device, mjtModel** out) {
+  if (!blob_host || !out || nbytes < MJT_HDR_WORDS * 4) return fail("mjt_model_create: bad arguments");
+  const int* w = static_cast<const int*>(blob_host);
+  if ((unsigned)w[H_magic] != MJT_MAGIC) return fail("mjt_model_create: bad blob magic (layout mismatch?)");
+  if ((size_t)w[H_blob_words] * 4 != nbytes) return fail("mjt_model_create: blob size mismatch");
+  CUDA_OK(cudaSetDevice(device));
+  mjtModel* m = new mjtModel();
+  m->device = device;
+  m->blob_words = w[H_blob_words];
+  m->h.assign(w, w + m->blob_words);
+  m->f64 = w[H_is_f64] != 0;
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  m->sm_count = prop.multiProcessorCount;
+  m->max_smem = (int)prop.sharedMemPerBlockOptin;
+  CUDA_OK(cudaMalloc(&m->d_blob, nbytes));
+  CUDA_OK(cudaMemcpy(m->d_blob, blob_host, nbytes, cudaMemcpyHostToDevice));
+  // k_solve shared-memory budget: blob + E per-env regions; pick the E in {8,4,2,1} that maximises resident warps per SM
+  const int nv = w[H_nv], nefc = w[H_nefc];
+  const size_t tsz = m->f64 ? 8 : 4;
+  const size_t region = (size_t)solve_layout(nv, nefc).words * tsz;
+  const size_t blob_b = ((size_t)m->blob_words + 3) / 4 * 16;
+  const size_t sm_total = (size_t)prop.sharedMemPerMultiprocessor;
+  int best_e = 0;
+  size_t best_warps = 0;
+  for (int e = 8; e >= 1; e >>= 1) {
+    const size_t need = blob_b + region * e + 1024;
+    if (need > (size_t)m->max_smem) continue;
+    size_t ctas = sm_total / need;
+    if (ctas > 32) ctas = 32;
+    size_t warps = ctas * e;
+    if (warps > 64) warps = 64;
+    if (warps > best_warps) { best_warps = warps; best_e = e; }
+  }
+  if (best_e == 0) {
+    delete m;
+    return fail("mjt_model_create: model too large for the shared-memory solver tile (nv * nefc)");
+  }
+  m->solve_envs = best_e;
+  m->solve_smem = blob_b + region * best_e;
+  if (blob_b + 64 > (size_t)m->max_smem) {
+    delete m;
+    return fail("mjt_model_create: model blob exceeds shared memory");
+  }
+  *out = m;
+  return 0;
+}
+
+extern "C" void mjt_model_destroy(mjtModel* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  cudaFree(m->d_blob);
+  delete m;
+}
+
+extern "C" int mjt_model_data_words(const mjtModel* m) { return m->hv(H_data_words); }
+extern "C" int mjt_model_dtype_size(const mjtModel* m) { return m->f64 ? 8 : 4; }
+extern "C" int mjt_model_scratch_words(const mjtModel* m) {
+  if (m->hv(H_integrator) != INT_RK4) return 0;
+  return m->hv(H_data_words) + m->hv(H_nq) + 3 * m->hv(H_nv) + 2 * m->hv(H_na) + 1;
+}
+extern "C" int mjt_model_field(const mjtModel* m, const char* name, int* offset, int* words) {
+  for (int k = 0; k < NUM_D; ++k)
+    if (strcmp(name, kFieldNames[k]) == 0) {
+      if (offset) *offset = m->hv(MJT_OFF_D + k);
+      if (words) *words = m->hv(MJT_OFF_DSZ + k);
+      return 0;
+    }
+  return -1;
+}
+
+static MjtIn to_in(const mjtStateIn* s) {
+  MjtIn in;
+  in.qpos = s->qpos; in.qvel = s->qvel; in.act = s->act; in.time = s->time; in.qacc = s->qacc; in.qacc_warmstart = s->qacc_warmstart;
+  in.ctrl = s->ctrl; in.qfrc_applied = s->qfrc_applied; in.xfrc_applied = s->xfrc_applied; in.mocap_pos = s->mocap_pos;
+  in.mocap_quat = s->mocap_quat; in.sensordata = s->sensordata; in.qfrc_constraint = s->qfrc_constraint; in.eq_active = s->eq_active;
+  return in;
+}
+
+template <typename T>
+static int set_smem(const void* fn, size_t bytes) {
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return fail(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+  }
+  return 0;
+}
+
+// one forward pass (optionally followed by the in-kernel integrator) into `out`
+template <typename T>
+static int run_forward(const mjtModel* m, const MjtIn& in, T* out, int B, int mode, cudaStream_t st, int* launches) {
+  const int threads = 128;
+  const int gx = (B + threads - 1) / threads;
+  const size_t blob_b = ((size_t)m->blob_words + 3) / 4 * 16;
+  const int nsens = m->hv(H_nsensordata);
+  int n = 0;
+  if (set_smem<T>((const void*)k_smooth<T>, blob_b)) return 1;
+  k_smooth<T><<<gx, threads, blob_b, st>>>(m->d_blob, m->blob_words, in, out, B);
+  ++n;
+  if (m->hv(H_npair_cand) > 0) {
+    if (set_smem<T>((const void*)k_collision<T>, blob_b)) return 1;
+    dim3 grid(gx, m->hv(H_npair_cand) < 65535 ? m->hv(H_npair_cand) : 65535);
+    k_collision<T><<<grid, threads, blob_b, st>>>(m->d_blob, m->blob_words, out, B);
+    ++n;
+  }
+  if (m->hv(H_nsrc) > 0) {
+    if (set_smem<T>((const void*)k_constraint<T>, blob_b)) return 1;
+    dim3 grid(gx, m->hv(H_nsrc) < 65535 ? m->hv(H_nsrc) : 65535);
+    k_constraint<T><<<grid, threads, blob_b, st>>>(m->d_blob, m->blob_words, in, out, B);
+    ++n;
+  }
+  if (nsens > 0) {
+    if (set_smem<T>((const void*)k_sensor<T>, blob_b)) return 1;
+    k_sensor<T><<<gx, threads, blob_b, st>>>(m->d_blob, m->blob_words, in, out, B, (1 << 1) | (1 << 2));
+    ++n;
+  }
+  {
+    const int E = m->solve_envs;
+    const int gs = (B + E - 1) / E;
+    if (m->hv(H_nv) <= 32) {
+      if (set_smem<T>((const void*)k_solve<T, 1>, m->solve_smem)) return 1;
+      k_solve<T, 1><<<gs, 32 * E, m->solve_smem, st>>>(m->d_blob, m->blob_words, in, out, B, mode);
+    } else if (m->hv(H_nv) <= 64) {
+      if (set_smem<T>((const void*)k_solve<T, 2>, m->solve_smem)) return 1;
+      k_solve<T, 2><<<gs, 32 * E, m->solve_smem, st>>>(m->d_blob, m->blob_words, in, out, B, mode);
+    } else {
+      return fail("mjt: nv > 64 not supported by the dense solver kernel");
+    }
+    ++n;
+  }
+  // acc-stage sensors run only when the solver ran (reference forward.py:390-401 returns early when nefc == 0)
+  if (nsens > 0 && m->hv(H_nsens_acc) > 0 && m->hv(H_nefc) > 0) {
+    k_sensor<T><<<gx, threads, blob_b, st>>>(m->d_blob, m->blob_words, in, out, B, 1 << 3);
+    ++n;
+  }
+  if (launches) *launches = n;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(std::string("kernel launch: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+template <typename T>
+static int run_step(const mjtModel* m, const MjtIn& in, T* out, T* scratch, int B, cudaStream_t st, int* launches) {
+  int total = 0, n = 0;
+  if (m->hv(H_integrator) != INT_RK4) {
+    if (run_forward<T>(m, in, out, B, MJT_MODE_STEP, st, &n)) return 1;
+    if (launches) *launches = n;
+    return 0;
+  }
+  if (!scratch) return fail("mjt_step: RK4 needs a scratch buffer (mjt_model_scratch_words)");
+  const int threads = 128, gx = (B + threads - 1) / threads;
+  const size_t blob_b = ((size_t)m->blob_words + 3) / 4 * 16;
+  const int nq = m->hv(H_nq), nv = m->hv(H_nv), na = m->hv(H_na);
+  T* stage_buf = scratch;
+  T* tail = scratch + (size_t)m->hv(H_data_words) * B;
+  if (set_smem<T>((const void*)k_rk4_stage<T>, blob_b)) return 1;
+  if (run_forward<T>(m, in, out, B, MJT_MODE_FORWARD, st, &n)) return 1;
+  total += n;
+  T* prev = out;
+  for (int i = 0; i < 3; ++i) {
+    k_rk4_stage<T><<<gx, threads, blob_b, st>>>(m->d_blob, m->blob_words, out, prev, tail, B, i);
+    ++total;
+    MjtIn sin = in;
+    sin.qpos = tail;
+    sin.qvel = tail + (size_t)nq * B;
+    sin.act = tail + (size_t)(nq + nv) * B;
+    sin.time = tail + (size_t)(nq + nv + na) * B;
+    // warm start carried from the previous stage's solution (the running Data of the reference's loop)
+    sin.qacc_warmstart = prev + (size_t)m->hv(MJT_OFF_D + D_qacc_warmstart) * B;
+    sin.sensordata = prev + (size_t)m->hv(MJT_OFF_D + D_sensordata) * B;
+    if (run_forward<T>(m, sin, stage_buf, B, MJT_MODE_FORWARD, st, &n)) return 1;
+    total += n;
+    prev = stage_buf;
+  }
+  k_rk4_stage<T><<<gx, threads, blob_b, st>>>(m->d_blob, m->blob_words, out, prev, tail, B, 3);
+  ++total;
+  if (launches) *launches = total;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(std::string("kernel launch: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+static int check_args(const mjtModel* m, const mjtStateIn* in, void* out, int nenv) {
+  if (!m || !in || !out) return fail("mjt: null argument");
+  if (nenv <= 0) return fail("mjt: nenv must be positive");
+  cudaError_t e = cudaSetDevice(m->device);
+  if (e != cudaSuccess) return fail(std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int mjt_step(const mjtModel* m, const mjtStateIn* in, void* out, void* scratch, int nenv, void* stream) {
+  if (check_args(m, in, out, nenv)) return 1;
+  const MjtIn i = to_in(in);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return m->f64 ? run_step<double>(m, i, (double*)out, (double*)scratch, nenv, st, nullptr)
+                : run_step<float>(m, i, (float*)out, (float*)scratch, nenv, st, nullptr);
+}
+
+extern "C" int mjt_forward(const mjtModel* m, const mjtStateIn* in, void* out, int nenv, void* stream) {
+  if (check_args(m, in, out, nenv)) return 1;
+  const MjtIn i = to_in(in);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return m->f64 ? run_forward<double>(m, i, (double*)out, nenv, MJT_MODE_FORWARD, st, nullptr)
+                : run_forward<float>(m, i, (float*)out, nenv, MJT_MODE_FORWARD, st, nullptr);
+}
+
+extern "C" int mjt_step_launches(const mjtModel* m) {
+  int per_forward = 2;  // k_smooth + k_solve
+  if (m->hv(H_npair_cand) > 0) ++per_forward;
+  if (m->hv(H_nsrc) > 0) ++per_forward;
+  if (m->hv(H_nsensordata) > 0) ++per_forward;
+  if (m->hv(H_nsensordata) > 0 && m->hv(H_nsens_acc) > 0 && m->hv(H_nefc) > 0) ++per_forward;
+  return m->hv(H_integrator) == INT_RK4 ? 4 * per_forward + 4 : per_forward;
+}

@@ -1,0 +1,81 @@
+"""Shared helpers for the parity tests: seeded inputs and oracle / CUDA runners."""
+
+import os
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MODELS = os.path.join(ROOT, "assets", "models")
+
+
+def load_model(name, **opt_overrides):
+    from mujoco_torch_b200.mjmodel import MjModelLite
+
+    mj = MjModelLite.load_npz(os.path.join(MODELS, name + ".npz"))
+    for k, v in opt_overrides.items():
+        setattr(mj.opt, k, v)
+    return mj
+
+
+def seeded_state(mj, B, seed=42, qpos_noise=0.05, qvel_scale=0.5, drop=0.0, ctrl=True):
+    """Synthetic initial states: qpos0 + U(-s, s), qvel ~ N(0, scale^2), ctrl ~ U(-1, 1); root height lowered by
+    U(0, drop) for free-root models so contacts are active in a good fraction of envs."""
+    rng = np.random.RandomState(seed)
+    qpos = np.tile(np.asarray(mj.qpos0), (B, 1)) + rng.uniform(-qpos_noise, qpos_noise, size=(B, mj.nq))
+    qvel = qvel_scale * rng.randn(B, mj.nv)
+    c = rng.uniform(-1, 1, size=(B, mj.nu)) if ctrl else np.zeros((B, mj.nu))
+    if drop > 0:
+        if mj.njnt and int(mj.jnt_type[0]) == 0:
+            qpos[:, 2] -= rng.uniform(0, drop, size=B)
+        else:
+            qpos[:, min(1, mj.nq - 1)] -= rng.uniform(0, drop, size=B)
+    return qpos, qvel, c
+
+
+def run_oracle(mj, qpos, qvel, ctrl, dtype=torch.float64, nsteps=1, warm=None):
+    from oracle import forward as of
+    from oracle import model as om
+
+    m = om.OModel(mj, dtype)
+    d = of.make_data(m, qpos.shape[0])
+    d.qpos, d.qvel, d.ctrl = (torch.as_tensor(x).to(dtype) for x in (qpos, qvel, ctrl))
+    if warm is not None:
+        d.qacc_warmstart = torch.as_tensor(warm).to(dtype)
+    for _ in range(nsteps):
+        d = of.step(m, d)
+    return m, d
+
+
+def run_cuda(mj, qpos, qvel, ctrl, dtype=torch.float64, nsteps=1, warm=None, device="cuda:0"):
+    import mujoco_torch_b200 as mt
+
+    mx = mt.device_put(mj, dtype=dtype).to(device)
+    d = mt.make_data(mx).expand(qpos.shape[0]).clone()
+    kw = dict(qpos=torch.as_tensor(qpos, device=device).to(dtype), qvel=torch.as_tensor(qvel, device=device).to(dtype),
+              ctrl=torch.as_tensor(ctrl, device=device).to(dtype))
+    if warm is not None:
+        kw["qacc_warmstart"] = torch.as_tensor(warm, device=device).to(dtype)
+    d = d.replace(**kw)
+    for _ in range(nsteps):
+        d = mt.step(mx, d)
+    torch.cuda.synchronize()
+    return mx, d
+
+
+def rel_err(a, b):
+    """max |a-b| / max(|b|, tiny) over the whole field (field-scale relative error)."""
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    if a.numel() == 0:
+        return 0.0
+    return float((a - b).abs().max() / max(float(b.abs().max()), 1e-12))
+
+
+ORACLE_FIELD = {"contact_dist": "contact.dist", "contact_pos": "contact.pos", "contact_frame": "contact.frame"}
+
+
+def get(d, name):
+    obj = d
+    for part in name.split("."):
+        obj = getattr(obj, part)
+    return obj
