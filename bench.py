@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the batched physics step (BASELINE.json metric), one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--model humanoid] [--batch 65536] [--dtype f64]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference          # the CPU arm: the oracle port timed on the host cores
+
+Workload (config.workload): Humanoid (the reference's humanoid.xml: Newton, 1 iteration / 4 line-search iterations,
+Euler, eulerdamp disabled -- the configuration the reference's README numbers are quoted on), batch 65 536 per GPU,
+float64 like every published reference number.  A step = one `step(mx, d)` over the whole batch.
+`value` is measured with the state resident in HBM; `e2e` runs the same step through the public API from pinned
+host buffers (H2D of the state + ctrl, step, D2H of qpos/qvel/qacc_warmstart) inside the timed region.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+PUBLISHED = {("humanoid", "f64", 65536): 2333178.0}  # H200, compile tuned (reference README.md:190)
+RESET_NOISE = {"humanoid": 0.01, "ant": 0.1, "ant_zoo": 0.1, "halfcheetah": 0.1}
+# minimal state I/O words per env-step: read qpos,qvel,ctrl,warmstart,time(+act); write qpos,qvel,qacc,warmstart,time(+act)
+
+
+def algorithmic_bytes(mj, tsize):
+    rd = mj.nq + mj.nv + mj.nu + mj.nv + 1 + mj.na
+    wr = mj.nq + mj.nv + mj.nv + mj.nv + 1 + mj.na + mj.nsensordata
+    return (rd + wr) * tsize
+
+
+def load_model(name, args):
+    from mujoco_torch_b200.mjmodel import MjModelLite
+
+    mj = MjModelLite.load_npz(os.path.join(ROOT, "assets", "models", name + ".npz"))
+    if args.integrator is not None:
+        mj.opt.integrator = {"euler": 0, "rk4": 1, "implicitfast": 3}[args.integrator]
+    if args.solver is not None:
+        mj.opt.solver = {"cg": 1, "newton": 2}[args.solver]
+    if args.cone is not None:
+        mj.opt.cone = {"pyramidal": 0, "elliptic": 1}[args.cone]
+    return mj
+
+
+def initial_state(mj, name, B, seed):
+    """Synthetic randomised initial states: qpos0 + U(-s, s), qvel = 0.01 N(0,1); half of the envs of
+    free-root models start lowered so that contacts are active from the first step."""
+    rng = np.random.RandomState(seed)
+    s = RESET_NOISE.get(name, 0.05)
+    qpos = np.tile(np.asarray(mj.qpos0), (B, 1)) + rng.uniform(-s, s, size=(B, mj.nq))
+    qvel = 0.01 * rng.randn(B, mj.nv)
+    if mj.njnt and int(mj.jnt_type[0]) == 0:
+        drop = rng.uniform(0.0, 0.35, size=B) * (rng.rand(B) < 0.5)
+        qpos[:, 2] -= drop
+    ctrl = rng.uniform(-1, 1, size=(4, B, mj.nu))
+    return qpos, qvel, ctrl
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_rate(mj, name, B, nsteps, threads):
+    """CPU arm: the oracle port (float64 batched torch on the host cores)."""
+    from oracle import forward as of
+    from oracle import model as om
+
+    torch.set_num_threads(threads)
+    m = om.OModel(mj, torch.float64)
+    qpos, qvel, ctrl = initial_state(mj, name, B, 42)
+    d = of.make_data(m, B)
+    d.qpos, d.qvel = torch.as_tensor(qpos), torch.as_tensor(qvel)
+    d.ctrl = torch.as_tensor(ctrl[0])
+    d = of.step(m, d)  # warm-up
+    t0 = time.perf_counter()
+    for i in range(nsteps):
+        d.ctrl = torch.as_tensor(ctrl[i % 4])
+        d = of.step(m, d)
+    dt = time.perf_counter() - t0
+    return B * nsteps / dt, dt / nsteps
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's own implementation cannot be imported here (mujoco / tensordict are not
+    installed), so this arm times the oracle port with all host threads on a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    mj = load_model(args.model, args)
+    cores = os.cpu_count() or 1
+    B = args.cpu_batch
+    rates, per = [], []
+    for _ in range(max(1, args.warmup // 3)):
+        oracle_rate(mj, args.model, B, 1, cores)
+    for _ in range(max(1, min(args.steps, 3))):
+        r, ms = oracle_rate(mj, args.model, B, 2, cores)
+        rates.append(r)
+        per.append(ms)
+    v = float(np.median(rates))
+    sample = f"oracle port, B={B} envs x 2 steps per sample, {len(rates)} samples, {cores} torch threads, float64"
+    print(json.dumps({
+        "impl": "reference", "metric": "env-steps/sec", "value": v, "unit": "env-steps/s", "n_gpus": 0, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": float(np.median(per)) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args, mj), "batch": B},
+        "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_name(args, mj):
+    integ = {0: "Euler", 1: "RK4", 3: "ImplicitFast"}[int(mj.opt.integrator)]
+    solver = {1: "CG", 2: "Newton"}[int(mj.opt.solver)]
+    cone = {0: "pyramidal", 1: "elliptic"}[int(mj.opt.cone)]
+    return (f"{args.model} (nv={mj.nv}), {solver} it={int(mj.opt.iterations)}/ls={int(mj.opt.ls_iterations)}, {cone} cone, {integ}, "
+            f"dt={float(mj.opt.timestep)}, batch {args.batch}/GPU")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="humanoid")
+    ap.add_argument("--batch", type=int, default=65536)
+    ap.add_argument("--dtype", default="f64", choices=["f32", "f64"])
+    ap.add_argument("--integrator", default=None, choices=["euler", "rk4", "implicitfast"])
+    ap.add_argument("--solver", default=None, choices=["cg", "newton"])
+    ap.add_argument("--cone", default=None, choices=["pyramidal", "elliptic"])
+    ap.add_argument("--cpu-batch", type=int, default=2048)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import mujoco_torch_b200 as mt
+    from mujoco_torch_b200 import ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = world > 1
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if dist:
+        import torch.distributed as td
+
+        td.init_process_group("nccl", device_id=dev)
+
+    dtype = torch.float64 if args.dtype == "f64" else torch.float32
+    tsize = 8 if args.dtype == "f64" else 4
+    mj = load_model(args.model, args)
+    B = args.batch
+    mx = mt.device_put(mj, dtype=dtype).to(dev)
+    qpos, qvel, ctrl = initial_state(mj, args.model, B, 42 + rank)  # seeds offset by rank: the union is one big batch
+    d0 = mt.make_data(mx).expand(B).clone()
+    d0 = d0.replace(qpos=torch.as_tensor(qpos, device=dev).to(dtype), qvel=torch.as_tensor(qvel, device=dev).to(dtype))
+    ctrls = [torch.as_tensor(c, device=dev).to(dtype).t().contiguous().t() for c in ctrl]  # env-minor resident ctrl
+
+    def barrier():
+        if dist:
+            td.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput
+    d = d0
+    for i in range(args.warmup):
+        d = mt.step(mx, d.replace(ctrl=ctrls[i % 4]))
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        d = mt.step(mx, d.replace(ctrl=ctrls[i % 4]))
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    finite = bool(torch.isfinite(d.qpos).all())
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if dist:
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * B * args.steps / (ms_max * 1e-3)
+
+    # ---- per-kernel device timing for the roofline (same state, a few extra steps)
+    ops.profile_begin()
+    nprof = min(20, args.steps)
+    for i in range(nprof):
+        d = mt.step(mx, d.replace(ctrl=ctrls[i % 4]))
+    prof = ops.profile_end()
+    kern = {k: v[0] / v[1] for k, v in prof.items()}
+    per_step = {k: v[0] / nprof for k, v in prof.items()}
+    top = max(per_step, key=per_step.get)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    abytes = algorithmic_bytes(mj, tsize) * B
+    ach = abytes / (per_step[top] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
+                "algorithmic_bytes_per_env_step": algorithmic_bytes(mj, tsize),
+                "kernel_ms_per_step": per_step, "kernel_share": {k: v / sum(per_step.values()) for k, v in per_step.items()}}
+
+    # ---- end to end through the public API from pinned host buffers
+    e2e = None
+    if not args.no_e2e:
+        keys_in = ("qpos", "qvel", "qacc_warmstart", "ctrl")
+        keys_out = ("qpos", "qvel", "qacc_warmstart")
+        host = {k: getattr(d, k).detach().cpu().contiguous().pin_memory() for k in keys_in}
+        base = d
+        nb_in = sum(host[k].numel() * host[k].element_size() for k in keys_in)
+        nb_out = sum(host[k].numel() * host[k].element_size() for k in keys_out)
+
+        def e2e_step():
+            dev_in = {k: host[k].to(dev, non_blocking=True) for k in keys_in}
+            out = mt.step(mx, base.replace(**dev_in))
+            for k in keys_out:
+                host[k].copy_(getattr(out, k), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        n_e2e = max(5, min(args.steps, 30))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        barrier()
+        el = time.perf_counter() - t0
+        te = torch.tensor([el], device=dev, dtype=torch.float64)
+        if dist:
+            td.all_reduce(te, op=td.ReduceOp.MAX)
+        e2e = {"value": world * B * n_e2e / float(te.item()), "unit": "env-steps/s", "h2d_bytes_per_step": nb_in,
+               "d2h_bytes_per_step": nb_out, "steps": n_e2e}
+
+    if rank != 0:
+        if dist:
+            td.destroy_process_group()
+        return
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        v, sec = oracle_rate(mj, args.model, args.cpu_batch, 3, cores)
+        cpu = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
+               "sample": f"oracle port (float64 batched torch), B={args.cpu_batch} envs x 3 steps, {cores} threads"}
+
+    pub = PUBLISHED.get((args.model, args.dtype, B)) if int(mj.opt.integrator) == 0 and args.solver is None else None
+    launches = ops.lib().mjt_step_launches(ops.model_handle(mx)) * args.steps
+    line = {
+        "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": (value / pub / world) if pub else None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": workload_name(args, mj), "batch_per_gpu": B, "parallelism": f"dp{world} (envs sharded, no collective)",
+                   "l2": f"per-step working set {mx.data_words * B * tsize / 1e6:.0f} MB > 126 MB L2 (inputs larger than L2)",
+                   "nv": mj.nv, "ncon": mx.ncon, "nefc": mx.nefc},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "finite": finite,
+        "published_baseline": {"value": pub, "hardware": "H200 f64 torch.compile(vmap) tuned, reference README.md:190"} if pub else None,
+    }
+    print(json.dumps(line))
+    if dist:
+        td.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

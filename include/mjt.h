@@ -77,6 +77,14 @@ int mjt_forward(const mjtModel* m, const mjtStateIn* in, void* out, int nenv, vo
 /* Number of kernel launches mjt_step issues for this model (used by bench.py's gpu_launches claim). */
 int mjt_step_launches(const mjtModel* m);
 
+/* Per-kernel device timing for the roofline report: between begin/end every kernel launched by the calling thread is
+ * bracketed by CUDA events on its stream; end() synchronises and writes "name:total_ms:launches;..." into buf. */
+void mjt_profile_begin(void);
+int mjt_profile_end(char* buf, size_t nbuf);
+
+/* Launch configuration of the solver kernel (environments = warps per CTA, dynamic shared memory bytes). */
+int mjt_solve_config(const mjtModel* m, int* envs_per_cta, int* smem_bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -449,6 +449,52 @@ __device__ void smooth_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<
     }
   }
 
+  // ---- fluid forces, inertia-box model (passive.py:30-77,158-173)
+  if (m.h(H_has_fluid) && !(flags & (DSBL_SPRING | DSBL_DAMPER))) {
+    const T density = m.opt(OPT_density), viscosity = m.opt(OPT_viscosity);
+    const V3<T> wind(m.opt(OPT_wind0), m.opt(OPT_wind1), m.opt(OPT_wind2));
+    const T pi = T(3.14159265358979323846);
+    for (int b = 1; b < nbody; ++b) {
+      const T ms = body_mass[b];
+      if (!(ms > T(0))) continue;
+      const T* I3 = m.F(F_body_inertia) + 3 * b;
+      T box[3];
+      box[0] = I3[1] + I3[2] - I3[0]; box[1] = I3[0] + I3[2] - I3[1]; box[2] = I3[0] + I3[1] - I3[2];
+      for (int k = 0; k < 3; ++k) box[k] = t_sqrt(T(6) * t_max(box[k], T(1e-12)) / t_max(ms, T(1e-12)));
+      T R[9], cv[6];
+      for (int k = 0; k < 9; ++k) R[k] = d.get(oXimat + 9 * b + k);
+      for (int k = 0; k < 6; ++k) cv[k] = d.get(oCvel + 6 * b + k);
+      V3<T> ip, rc;
+      ld3(d, oXipos + 3 * b, ip);
+      ld3(d, oCom + 3 * body_root[b], rc);
+      const V3<T> off = ip - rc;
+      // transform_motion (math.py:437-452): local = R^T (lin - off x ang), R^T ang
+      const V3<T> ang(cv[0], cv[1], cv[2]), lin0 = V3<T>(cv[3], cv[4], cv[5]) - cross(off, ang);
+      auto rt = [&](const V3<T>& v) { return V3<T>(R[0] * v.x + R[3] * v.y + R[6] * v.z, R[1] * v.x + R[4] * v.y + R[7] * v.z,
+                                                    R[2] * v.x + R[5] * v.y + R[8] * v.z); };
+      auto rr = [&](const V3<T>& v) { return V3<T>(R[0] * v.x + R[1] * v.y + R[2] * v.z, R[3] * v.x + R[4] * v.y + R[5] * v.z,
+                                                    R[6] * v.x + R[7] * v.y + R[8] * v.z); };
+      const V3<T> la = rt(ang), ll = rt(lin0) - rt(wind);
+      const T diam = (box[0] + box[1] + box[2]) / T(3);
+      const T lav[3] = {la.x, la.y, la.z}, llv[3] = {ll.x, ll.y, ll.z};
+      const T sv[3] = {box[1] * box[2], box[0] * box[2], box[0] * box[1]};
+      const T b4[3] = {box[0] * box[0] * box[0] * box[0], box[1] * box[1] * box[1] * box[1], box[2] * box[2] * box[2] * box[2]};
+      const T sa[3] = {box[0] * (b4[1] + b4[2]), box[1] * (b4[0] + b4[2]), box[2] * (b4[0] + b4[1])};
+      T fa[3], fv[3];
+      for (int k = 0; k < 3; ++k) {
+        fa[k] = lav[k] * -pi * diam * diam * diam * viscosity - (T(1) * density * sa[k] * t_abs(lav[k]) * lav[k] / T(64));
+        fv[k] = llv[k] * T(-3) * pi * diam * viscosity - T(0.5) * density * sv[k] * t_abs(llv[k]) * llv[k];
+      }
+      const V3<T> force = rr(V3<T>(fv[0], fv[1], fv[2])), torque = rr(V3<T>(fa[0], fa[1], fa[2]));
+      for_ancestor_dofs(m, b, [&](int i) {
+        V3<T> a, l;
+        ld3(d, oCdof + 6 * i, a);
+        ld3(d, oCdof + 6 * i + 3, l);
+        d.set(oPassive + i, d.get(oPassive + i) + dot(l + cross(a, off), force) + dot(a, torque));
+      });
+    }
+  }
+
   // ---- rne (smooth.py:427-467)
   const int oCacc = m.D(D_scr_cacc), oCfrc = m.D(D_scr_cfrc), oBias = m.D(D_qfrc_bias);
   {

@@ -4,35 +4,39 @@
 // re-factorisations (forward.py:313-328, 404-416; derivative.py:22-68) and _advance (forward.py:255-310).
 //
 // Mapping: lane i owns dof i (and i+32 when nv > 32): every nv-vector (qacc, Ma, grad, search ...) lives in
-// registers, one element per lane; dot products and costs are warp-shuffle reductions.  The per-env matrices
-// (J, M, and one factor workspace) live in shared memory with odd leading dimensions (bank-conflict-free row
-// and column walks).  Because a warp == an environment, every data-dependent branch (active rows, line-search
-// bracketing, early exit) is warp-uniform: inactive constraint rows and converged envs cost nothing, which is
-// exactly the per-env early exit the reference's masked while_loop emulates.
+// registers, one element per lane; dot products and costs are warp-shuffle reductions.  Per-env matrices live in
+// shared memory: M and one factor workspace as packed lower triangles, and the constraint Jacobian COMPACTED to
+// each row's static column support (the dofs a contact / limit can touch), which is 3x smaller than dense J for
+// Humanoid and is what lets 16 f64 envs share one SM.  The Newton Hessian M + J^T D J is assembled only over active
+// rows and only over their support (rank-k updates of the packed triangle).  Because a warp == an environment,
+// every data-dependent branch (active rows, line-search bracketing, early exit) is warp-uniform: inactive rows and
+// converged envs cost nothing -- the per-env early exit the reference's masked while_loop emulates.
 #pragma once
 #include "mjt_common.cuh"
 #include "k_smooth.cuh"
 
 struct SolveLayout {
-  int ldj, ldm, oJ, oM, oL, oXs, oD, oAref, oFloss, oJaref, oJv, oForce, oAct, words;
+  int nP, oJ, oM, oL, oDinv, oXs, oYs, oD, oAref, oFloss, oJaref, oJv, oForce, oMask, nchunk, words;
 };
 
-__host__ __device__ inline SolveLayout solve_layout(int nv, int nefc) {
+__host__ __device__ inline SolveLayout solve_layout(int nv, int nefc, int jc_words, int nf) {
   SolveLayout s;
-  s.ldj = nv | 1;
-  s.ldm = nv | 1;
+  s.nP = nv * (nv + 1) / 2;
+  s.nchunk = (nefc + 31) / 32;
   int o = 0;
-  s.oJ = o; o += nefc * s.ldj;
-  s.oM = o; o += nv * s.ldm;
-  s.oL = o; o += nv * s.ldm;
-  s.oXs = o; o += nv + 1;
+  s.oJ = o; o += jc_words;
+  s.oM = o; o += s.nP;
+  s.oL = o; o += s.nP;
+  s.oDinv = o; o += nv;
+  s.oXs = o; o += nv;
+  s.oYs = o; o += nv;
   s.oD = o; o += nefc;
   s.oAref = o; o += nefc;
-  s.oFloss = o; o += nefc;
+  s.oFloss = o; o += nf > 0 ? nefc : 0;
   s.oJaref = o; o += nefc;
   s.oJv = o; o += nefc;
   s.oForce = o; o += nefc;
-  s.oAct = o; o += nefc;  // active flags / compacted active indices (stored as T-sized ints)
+  s.oMask = o; o += 2 * s.nchunk;  // active-row and nonzero-force bitmasks (uint32 each, stored in T-sized slots)
   s.words = (o + 3) & ~3;
   return s;
 }
@@ -42,7 +46,6 @@ struct Vec {
   T v[DPL];
 };
 
-// DPL-indexed shuffle helper needs a compile-time register index; specialise the access.
 template <typename T>
 __device__ __forceinline__ T vec_bcast(const Vec<T, 1>& x, int i) { return __shfl_sync(0xffffffffu, x.v[0], i & 31); }
 template <typename T>
@@ -51,17 +54,31 @@ __device__ __forceinline__ T vec_bcast(const Vec<T, 2>& x, int i) {
   return (i >> 5) ? b : a;
 }
 
+__device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
+
 template <typename T, int DPL>
 struct SolveCtx {
   const ModelView<T>& m;
   T* s;  // this env's shared-memory region
   SolveLayout L;
   int nv, nefc, lane;
+  const int* row_src;
+  const int* row_jadr;
+  const int* src_nsup;
+  const int* src_cadr;
+  const int* src_row;
+  const int* src_nrows;
+  const int* sup_col;
 
-  __device__ __forceinline__ T* J() const { return s + L.oJ; }
-  __device__ __forceinline__ T* Mx() const { return s + L.oM; }
-  __device__ __forceinline__ T* Lx() const { return s + L.oL; }
+  __device__ __forceinline__ T* Jc() const { return s + L.oJ; }
+  __device__ __forceinline__ T* Mp() const { return s + L.oM; }
+  __device__ __forceinline__ T* Lp() const { return s + L.oL; }
+  __device__ __forceinline__ T* dinv() const { return s + L.oDinv; }
   __device__ __forceinline__ T* xs() const { return s + L.oXs; }
+  __device__ __forceinline__ T* ys() const { return s + L.oYs; }
+  __device__ __forceinline__ unsigned* amask() const { return reinterpret_cast<unsigned*>(s + L.oMask); }
+  __device__ __forceinline__ unsigned* fmask() const { return reinterpret_cast<unsigned*>(s + L.oMask) + L.nchunk; }
+  __device__ __forceinline__ bool row_active(int r) const { return (amask()[r >> 5] >> (r & 31)) & 1u; }
 
   __device__ __forceinline__ Vec<T, DPL> zero() const {
     Vec<T, DPL> r;
@@ -84,110 +101,171 @@ struct SolveCtx {
     }
     __syncwarp();
   }
-  // y = A x for a dense (nv x nv) shared-memory matrix
-  __device__ __forceinline__ Vec<T, DPL> matvec(const T* A, const Vec<T, DPL>& x) const {
+  // y = A x for a symmetric matrix stored as a packed lower triangle
+  __device__ __forceinline__ Vec<T, DPL> symv(const T* A, const Vec<T, DPL>& x) const {
     to_smem(x, xs());
     Vec<T, DPL> y = zero();
-    for (int c = 0; c < nv; ++c) {
-      const T xc = xs()[c];
 #pragma unroll
-      for (int k = 0; k < DPL; ++k) {
-        const int i = lane + 32 * k;
-        if (i < nv) y.v[k] += A[i * L.ldm + c] * xc;
+    for (int k = 0; k < DPL; ++k) {
+      const int i = lane + 32 * k;
+      if (i < nv) {
+        const T* row = A + tri(i);
+        T acc = 0;
+        for (int c = 0; c <= i; ++c) acc += row[c] * xs()[c];
+        for (int c = i + 1; c < nv; ++c) acc += A[tri(c) + i] * xs()[c];
+        y.v[k] = acc;
       }
     }
     return y;
   }
-  // out[r] = J[r,:] . x  (+ optional subtraction of sub[r])
+  // out[r] = J[r,:] . x (- sub[r])   over each row's compact support
   __device__ __forceinline__ void jmul(const Vec<T, DPL>& x, T* out, const T* sub) const {
     to_smem(x, xs());
     for (int r = lane; r < nefc; r += 32) {
-      const T* row = J() + r * L.ldj;
+      const int sidx = row_src[r];
+      const int ns = src_nsup[sidx];
+      const int* col = sup_col + src_cadr[sidx];
+      const T* jr = Jc() + row_jadr[r];
       T acc = 0;
-      for (int c = 0; c < nv; ++c) acc += row[c] * xs()[c];
+      for (int k = 0; k < ns; ++k) acc += jr[k] * xs()[col[k]];
       out[r] = sub ? acc - sub[r] : acc;
     }
     __syncwarp();
   }
-  // y = J^T f  (f in shared memory; zero entries skipped, warp-uniformly)
+  // y = J^T f over rows whose force is non-zero (bitmask fmask), scattered through shared memory
   __device__ __forceinline__ Vec<T, DPL> jtmul(const T* f) const {
-    Vec<T, DPL> y = zero();
-    for (int r = 0; r < nefc; ++r) {
-      const T fr = f[r];
-      if (fr == T(0)) continue;
-#pragma unroll
-      for (int k = 0; k < DPL; ++k) {
-        const int i = lane + 32 * k;
-        if (i < nv) y.v[k] += J()[r * L.ldj + i] * fr;
+    T* y = ys();
+    for (int i = lane; i < nv; i += 32) y[i] = T(0);
+    __syncwarp();
+    for (int c = 0; c < L.nchunk; ++c) {
+      unsigned mk = fmask()[c];
+      while (mk) {
+        const int r = (c << 5) + __ffs(mk) - 1;
+        mk &= mk - 1;
+        const int sidx = row_src[r];
+        const int ns = src_nsup[sidx];
+        const int* col = sup_col + src_cadr[sidx];
+        const T* jr = Jc() + row_jadr[r];
+        const T fr = f[r];
+        for (int k = lane; k < ns; k += 32) y[col[k]] += jr[k] * fr;
+        __syncwarp();
       }
     }
-    return y;
+    Vec<T, DPL> out;
+#pragma unroll
+    for (int k = 0; k < DPL; ++k) { const int i = lane + 32 * k; out.v[k] = i < nv ? y[i] : T(0); }
+    return out;
   }
-  // In-place dense Cholesky of the lower triangle of A (n x n, ld = ldm); upper triangle zeroed.
+  // In-place Cholesky of a packed lower triangle; reciprocal pivots go to dinv().
   // Numeric conventions of reference math.small_cholesky :87-129: n <= 16 clamps each pivot at 1e-12,
   // n > 16 adds 1e-10 to the diagonal (the torch.linalg.cholesky fallback path).
   __device__ __forceinline__ void cholesky(T* A) const {
-    const int n = nv, ld = L.ldm;
+    const int n = nv;
     const bool big = n > 16;
+    T* di = dinv();
     for (int j = 0; j < n; ++j) {
-      T p = 0;
-      for (int k = lane; k < j; k += 32) { const T l = A[j * ld + k]; p += l * l; }
-      T sdiag = A[j * ld + j] + (big ? T(1e-10) : T(0)) - warp_sum(p);
-      if (!big) sdiag = t_max(sdiag, T(1e-12));
-      const T ljj = t_sqrt(sdiag);
-      for (int i = j + 1 + lane; i < n; i += 32) {
-        T t = A[i * ld + j];
-        for (int k = 0; k < j; ++k) t -= A[i * ld + k] * A[j * ld + k];
-        A[i * ld + j] = t / ljj;
-        A[j * ld + i] = T(0);
+      const T* rowj = A + tri(j);
+      T t[DPL];
+#pragma unroll
+      for (int p = 0; p < DPL; ++p) {
+        const int i = j + lane + 32 * p;
+        t[p] = T(0);
+        if (i < n) {
+          const T* rowi = A + tri(i);
+          T acc = rowi[j];
+          for (int k = 0; k < j; ++k) acc -= rowi[k] * rowj[k];
+          t[p] = acc;
+        }
       }
-      if (lane == 0) A[j * ld + j] = ljj;
+      T sdiag = __shfl_sync(0xffffffffu, t[0], 0);
+      if (big) sdiag += T(1e-10); else sdiag = t_max(sdiag, T(1e-12));
+      const T ljj = t_sqrt(sdiag);
+      const T inv = T(1) / ljj;
+      __syncwarp();
+#pragma unroll
+      for (int p = 0; p < DPL; ++p) {
+        const int i = j + lane + 32 * p;
+        if (i < n) A[tri(i) + j] = (i == j) ? ljj : t[p] * inv;
+      }
+      if (lane == 0) di[j] = inv;
       __syncwarp();
     }
   }
   // x <- (L L^T)^-1 x with x distributed one element per lane (reference small_cholesky_solve :132-168)
   __device__ __forceinline__ Vec<T, DPL> cho_solve(const T* Lm, Vec<T, DPL> x) const {
-    const int n = nv, ld = L.ldm;
+    const int n = nv;
+    const T* di = dinv();
     for (int i = 0; i < n; ++i) {
-      const T xi = vec_bcast(x, i) / Lm[i * ld + i];
+      const T xi = vec_bcast(x, i) * di[i];
 #pragma unroll
       for (int k = 0; k < DPL; ++k) {
         const int j = lane + 32 * k;
         if (j == i) x.v[k] = xi;
-        else if (j > i && j < n) x.v[k] -= Lm[j * ld + i] * xi;
+        else if (j > i && j < n) x.v[k] -= Lm[tri(j) + i] * xi;
       }
     }
     for (int i = n - 1; i >= 0; --i) {
-      const T xi = vec_bcast(x, i) / Lm[i * ld + i];
+      const T xi = vec_bcast(x, i) * di[i];
+      const T* rowi = Lm + tri(i);
 #pragma unroll
       for (int k = 0; k < DPL; ++k) {
         const int j = lane + 32 * k;
         if (j == i) x.v[k] = xi;
-        else if (j < i) x.v[k] -= Lm[i * ld + j] * xi;
+        else if (j < i) x.v[k] -= rowi[j] * xi;
       }
     }
     return x;
   }
+  // Lp <- Mp + sum over active rows r of D_r J_r^T J_r, source by source over the packed support pairs
+  __device__ __forceinline__ void hessian(const T* D) const {
+    T* H = Lp();
+    const T* M0 = Mp();
+    for (int p = lane; p < L.nP; p += 32) H[p] = M0[p];
+    __syncwarp();
+    const int nsrc = m.h(H_nsrc);
+    for (int sidx = 0; sidx < nsrc; ++sidx) {
+      const int r0 = src_row[sidx], nr = src_nrows[sidx];
+      bool any = false;
+      for (int e = 0; e < nr; ++e) any |= row_active(r0 + e);
+      if (!any) continue;
+      const int ns = src_nsup[sidx];
+      const int* col = sup_col + src_cadr[sidx];
+      const int npair = (ns * (ns + 1)) >> 1;
+      for (int p = lane; p < npair; p += 32) {
+        int a = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
+        while (tri(a + 1) <= p) ++a;
+        while (tri(a) > p) --a;
+        const int b = p - tri(a);
+        T acc = 0;
+        for (int e = 0; e < nr; ++e) {
+          const int r = r0 + e;
+          if (!row_active(r)) continue;
+          const T* jr = Jc() + row_jadr[r];
+          acc += D[r] * jr[a] * jr[b];
+        }
+        H[tri(col[a]) + col[b]] += acc;  // support columns are sorted ascending: col[a] >= col[b]
+      }
+      __syncwarp();
+    }
+  }
 };
 
 template <typename T, int DPL>
-__device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T>& d, size_t B, int env, T* sm, int mode) {
+__device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T>& d, size_t B, int env,
+                          SolveCtx<T, DPL>& c, const Vec<T, DPL>& qfrc_smooth, const Vec<T, DPL>& qacc_smooth, int mode) {
   typedef Vec<T, DPL> V;
-  const int lane = threadIdx.x & 31;
-  const int nv = m.h(H_nv), nefc = m.h(H_nefc), flags = m.h(H_disableflags);
-  SolveCtx<T, DPL> c{m, sm, solve_layout(nv, nefc), nv, nefc, lane};
+  const int lane = c.lane;
+  const int nv = c.nv, nefc = c.nefc, flags = m.h(H_disableflags);
   const SolveLayout& Lo = c.L;
-  T* const Jm = c.J();
-  T* const Mm = c.Mx();
-  T* const Lm = c.Lx();
+  T* const sm = c.s;
+  T* const Mm = c.Mp();
+  T* const Lm = c.Lp();
   T* const D = sm + Lo.oD;
   T* const aref = sm + Lo.oAref;
   T* const floss = sm + Lo.oFloss;
   T* const Jaref = sm + Lo.oJaref;
   T* const jv = sm + Lo.oJv;
   T* const force = sm + Lo.oForce;
-  T* const actf = sm + Lo.oAct;
-  const int ld = Lo.ldm;
 
   auto loadv = [&](int off) {
     V r;
@@ -199,7 +277,7 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
 #pragma unroll
     for (int k = 0; k < DPL; ++k) { const int i = lane + 32 * k; if (i < nv) d.set(off + i, x.v[k]); }
   };
-  auto axpy = [&](const V& a, T s, const V& b) {  // a + s*b
+  auto axpy = [&](const V& a, T s, const V& b) {
     V r;
 #pragma unroll
     for (int k = 0; k < DPL; ++k) r.v[k] = a.v[k] + s * b.v[k];
@@ -212,26 +290,11 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
     return r;
   };
 
-  // ---- factor_m + qacc_smooth
-  for (int idx = lane; idx < nv * nv; idx += 32) {
-    const int i = idx / nv, j = idx - i * nv;
-    Lm[i * ld + j] = Mm[i * ld + j];
-  }
-  __syncwarp();
-  c.cholesky(Lm);
-  for (int idx = lane; idx < nv * nv; idx += 32) {
-    const int i = idx / nv, j = idx - i * nv;
-    d.set(m.D(D_qLD) + idx, Lm[i * ld + j]);
-  }
-  const V qfrc_smooth = loadv(m.D(D_qfrc_smooth));
-  const V qacc_smooth = c.cho_solve(Lm, qfrc_smooth);
-  storev(m.D(D_qacc_smooth), qacc_smooth);
-
   V qacc = qacc_smooth;
   V qfrc_con = c.zero();
 
   if (nefc == 0) {
-    // forward.py:390-396; qfrc_constraint keeps the caller's value (solve() never runs)
+    // forward.py:390-396: solve() never runs; qfrc_constraint and qacc_warmstart keep the caller's values
 #pragma unroll
     for (int k = 0; k < DPL; ++k) {
       const int i = lane + 32 * k;
@@ -251,28 +314,35 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
     V Ma, grad, Mgrad, search;
     T gauss = 0, cost = t_inf<T>(), prev_cost = 0;
 
-    // reference _update_constraint :320-357
-    auto update_constraint = [&]() {
+    // reference _update_constraint :320-357 (cost only, or cost + forces + J^T f)
+    auto update_constraint = [&](bool with_force) {
       T cpart = 0;
-      for (int r = lane; r < nefc; r += 32) {
-        const T ja = Jaref[r], dr = D[r];
-        bool act = (ja < T(0)) || (r < ne_nf);
-        T ff = 0;
-        if (use_floss) {
-          const T fl = floss[r];
-          if (fl > T(0)) {
-            const T rr = T(1) / (dr + (dr == T(0) ? T(MJT_MINVAL) : T(0)));
-            const bool lin_neg = ja <= -rr * fl, lin_pos = ja >= rr * fl;
-            if (lin_neg) { act = false; ff = fl; cpart += -T(0.5) * rr * fl * fl - fl * ja; }
-            if (lin_pos) { act = false; ff = -fl; cpart += -T(0.5) * rr * fl * fl + fl * ja; }
+      for (int ch = 0; ch < Lo.nchunk; ++ch) {
+        const int r = (ch << 5) + lane;
+        bool act = false;
+        T fo = 0;
+        if (r < nefc) {
+          const T ja = Jaref[r], dr = D[r];
+          act = (ja < T(0)) || (r < ne_nf);
+          T ff = 0;
+          if (use_floss) {
+            const T fl = floss[r];
+            if (fl > T(0)) {
+              const T rr = T(1) / (dr + (dr == T(0) ? T(MJT_MINVAL) : T(0)));
+              const bool lin_neg = ja <= -rr * fl, lin_pos = ja >= rr * fl;
+              if (lin_neg) { act = false; ff = fl; cpart += -T(0.5) * rr * fl * fl - fl * ja; }
+              if (lin_pos) { act = false; ff = -fl; cpart += -T(0.5) * rr * fl * fl + fl * ja; }
+            }
           }
+          fo = (act ? dr * -ja : T(0)) + ff;
+          if (act) cpart += T(0.5) * dr * ja * ja;
+          if (with_force) force[r] = fo;
         }
-        force[r] = (act ? dr * -ja : T(0)) + ff;
-        actf[r] = act ? T(1) : T(0);
-        if (act) cpart += T(0.5) * dr * ja * ja;
+        const unsigned am = __ballot_sync(0xffffffffu, act), fm = __ballot_sync(0xffffffffu, fo != T(0));
+        if (with_force && lane == 0) { c.amask()[ch] = am; c.fmask()[ch] = fm; }
       }
       __syncwarp();
-      qfrc_con = c.jtmul(force);
+      if (with_force) qfrc_con = c.jtmul(force);
       T g = 0;
 #pragma unroll
       for (int k = 0; k < DPL; ++k) g += (Ma.v[k] - qfrc_smooth.v[k]) * (qacc.v[k] - qacc_smooth.v[k]);
@@ -281,54 +351,24 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
       cost = warp_sum(cpart) + gauss;
     };
 
-    // reference _update_gradient :359-376
-    auto update_gradient = [&]() {
+    auto compute_grad = [&]() {
 #pragma unroll
       for (int k = 0; k < DPL; ++k) grad.v[k] = Ma.v[k] - qfrc_smooth.v[k] - qfrc_con.v[k];
-      if (!newton) {
-        Mgrad = c.cho_solve(Lm, grad);  // Lm still holds chol(M)
-        return;
-      }
-      // H = M + J^T diag(D * active) J, accumulated per lane-owned row in registers, structural zeros skipped
-      for (int col = 0; col < nv; ++col) {
-        T acc[DPL];
-#pragma unroll
-        for (int k = 0; k < DPL; ++k) { const int i = lane + 32 * k; acc[k] = i < nv ? Mm[i * ld + col] : T(0); }
-        for (int r = 0; r < nefc; ++r) {
-          if (actf[r] == T(0)) continue;
-          const T jrc = Jm[r * Lo.ldj + col];
-          if (jrc == T(0)) continue;
-          const T w = D[r] * jrc;
-#pragma unroll
-          for (int k = 0; k < DPL; ++k) { const int i = lane + 32 * k; if (i < nv) acc[k] += Jm[r * Lo.ldj + i] * w; }
-        }
-#pragma unroll
-        for (int k = 0; k < DPL; ++k) { const int i = lane + 32 * k; if (i < nv) Lm[i * ld + col] = acc[k]; }
-      }
-      __syncwarp();
-      c.cholesky(Lm);
-      Mgrad = c.cho_solve(Lm, grad);
     };
-
-    // reference _create_context :293-318
-    auto create_context = [&](const V& q, bool grad_flag) {
-      qacc = q;
-      c.jmul(qacc, Jaref, aref);
-      Ma = c.matvec(Mm, qacc);
-      cost = t_inf<T>();
-      prev_cost = 0;
-      update_constraint();
-      if (grad_flag) {
-        update_gradient();
-        search = neg(Mgrad);
+    // reference _update_gradient :359-376 (the M^-1 / H^-1 application)
+    auto compute_mgrad = [&]() {
+      if (newton) {
+        c.hessian(D);
+        c.cholesky(Lm);
       }
+      Mgrad = c.cho_solve(Lm, grad);  // CG: Lm still holds chol(M)
     };
 
     // reference _linesearch :378-497
     auto linesearch = [&]() {
       const T smag = t_sqrt(c.dotv(search, search)) * scale;
       const T gtol = tolerance * ls_tolerance * smag;
-      const V mv = c.matvec(Mm, search);
+      const V mv = c.symv(Mm, search);
       c.jmul(search, jv, nullptr);
       T qg0 = gauss, qg1, qg2;
       {
@@ -339,9 +379,10 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
         qg2 = T(0.5) * warp_sum(e);
       }
       struct Pt { T alpha, cost, d0, d1; };
-      // evaluates up to three step sizes in one pass over the constraint rows
-      auto points = [&](const T* al, int n, Pt* out) {
+      // evaluates NA step sizes in one pass over the constraint rows
+      auto points = [&](const T* al, const int NA, Pt* out) {
         T q[3][3];
+#pragma unroll
         for (int a = 0; a < 3; ++a) q[a][0] = q[a][1] = q[a][2] = T(0);
         for (int r = lane; r < nefc; r += 32) {
           const T ja = Jaref[r], jr = jv[r], dr = D[r];
@@ -351,22 +392,26 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
           if (hasf) rf = fl / (dr + (dr == T(0) ? T(MJT_MINVAL) : T(0)));
 #pragma unroll
           for (int a = 0; a < 3; ++a) {
-            if (a >= n) break;
-            const T x = ja + al[a] * jr;
-            bool act = (x < T(0)) || (r < ne_nf);
-            if (hasf) {
-              if (x <= -rf) { act = false; q[a][0] += fl * (-T(0.5) * rf - ja); q[a][1] += -fl * jr; }
-              if (x >= rf) { act = false; q[a][0] += fl * (-T(0.5) * rf + ja); q[a][1] += fl * jr; }
+            if (a < NA) {
+              const T x = ja + al[a] * jr;
+              bool act = (x < T(0)) || (r < ne_nf);
+              if (hasf) {
+                if (x <= -rf) { act = false; q[a][0] += fl * (-T(0.5) * rf - ja); q[a][1] += -fl * jr; }
+                if (x >= rf) { act = false; q[a][0] += fl * (-T(0.5) * rf + ja); q[a][1] += fl * jr; }
+              }
+              if (act) { q[a][0] += c0; q[a][1] += c1; q[a][2] += c2; }
             }
-            if (act) { q[a][0] += c0; q[a][1] += c1; q[a][2] += c2; }
           }
         }
-        for (int a = 0; a < n; ++a) {
-          const T t0 = qg0 + warp_sum(q[a][0]), t1 = qg1 + warp_sum(q[a][1]), t2 = qg2 + warp_sum(q[a][2]);
-          out[a].alpha = al[a];
-          out[a].cost = al[a] * al[a] * t2 + al[a] * t1 + t0;
-          out[a].d0 = T(2) * al[a] * t2 + t1;
-          out[a].d1 = T(2) * t2 + (t2 == T(0) ? T(MJT_MINVAL) : T(0));
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          if (a < NA) {
+            const T t0 = qg0 + warp_sum(q[a][0]), t1 = qg1 + warp_sum(q[a][1]), t2 = qg2 + warp_sum(q[a][2]);
+            out[a].alpha = al[a];
+            out[a].cost = al[a] * al[a] * t2 + al[a] * t1 + t0;
+            out[a].d0 = T(2) * al[a] * t2 + t1;
+            out[a].d1 = T(2) * t2 + (t2 == T(0) ? T(MJT_MINVAL) : T(0));
+          }
         }
       };
       Pt p0, p1, lo, hi;
@@ -389,18 +434,18 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
         al[1] = hi.alpha - hi.d0 / hi.d1;
         al[2] = T(0.5) * (lo.alpha + hi.alpha);
         points(al, 3, cand);
-        const Pt &lo_next = cand[0], &hi_next = cand[1], &mid = cand[2];
+        const Pt lo_next = cand[0], hi_next = cand[1], mid = cand[2];
         const bool not_bracketed = (lo.d0 < T(0)) == (hi.d0 < T(0));
         auto sw = [&](T cur, T cd) {
           const bool in_bracket = ((cur < cd) && (cd < T(0))) || ((cur > cd) && (cd > T(0)));
           return in_bracket || (not_bracketed && (t_abs(cd) < t_abs(cur)));
         };
-        bool s1 = sw(lo.d0, lo_next.d0); if (s1) lo = lo_next;
-        bool s2 = sw(lo.d0, mid.d0); if (s2) lo = mid;
-        bool s3 = sw(lo.d0, hi_next.d0); if (s3) lo = hi_next;
-        bool s4 = sw(hi.d0, hi_next.d0); if (s4) hi = hi_next;
-        bool s5 = sw(hi.d0, mid.d0); if (s5) hi = mid;
-        bool s6 = sw(hi.d0, lo_next.d0); if (s6) hi = lo_next;
+        const bool s1 = sw(lo.d0, lo_next.d0); if (s1) lo = lo_next;
+        const bool s2 = sw(lo.d0, mid.d0); if (s2) lo = mid;
+        const bool s3 = sw(lo.d0, hi_next.d0); if (s3) lo = hi_next;
+        const bool s4 = sw(hi.d0, hi_next.d0); if (s4) hi = hi_next;
+        const bool s5 = sw(hi.d0, mid.d0); if (s5) hi = mid;
+        const bool s6 = sw(hi.d0, lo_next.d0); if (s6) hi = lo_next;
         swap = s1 || s2 || s3 || s4 || s5 || s6;
         ++it;
       }
@@ -414,11 +459,79 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
       }
     };
 
-    auto body = [&]() {
+    // ---- warm start (:526-531): cost at qacc_warmstart vs cost at qacc_smooth; the winner's context is kept
+    // instead of being rebuilt (same values: the reference's third _create_context repeats the same arithmetic)
+    bool take_warm = false;
+    V warm = c.zero(), Ma_w = c.zero();
+    T cost_w = t_inf<T>();
+    if (!(flags & DSBL_WARMSTART)) {
+#pragma unroll
+      for (int k = 0; k < DPL; ++k) { const int i = lane + 32 * k; warm.v[k] = i < nv ? in_get<T>(in.qacc_warmstart, B, env, i) : T(0); }
+      qacc = warm;
+      c.jmul(qacc, Jaref, aref);
+      Ma = c.symv(Mm, qacc);
+      Ma_w = Ma;
+      cost = t_inf<T>();
+      update_constraint(false);
+      cost_w = cost;
+    }
+    qacc = qacc_smooth;
+    c.jmul(qacc, jv, aref);  // Jaref(smooth) parked in jv while the two costs are compared
+    Ma = c.symv(Mm, qacc);
+    {
+      T* keep = Jaref;
+      // evaluate the smooth cost on the parked values
+      T cpart = 0;
+      for (int r = lane; r < nefc; r += 32) {
+        const T ja = jv[r], dr = D[r];
+        bool act = (ja < T(0)) || (r < ne_nf);
+        if (use_floss) {
+          const T fl = floss[r];
+          if (fl > T(0)) {
+            const T rr = T(1) / (dr + (dr == T(0) ? T(MJT_MINVAL) : T(0)));
+            if (ja <= -rr * fl) { act = false; cpart += -T(0.5) * rr * fl * fl - fl * ja; }
+            if (ja >= rr * fl) { act = false; cpart += -T(0.5) * rr * fl * fl + fl * ja; }
+          }
+        }
+        if (act) cpart += T(0.5) * dr * ja * ja;
+      }
+      const T cost_s = warp_sum(cpart);  // gauss term is exactly zero at qacc_smooth
+      take_warm = cost_w < cost_s;
+      if (take_warm) {
+        qacc = warm;
+        Ma = Ma_w;
+      } else {
+        for (int r = lane; r < nefc; r += 32) keep[r] = jv[r];
+      }
+      __syncwarp();
+    }
+    cost = t_inf<T>();
+    prev_cost = 0;
+    update_constraint(true);
+    compute_grad();
+    compute_mgrad();
+    search = neg(Mgrad);
+
+    // ---- main loop (:501-539).  The gradient solve at the end of body() is only needed if another iteration
+    // follows, so the termination test is evaluated first (identical outputs, one factorisation less per solve).
+    int niter = 0;
+    bool run = true;
+    if (iterations != 1) {
+      const T improvement = (prev_cost - cost) / scale;
+      const T gradient = t_sqrt(c.dotv(grad, grad)) / scale;
+      run = !(niter >= iterations || improvement < tolerance || gradient < tolerance);
+    }
+    while (run) {
       linesearch();
       const V prev_grad = grad, prev_Mgrad = Mgrad;
-      update_constraint();
-      update_gradient();
+      update_constraint(true);
+      compute_grad();
+      ++niter;
+      if (iterations == 1) break;
+      const T improvement = (prev_cost - cost) / scale;
+      const T gradient = t_sqrt(c.dotv(grad, grad)) / scale;
+      if (niter >= iterations || improvement < tolerance || gradient < tolerance) break;
+      compute_mgrad();
       if (newton) {
         search = neg(Mgrad);
       } else {  // Polak-Ribiere :519-523
@@ -429,34 +542,6 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
         beta = t_max(beta, T(0));
 #pragma unroll
         for (int k = 0; k < DPL; ++k) search.v[k] = -Mgrad.v[k] + beta * search.v[k];
-      }
-    };
-
-    // warm start :526-531
-    V q0 = qacc_smooth;
-    if (!(flags & DSBL_WARMSTART)) {
-      V warm;
-#pragma unroll
-      for (int k = 0; k < DPL; ++k) { const int i = lane + 32 * k; warm.v[k] = i < nv ? in_get<T>(in.qacc_warmstart, B, env, i) : T(0); }
-      create_context(warm, false);
-      const T cw = cost;
-      create_context(qacc_smooth, false);
-      if (cw < cost) q0 = warm;
-    }
-    create_context(q0, true);
-    if (iterations == 1) {
-      body();
-    } else {
-      int niter = 0;
-      while (true) {
-        const T improvement = (prev_cost - cost) / scale;
-        const T gradient = t_sqrt(c.dotv(grad, grad)) / scale;
-        bool done = niter >= iterations;
-        done = done || (improvement < tolerance);
-        done = done || (gradient < tolerance);
-        if (done) break;
-        body();
-        ++niter;
       }
     }
     storev(m.D(D_qacc_warmstart), qacc);
@@ -474,33 +559,49 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
   V qacc_int = qacc;
   bool refactor = false;
   if (integrator == INT_EULER && !(flags & DSBL_EULERDAMP)) {
-    for (int idx = lane; idx < nv * nv; idx += 32) {
-      const int i = idx / nv, j = idx - i * nv;
-      Lm[i * ld + j] = Mm[i * ld + j] + (i == j ? dt * m.F(F_dof_damping)[i] : T(0));
-    }
+    for (int p = lane; p < Lo.nP; p += 32) Lm[p] = Mm[p];
+    __syncwarp();
+    for (int i = lane; i < nv; i += 32) Lm[tri(i) + i] += dt * m.F(F_dof_damping)[i];
     refactor = true;
   } else if (integrator == INT_IMPLICITFAST) {
     // qderiv = moment^T diag(biasprm2*[affine] + gainprm2*[affine]*ctrl) moment - diag(damping)  (derivative.py:22-68)
     const int nu = m.h(H_nu);
     const bool actuation = !(flags & DSBL_ACTUATION), damper = !(flags & DSBL_DAMPER);
     if (actuation || damper || m.h(H_ntendon)) {
-      for (int idx = lane; idx < nv * nv; idx += 32) {
-        const int i = idx / nv, j = idx - i * nv;
-        T qd = (damper && i == j) ? -m.F(F_dof_damping)[i] : T(0);
-        if (actuation)
-          for (int u = 0; u < nu; ++u) {
-            T vel = 0;
-            if (m.I(I_act_biastype)[u] == BIAS_AFFINE) vel += m.F(F_act_biasprm)[10 * u + 2];
-            if (m.I(I_act_gaintype)[u] == GAIN_AFFINE) {
-              const T cu = m.I(I_act_dyntype)[u] != DYN_NONE ? d.get(m.D(D_act) + m.I(I_act_actadr)[u]) : in_get<T>(in.ctrl, B, env, u);
-              vel += m.F(F_act_gainprm)[10 * u + 2] * cu;
-            }
-            if (vel == T(0)) continue;
-            qd += d.get(m.D(D_actuator_moment) + u * nv + i) * vel * d.get(m.D(D_actuator_moment) + u * nv + j);
+      for (int p = lane; p < Lo.nP; p += 32) Lm[p] = Mm[p];
+      __syncwarp();
+      if (damper)
+        for (int i = lane; i < nv; i += 32) Lm[tri(i) + i] += dt * m.F(F_dof_damping)[i];
+      __syncwarp();
+      if (actuation)
+        for (int u = 0; u < nu; ++u) {
+          T vel = 0;
+          if (m.I(I_act_biastype)[u] == BIAS_AFFINE) vel += m.F(F_act_biasprm)[10 * u + 2];
+          if (m.I(I_act_gaintype)[u] == GAIN_AFFINE) {
+            const T cu = m.I(I_act_dyntype)[u] != DYN_NONE ? d.get(m.D(D_act) + m.I(I_act_actadr)[u]) : in_get<T>(in.ctrl, B, env, u);
+            vel += m.F(F_act_gainprm)[10 * u + 2] * cu;
           }
-        for (int t = 0; t < m.h(H_ntendon); ++t)
-          qd -= d.get(m.D(D_ten_J) + t * nv + i) * m.F(F_ten_damping)[t] * d.get(m.D(D_ten_J) + t * nv + j);
-        Lm[i * ld + j] = Mm[i * ld + j] - dt * qd;
+          if (vel == T(0)) continue;
+          for (int p = lane; p < Lo.nP; p += 32) {
+            int i = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
+            while (tri(i + 1) <= p) ++i;
+            while (tri(i) > p) --i;
+            const int j = p - tri(i);
+            Lm[p] -= dt * d.get(m.D(D_actuator_moment) + u * nv + i) * vel * d.get(m.D(D_actuator_moment) + u * nv + j);
+          }
+          __syncwarp();
+        }
+      for (int t = 0; t < m.h(H_ntendon); ++t) {
+        const T td = m.F(F_ten_damping)[t];
+        if (td == T(0)) continue;
+        for (int p = lane; p < Lo.nP; p += 32) {
+          int i = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
+          while (tri(i + 1) <= p) ++i;
+          while (tri(i) > p) --i;
+          const int j = p - tri(i);
+          Lm[p] += dt * d.get(m.D(D_ten_J) + t * nv + i) * td * d.get(m.D(D_ten_J) + t * nv + j);
+        }
+        __syncwarp();
       }
       refactor = true;
     }
@@ -515,7 +616,7 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
   }
 
   // ---- _advance (forward.py:255-310)
-  const int na = m.h(H_na), nu = m.h(H_nu);
+  const int nu = m.h(H_nu);
   for (int u = lane; u < nu; u += 32) {
     const int adr = m.I(I_act_actadr)[u];
     if (adr < 0) continue;
@@ -532,7 +633,6 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
       d.set(m.D(D_act) + a, nx);
     }
   }
-  (void)na;
   V qvel = loadv(m.D(D_qvel));
   qvel = axpy(qvel, dt, qacc_int);
   storev(m.D(D_qvel), qvel);
@@ -559,38 +659,79 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
 }
 
 template <typename T, int DPL>
-__global__ void __launch_bounds__(256) k_solve(const int* __restrict__ gblob, int blob_words, MjtIn in, T* __restrict__ out, int B, int mode) {
+__global__ void __launch_bounds__(512) k_solve(const int* __restrict__ gblob, int blob_words, MjtIn in, T* __restrict__ out, int B, int mode) {
   extern __shared__ __align__(16) int smem_blob[];
   __shared__ uint64_t bar;
   stage_blob(smem_blob, &bar, gblob, blob_words);
   const ModelView<T> m = make_view<T>(smem_blob);
   const int E = blockDim.x >> 5;
-  const int warp = threadIdx.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int env0 = blockIdx.x * E;
   const int nv = m.h(H_nv), nefc = m.h(H_nefc);
-  const SolveLayout Lo = solve_layout(nv, nefc);
+  const SolveLayout Lo = solve_layout(nv, nefc, m.h(H_jc_words), m.h(H_nf));
   T* region = reinterpret_cast<T*>(smem_blob + ((blob_words + 3) & ~3));
+  const size_t Bs = (size_t)B;
 
-  // cooperative, env-contiguous loads of J, M, D, aref, frictionloss for the CTA's E envs
-  auto load_tile = [&](int src_off, int rows, int cols, int dst_off, int ldd) {
-    const int total = rows * cols * E;
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+  // ---- cooperative, env-contiguous loads (E consecutive envs share every word's cache line)
+  {
+    const int oM = m.D(D_qM);
+    for (int idx = threadIdx.x; idx < nv * nv * E; idx += blockDim.x) {
       const int e = idx % E, k = idx / E;
-      const int r = k / cols, cc = k - r * cols;
-      const int env = env0 + e;
-      if (env < B) region[(size_t)e * Lo.words + dst_off + r * ldd + cc] = out[(size_t)(src_off + k) * B + env];
+      const int i = k / nv, j = k - i * nv;
+      if (j <= i && env0 + e < B) region[(size_t)e * Lo.words + Lo.oM + tri(i) + j] = out[(size_t)(oM + k) * Bs + env0 + e];
     }
-  };
-  load_tile(m.D(D_qM), nv, nv, Lo.oM, Lo.ldm);
-  if (nefc) {
-    load_tile(m.D(D_efc_J), nefc, nv, Lo.oJ, Lo.ldj);
-    load_tile(m.D(D_efc_D), 1, nefc, Lo.oD, nefc);
-    load_tile(m.D(D_efc_aref), 1, nefc, Lo.oAref, nefc);
-    load_tile(m.D(D_efc_frictionloss), 1, nefc, Lo.oFloss, nefc);
+    if (nefc) {
+      const int oJ = m.D(D_efc_J), jcw = m.h(H_jc_words);
+      const int* jrow = m.I(I_jc_row);
+      const int* jcol = m.I(I_jc_col);
+      for (int idx = threadIdx.x; idx < jcw * E; idx += blockDim.x) {
+        const int e = idx % E, k = idx / E;
+        if (env0 + e < B) region[(size_t)e * Lo.words + Lo.oJ + k] = out[(size_t)(oJ + jrow[k] * nv + jcol[k]) * Bs + env0 + e];
+      }
+      const int oD = m.D(D_efc_D), oA = m.D(D_efc_aref), oF = m.D(D_efc_frictionloss);
+      const bool hasf = m.h(H_nf) > 0;
+      for (int idx = threadIdx.x; idx < nefc * E; idx += blockDim.x) {
+        const int e = idx % E, k = idx / E;
+        if (env0 + e < B) {
+          T* rg = region + (size_t)e * Lo.words;
+          rg[Lo.oD + k] = out[(size_t)(oD + k) * Bs + env0 + e];
+          rg[Lo.oAref + k] = out[(size_t)(oA + k) * Bs + env0 + e];
+          if (hasf) rg[Lo.oFloss + k] = out[(size_t)(oF + k) * Bs + env0 + e];
+        }
+      }
+    }
   }
   __syncthreads();
+
   const int env = env0 + warp;
-  if (env >= B) return;
-  EnvBuf<T> d{out + env, (size_t)B};
-  solve_env<T, DPL>(m, in, d, (size_t)B, env, region + (size_t)warp * Lo.words, mode);
+  const bool valid = env < B;
+  EnvBuf<T> d{out + (valid ? env : 0), Bs};
+  SolveCtx<T, DPL> c{m, region + (size_t)warp * Lo.words, Lo, nv, nefc, lane,
+                     m.I(I_row_src), m.I(I_row_jadr), m.I(I_src_nsup), m.I(I_src_cadr), m.I(I_src_row), m.I(I_src_nrows), m.I(I_sup_col)};
+  Vec<T, DPL> qfrc_smooth = c.zero(), qacc_smooth = c.zero();
+  if (valid) {
+    // ---- factor_m + qacc_smooth
+    T* Lm = c.Lp();
+    const T* Mm = c.Mp();
+    for (int p = lane; p < Lo.nP; p += 32) Lm[p] = Mm[p];
+    __syncwarp();
+    c.cholesky(Lm);
+#pragma unroll
+    for (int k = 0; k < DPL; ++k) { const int i = lane + 32 * k; qfrc_smooth.v[k] = i < nv ? d.get(m.D(D_qfrc_smooth) + i) : T(0); }
+    qacc_smooth = c.cho_solve(Lm, qfrc_smooth);
+#pragma unroll
+    for (int k = 0; k < DPL; ++k) { const int i = lane + 32 * k; if (i < nv) d.set(m.D(D_qacc_smooth) + i, qacc_smooth.v[k]); }
+  }
+  __syncthreads();
+  {  // cooperative store of qLD = chol(M) (dense lower, zeros above the diagonal)
+    const int oL = m.D(D_qLD);
+    for (int idx = threadIdx.x; idx < nv * nv * E; idx += blockDim.x) {
+      const int e = idx % E, k = idx / E;
+      const int i = k / nv, j = k - i * nv;
+      if (env0 + e < B) out[(size_t)(oL + k) * Bs + env0 + e] = j <= i ? region[(size_t)e * Lo.words + Lo.oL + tri(i) + j] : T(0);
+    }
+  }
+  __syncthreads();
+  if (!valid) return;
+  solve_env<T, DPL>(m, in, d, Bs, env, c, qfrc_smooth, qacc_smooth, mode);
 }

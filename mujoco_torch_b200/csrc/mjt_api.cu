@@ -17,6 +17,27 @@
 
 static thread_local std::string g_err;
 
+// Optional per-kernel timing (bench.py's roofline leg): when enabled every launch is bracketed by CUDA events on the
+// launching stream; mjt_profile_end() synchronises and returns "name:ms:count;..." totals.
+struct ProfRec { const char* name; cudaEvent_t a, b; };
+static thread_local std::vector<ProfRec>* g_prof = nullptr;
+struct ProfScope {
+  ProfRec r;
+  cudaStream_t st;
+  bool on;
+  ProfScope(const char* name, cudaStream_t s) : st(s), on(g_prof != nullptr) {
+    if (on) { r.name = name; cudaEventCreate(&r.a); cudaEventCreate(&r.b); cudaEventRecord(r.a, st); }
+  }
+  ~ProfScope() {
+    if (on) { cudaEventRecord(r.b, st); g_prof->push_back(r); }
+  }
+};
+#define LAUNCH(name, st, ...)            \
+  do {                                   \
+    ProfScope prof__(name, st);          \
+    __VA_ARGS__;                         \
+  } while (0)
+
 static int fail(const std::string& msg) {
   g_err = msg;
   return 1;
@@ -74,18 +95,18 @@ extern "C" int mjt_model_create(const void* blob_host, size_t nbytes, int device
   // k_solve shared-memory budget: blob + E per-env regions; pick the E in {8,4,2,1} that maximises resident warps per SM
   const int nv = w[H_nv], nefc = w[H_nefc];
   const size_t tsz = m->f64 ? 8 : 4;
-  const size_t region = (size_t)solve_layout(nv, nefc).words * tsz;
+  const size_t region = (size_t)solve_layout(nv, nefc, w[H_jc_words], w[H_nf]).words * tsz;
   const size_t blob_b = ((size_t)m->blob_words + 3) / 4 * 16;
   const size_t sm_total = (size_t)prop.sharedMemPerMultiprocessor;
   int best_e = 0;
   size_t best_warps = 0;
-  for (int e = 8; e >= 1; e >>= 1) {
+  for (int e = 16; e >= 1; e >>= 1) {
     const size_t need = blob_b + region * e + 1024;
     if (need > (size_t)m->max_smem) continue;
     size_t ctas = sm_total / need;
     if (ctas > 32) ctas = 32;
     size_t warps = ctas * e;
-    if (warps > 64) warps = 64;
+    if (warps > 16) warps = 16;  // the kernel is compiled for <= 128 registers/thread: 16 resident warps per SM
     if (warps > best_warps) { best_warps = warps; best_e = e; }
   }
   if (best_e == 0) {
@@ -151,23 +172,23 @@ static int run_forward(const mjtModel* m, const MjtIn& in, T* out, int B, int mo
   const int nsens = m->hv(H_nsensordata);
   int n = 0;
   if (set_smem<T>((const void*)k_smooth<T>, blob_b)) return 1;
-  k_smooth<T><<<gx, threads, blob_b, st>>>(m->d_blob, m->blob_words, in, out, B);
+  LAUNCH("k_smooth", st, k_smooth<T><<<gx, threads, blob_b, st>>>(m->d_blob, m->blob_words, in, out, B));
   ++n;
   if (m->hv(H_npair_cand) > 0) {
     if (set_smem<T>((const void*)k_collision<T>, blob_b)) return 1;
     dim3 grid(gx, m->hv(H_npair_cand) < 65535 ? m->hv(H_npair_cand) : 65535);
-    k_collision<T><<<grid, threads, blob_b, st>>>(m->d_blob, m->blob_words, out, B);
+    LAUNCH("k_collision", st, k_collision<T><<<grid, threads, blob_b, st>>>(m->d_blob, m->blob_words, out, B));
     ++n;
   }
   if (m->hv(H_nsrc) > 0) {
     if (set_smem<T>((const void*)k_constraint<T>, blob_b)) return 1;
     dim3 grid(gx, m->hv(H_nsrc) < 65535 ? m->hv(H_nsrc) : 65535);
-    k_constraint<T><<<grid, threads, blob_b, st>>>(m->d_blob, m->blob_words, in, out, B);
+    LAUNCH("k_constraint", st, k_constraint<T><<<grid, threads, blob_b, st>>>(m->d_blob, m->blob_words, in, out, B));
     ++n;
   }
   if (nsens > 0) {
     if (set_smem<T>((const void*)k_sensor<T>, blob_b)) return 1;
-    k_sensor<T><<<gx, threads, blob_b, st>>>(m->d_blob, m->blob_words, in, out, B, (1 << 1) | (1 << 2));
+    LAUNCH("k_sensor", st, k_sensor<T><<<gx, threads, blob_b, st>>>(m->d_blob, m->blob_words, in, out, B, (1 << 1) | (1 << 2)));
     ++n;
   }
   {
@@ -175,10 +196,10 @@ static int run_forward(const mjtModel* m, const MjtIn& in, T* out, int B, int mo
     const int gs = (B + E - 1) / E;
     if (m->hv(H_nv) <= 32) {
       if (set_smem<T>((const void*)k_solve<T, 1>, m->solve_smem)) return 1;
-      k_solve<T, 1><<<gs, 32 * E, m->solve_smem, st>>>(m->d_blob, m->blob_words, in, out, B, mode);
+      LAUNCH("k_solve", st, k_solve<T, 1><<<gs, 32 * E, m->solve_smem, st>>>(m->d_blob, m->blob_words, in, out, B, mode));
     } else if (m->hv(H_nv) <= 64) {
       if (set_smem<T>((const void*)k_solve<T, 2>, m->solve_smem)) return 1;
-      k_solve<T, 2><<<gs, 32 * E, m->solve_smem, st>>>(m->d_blob, m->blob_words, in, out, B, mode);
+      LAUNCH("k_solve", st, k_solve<T, 2><<<gs, 32 * E, m->solve_smem, st>>>(m->d_blob, m->blob_words, in, out, B, mode));
     } else {
       return fail("mjt: nv > 64 not supported by the dense solver kernel");
     }
@@ -186,7 +207,7 @@ static int run_forward(const mjtModel* m, const MjtIn& in, T* out, int B, int mo
   }
   // acc-stage sensors run only when the solver ran (reference forward.py:390-401 returns early when nefc == 0)
   if (nsens > 0 && m->hv(H_nsens_acc) > 0 && m->hv(H_nefc) > 0) {
-    k_sensor<T><<<gx, threads, blob_b, st>>>(m->d_blob, m->blob_words, in, out, B, 1 << 3);
+    LAUNCH("k_sensor", st, k_sensor<T><<<gx, threads, blob_b, st>>>(m->d_blob, m->blob_words, in, out, B, 1 << 3));
     ++n;
   }
   if (launches) *launches = n;
@@ -214,7 +235,7 @@ static int run_step(const mjtModel* m, const MjtIn& in, T* out, T* scratch, int 
   total += n;
   T* prev = out;
   for (int i = 0; i < 3; ++i) {
-    k_rk4_stage<T><<<gx, threads, blob_b, st>>>(m->d_blob, m->blob_words, out, prev, tail, B, i);
+    LAUNCH("k_rk4_stage", st, k_rk4_stage<T><<<gx, threads, blob_b, st>>>(m->d_blob, m->blob_words, out, prev, tail, B, i));
     ++total;
     MjtIn sin = in;
     sin.qpos = tail;
@@ -228,7 +249,7 @@ static int run_step(const mjtModel* m, const MjtIn& in, T* out, T* scratch, int 
     total += n;
     prev = stage_buf;
   }
-  k_rk4_stage<T><<<gx, threads, blob_b, st>>>(m->d_blob, m->blob_words, out, prev, tail, B, 3);
+  LAUNCH("k_rk4_stage", st, k_rk4_stage<T><<<gx, threads, blob_b, st>>>(m->d_blob, m->blob_words, out, prev, tail, B, 3));
   ++total;
   if (launches) *launches = total;
   cudaError_t e = cudaGetLastError();
@@ -267,4 +288,41 @@ extern "C" int mjt_step_launches(const mjtModel* m) {
   if (m->hv(H_nsensordata) > 0) ++per_forward;
   if (m->hv(H_nsensordata) > 0 && m->hv(H_nsens_acc) > 0 && m->hv(H_nefc) > 0) ++per_forward;
   return m->hv(H_integrator) == INT_RK4 ? 4 * per_forward + 4 : per_forward;
+}
+
+extern "C" void mjt_profile_begin(void) {
+  if (!g_prof) g_prof = new std::vector<ProfRec>();
+  g_prof->clear();
+}
+
+extern "C" int mjt_profile_end(char* buf, size_t nbuf) {
+  if (!g_prof) return fail("mjt_profile_end: profiling was not started");
+  cudaDeviceSynchronize();
+  struct Acc { std::string name; double ms; int n; };
+  std::vector<Acc> acc;
+  for (auto& r : *g_prof) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+    bool found = false;
+    for (auto& a : acc)
+      if (a.name == r.name) { a.ms += ms; a.n += 1; found = true; }
+    if (!found) acc.push_back({r.name, ms, 1});
+  }
+  delete g_prof;
+  g_prof = nullptr;
+  std::string out;
+  for (auto& a : acc) out += a.name + ":" + std::to_string(a.ms) + ":" + std::to_string(a.n) + ";";
+  if (buf && nbuf) {
+    strncpy(buf, out.c_str(), nbuf - 1);
+    buf[nbuf - 1] = 0;
+  }
+  return 0;
+}
+
+extern "C" int mjt_solve_config(const mjtModel* m, int* envs_per_cta, int* smem_bytes) {
+  if (envs_per_cta) *envs_per_cta = m->solve_envs;
+  if (smem_bytes) *smem_bytes = (int)m->solve_smem;
+  return 0;
 }

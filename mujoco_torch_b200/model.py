@@ -317,10 +317,72 @@ class Model:
                 mask[b, dof // 32] |= np.uint32(1 << (dof % 32))
         self.body_dofmask = mask
         self.maskwords = mw
+        self._row_supports(S)
 
         for t in np.asarray(mj.sensor_type):
             if int(t) not in _SUPPORTED_SENSORS:
                 raise NotImplementedError(f"sensor type {int(t)} not implemented.")
+
+    def _row_supports(self, S):
+        """Static column support of every constraint source (the dofs its Jacobian rows can touch).
+
+        The solver kernel keeps J compacted to these columns in shared memory and assembles the Newton Hessian
+        only over them.  Contacts: dofs that are ancestors of exactly one of the two bodies (common ancestors
+        cancel exactly, reference support.jac_dif_pair :156-166); limits / friction: the joint's own dofs;
+        tendons: the wrapped joints' dofs; equalities: ancestors of either body (or the two joint dofs).
+        """
+        mj = self.mj
+        nv = self.nv
+
+        def anc(b):
+            bits = self.body_dofmask[b]
+            return {i for i in range(nv) if (int(bits[i // 32]) >> (i % 32)) & 1}
+
+        def tendon_dofs(t):
+            out = set()
+            for w in range(int(mj.tendon_adr[t]), int(mj.tendon_adr[t]) + int(mj.tendon_num[t])):
+                if int(mj.wrap_type[w]) == WrapType.JOINT:
+                    out.add(int(mj.jnt_dofadr[int(mj.wrap_objid[w])]))
+            return out
+
+        gb = np.asarray(mj.geom_bodyid)
+        src_cadr, src_nsup, src_nrows, cols = [], [], [], []
+        nrows_of = {}
+        for k, (t, i, row) in enumerate(self.src):
+            nxt = self.src[k + 1][2] if k + 1 < len(self.src) else self.nefc
+            nrows_of[k] = nxt - row
+        for k, (t, i, row) in enumerate(self.src):
+            name = L.SRC_TYPES[t]
+            if name == "CONTACT":
+                a, b = anc(int(gb[self.con["g1"][i]])), anc(int(gb[self.con["g2"][i]]))
+                sup = a ^ b
+            elif name in ("EQ_CONNECT", "EQ_WELD"):
+                sup = anc(int(mj.eq_obj1id[i])) | anc(int(mj.eq_obj2id[i]))
+            elif name == "EQ_JOINT":
+                j2 = int(mj.eq_obj2id[i])
+                sup = {int(mj.jnt_dofadr[int(mj.eq_obj1id[i])]), int(mj.jnt_dofadr[j2 if j2 >= 0 else self.njnt + j2])}
+            elif name == "FRIC_DOF":
+                sup = {i}
+            elif name in ("FRIC_TEN", "LIM_TEN"):
+                sup = tendon_dofs(i)
+            elif name == "LIM_BALL":
+                d0 = int(mj.jnt_dofadr[i])
+                sup = {d0, d0 + 1, d0 + 2}
+            else:  # LIM_SH
+                sup = {int(mj.jnt_dofadr[i])}
+            sup = sorted(sup)
+            src_cadr.append(len(cols))
+            src_nsup.append(len(sup))
+            src_nrows.append(nrows_of[k])
+            cols.extend(sup)
+        row_src, row_jadr, jadr = [], [], 0
+        for k, (t, i, row) in enumerate(self.src):
+            for _ in range(src_nrows[k]):
+                row_src.append(k)
+                row_jadr.append(jadr)
+                jadr += src_nsup[k]
+        self.sup = dict(src_cadr=src_cadr, src_nsup=src_nsup, src_nrows=src_nrows, cols=cols, row_src=row_src, row_jadr=row_jadr,
+                        jc_words=jadr)
 
     # ---- blob
     def _pack(self):
@@ -349,6 +411,15 @@ class Model:
         I["con_dim"], I["con_efcadr"] = i32(self.con["dim"]), i32(self.con_efcadr)
         I["con_geom1"], I["con_geom2"] = i32(self.con["g1"]), i32(self.con["g2"])
         I["src_type"], I["src_id"], I["src_row"] = (i32([s[k] for s in self.src]) for k in range(3))
+        sp = self.sup
+        I["src_cadr"], I["src_nsup"], I["src_nrows"] = i32(sp["src_cadr"]), i32(sp["src_nsup"]), i32(sp["src_nrows"])
+        I["sup_col"], I["row_src"], I["row_jadr"] = i32(sp["cols"]), i32(sp["row_src"]), i32(sp["row_jadr"])
+        jc_row, jc_col = [], []
+        for r, k in enumerate(sp["row_src"]):
+            ca, ns = sp["src_cadr"][k], sp["src_nsup"][k]
+            jc_row += [r] * ns
+            jc_col += sp["cols"][ca: ca + ns]
+        I["jc_row"], I["jc_col"] = i32(jc_row), i32(jc_col)
         I["eq_type"], I["eq_obj1"], I["eq_obj2"] = i32(mj.eq_type), i32(mj.eq_obj1id), i32(mj.eq_obj2id)
         I["sens_type"], I["sens_objid"], I["sens_adr"] = i32(mj.sensor_type), i32(mj.sensor_objid), i32(mj.sensor_adr)
         I["sens_dim"], I["sens_datatype"], I["sens_stage"] = i32(mj.sensor_dim), i32(mj.sensor_datatype), i32(mj.sensor_needstage)
@@ -435,7 +506,7 @@ class Model:
                  has_fluid=int(self.opt.has_fluid_params), nv_pad=self.nv | 1, nlim_sh=cnt("LIM_SH"), nlim_ball=cnt("LIM_BALL"),
                  nfric_dof=cnt("FRIC_DOF"), nfric_ten=cnt("FRIC_TEN"), nlim_ten=cnt("LIM_TEN"), ne_connect=cnt("EQ_CONNECT"),
                  ne_weld=cnt("EQ_WELD"), ne_joint=cnt("EQ_JOINT"), maskwords=self.maskwords, nsens_pos=int((st == 1).sum()),
-                 nsens_vel=int((st == 2).sum()), nsens_acc=int((st == 3).sum()), nconvex=len(cv), nrfgeom=len(rf))
+                 nsens_vel=int((st == 2).sum()), nsens_acc=int((st == 3).sum()), nconvex=len(cv), nrfgeom=len(rf), jc_words=self.sup["jc_words"])
         nH, nI, nF, nD = len(L.H_SCALARS), len(L.I_ARRAYS), len(L.F_ARRAYS), len(L.D_FIELDS)
         hdr = np.zeros(nH + nI + nF + 2 * nD, dtype=np.int32)
         ints, pos = [], hdr.size

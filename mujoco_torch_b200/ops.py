@@ -50,12 +50,34 @@ def lib():
     L.mjt_step.restype = ctypes.c_int
     L.mjt_forward.argtypes = [ctypes.c_void_p, ctypes.POINTER(StateIn), ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
     L.mjt_forward.restype = ctypes.c_int
+    L.mjt_profile_begin.restype = None
+    L.mjt_profile_end.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
+    L.mjt_profile_end.restype = ctypes.c_int
+    L.mjt_solve_config.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
+    L.mjt_solve_config.restype = ctypes.c_int
     _lib = L
     return L
 
 
+def profile_begin():
+    lib().mjt_profile_begin()
+
+
+def profile_end() -> dict:
+    """{kernel name: (total ms, launches)} since profile_begin()."""
+    buf = ctypes.create_string_buffer(4096)
+    _check(lib().mjt_profile_end(buf, 4096))
+    out = {}
+    for item in buf.value.decode().split(";"):
+        if item:
+            name, ms, n = item.split(":")
+            out[name] = (float(ms), int(n))
+    return out
+
+
 EXPORTS = ("mjt_version", "mjt_last_error", "mjt_model_create", "mjt_model_destroy", "mjt_model_data_words",
-           "mjt_model_scratch_words", "mjt_model_dtype_size", "mjt_model_field", "mjt_step", "mjt_forward", "mjt_step_launches")
+           "mjt_model_scratch_words", "mjt_model_dtype_size", "mjt_model_field", "mjt_step", "mjt_forward", "mjt_step_launches",
+           "mjt_profile_begin", "mjt_profile_end", "mjt_solve_config")
 
 
 def _check(rc):
