@@ -173,14 +173,15 @@ struct SolveCtx {
         if (i < n) {
           const T* rowi = A + tri(i);
           T acc = rowi[j];
+#pragma unroll 4
           for (int k = 0; k < j; ++k) acc -= rowi[k] * rowj[k];
           t[p] = acc;
         }
       }
       T sdiag = __shfl_sync(0xffffffffu, t[0], 0);
       if (big) sdiag += T(1e-10); else sdiag = t_max(sdiag, T(1e-12));
-      const T ljj = t_sqrt(sdiag);
-      const T inv = T(1) / ljj;
+      const T inv = t_rsqrt(sdiag);
+      const T ljj = sdiag * inv;
       __syncwarp();
 #pragma unroll
       for (int p = 0; p < DPL; ++p) {
@@ -659,7 +660,8 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
 }
 
 template <typename T, int DPL>
-__global__ void __launch_bounds__(512) k_solve(const int* __restrict__ gblob, int blob_words, MjtIn in, T* __restrict__ out, int B, int mode) {
+__global__ void __launch_bounds__(512) k_solve(const int* __restrict__ gfull, const int* __restrict__ gblob, int blob_words, MjtIn in,
+                                               T* __restrict__ out, int B, int mode) {
   extern __shared__ __align__(16) int smem_blob[];
   __shared__ uint64_t bar;
   stage_blob(smem_blob, &bar, gblob, blob_words);
@@ -682,8 +684,9 @@ __global__ void __launch_bounds__(512) k_solve(const int* __restrict__ gblob, in
     }
     if (nefc) {
       const int oJ = m.D(D_efc_J), jcw = m.h(H_jc_words);
-      const int* jrow = m.I(I_jc_row);
-      const int* jcol = m.I(I_jc_col);
+      // (row, column) of every compact J entry: read straight from the full blob in global memory (L1/L2 resident)
+      const int* jrow = gfull + gfull[MJT_OFF_I + I_jc_row];
+      const int* jcol = gfull + gfull[MJT_OFF_I + I_jc_col];
       for (int idx = threadIdx.x; idx < jcw * E; idx += blockDim.x) {
         const int e = idx % E, k = idx / E;
         if (env0 + e < B) region[(size_t)e * Lo.words + Lo.oJ + k] = out[(size_t)(oJ + jrow[k] * nv + jcol[k]) * Bs + env0 + e];

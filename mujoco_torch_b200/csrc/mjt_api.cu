@@ -53,6 +53,7 @@ struct mjtModel {
   int* d_blob;
   std::vector<int> h;  // host copy of the blob
   int blob_words;
+  int solve_words;  // reduced blob staged by k_solve (stored right after the full blob)
   bool f64;
   int sm_count;
   int max_smem;
@@ -79,11 +80,12 @@ extern "C" int mjt_model_create(const void* blob_host, size_t nbytes, int device
   if (!blob_host || !out || nbytes < MJT_HDR_WORDS * 4) return fail("mjt_model_create: bad arguments");
   const int* w = static_cast<const int*>(blob_host);
   if ((unsigned)w[H_magic] != MJT_MAGIC) return fail("mjt_model_create: bad blob magic (layout mismatch?)");
-  if ((size_t)w[H_blob_words] * 4 != nbytes) return fail("mjt_model_create: blob size mismatch");
+  if (((size_t)w[H_blob_words] + (size_t)w[H_solve_blob_words]) * 4 != nbytes) return fail("mjt_model_create: blob size mismatch");
   CUDA_OK(cudaSetDevice(device));
   mjtModel* m = new mjtModel();
   m->device = device;
   m->blob_words = w[H_blob_words];
+  m->solve_words = w[H_solve_blob_words];
   m->h.assign(w, w + m->blob_words);
   m->f64 = w[H_is_f64] != 0;
   cudaDeviceProp prop;
@@ -97,11 +99,12 @@ extern "C" int mjt_model_create(const void* blob_host, size_t nbytes, int device
   const size_t tsz = m->f64 ? 8 : 4;
   const size_t region = (size_t)solve_layout(nv, nefc, w[H_jc_words], w[H_nf]).words * tsz;
   const size_t blob_b = ((size_t)m->blob_words + 3) / 4 * 16;
+  const size_t sblob_b = ((size_t)m->solve_words + 3) / 4 * 16;
   const size_t sm_total = (size_t)prop.sharedMemPerMultiprocessor;
   int best_e = 0;
   size_t best_warps = 0;
   for (int e = 16; e >= 1; e >>= 1) {
-    const size_t need = blob_b + region * e + 1024;
+    const size_t need = sblob_b + region * e + 1024;
     if (need > (size_t)m->max_smem) continue;
     size_t ctas = sm_total / need;
     if (ctas > 32) ctas = 32;
@@ -114,7 +117,7 @@ extern "C" int mjt_model_create(const void* blob_host, size_t nbytes, int device
     return fail("mjt_model_create: model too large for the shared-memory solver tile (nv * nefc)");
   }
   m->solve_envs = best_e;
-  m->solve_smem = blob_b + region * best_e;
+  m->solve_smem = sblob_b + region * best_e;
   if (blob_b + 64 > (size_t)m->max_smem) {
     delete m;
     return fail("mjt_model_create: model blob exceeds shared memory");
@@ -196,10 +199,10 @@ static int run_forward(const mjtModel* m, const MjtIn& in, T* out, int B, int mo
     const int gs = (B + E - 1) / E;
     if (m->hv(H_nv) <= 32) {
       if (set_smem<T>((const void*)k_solve<T, 1>, m->solve_smem)) return 1;
-      LAUNCH("k_solve", st, k_solve<T, 1><<<gs, 32 * E, m->solve_smem, st>>>(m->d_blob, m->blob_words, in, out, B, mode));
+      LAUNCH("k_solve", st, k_solve<T, 1><<<gs, 32 * E, m->solve_smem, st>>>(m->d_blob, m->d_blob + m->blob_words, m->solve_words, in, out, B, mode));
     } else if (m->hv(H_nv) <= 64) {
       if (set_smem<T>((const void*)k_solve<T, 2>, m->solve_smem)) return 1;
-      LAUNCH("k_solve", st, k_solve<T, 2><<<gs, 32 * E, m->solve_smem, st>>>(m->d_blob, m->blob_words, in, out, B, mode));
+      LAUNCH("k_solve", st, k_solve<T, 2><<<gs, 32 * E, m->solve_smem, st>>>(m->d_blob, m->d_blob + m->blob_words, m->solve_words, in, out, B, mode));
     } else {
       return fail("mjt: nv > 64 not supported by the dense solver kernel");
     }

@@ -113,6 +113,9 @@ __device__ __forceinline__ T in_get(const void* base, size_t B, int env, int k) 
 template <typename T> __device__ __forceinline__ T t_sqrt(T x);
 template <> __device__ __forceinline__ float t_sqrt<float>(float x) { return sqrtf(x); }
 template <> __device__ __forceinline__ double t_sqrt<double>(double x) { return sqrt(x); }
+template <typename T> __device__ __forceinline__ T t_rsqrt(T x);
+template <> __device__ __forceinline__ float t_rsqrt<float>(float x) { return rsqrtf(x); }
+template <> __device__ __forceinline__ double t_rsqrt<double>(double x) { return rsqrt(x); }
 template <typename T> __device__ __forceinline__ void t_sincos(T x, T* s, T* c);
 template <> __device__ __forceinline__ void t_sincos<float>(float x, float* s, float* c) { sincosf(x, s, c); }
 template <> __device__ __forceinline__ void t_sincos<double>(double x, double* s, double* c) { sincos(x, s, c); }

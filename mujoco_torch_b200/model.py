@@ -508,37 +508,50 @@ class Model:
                  ne_weld=cnt("EQ_WELD"), ne_joint=cnt("EQ_JOINT"), maskwords=self.maskwords, nsens_pos=int((st == 1).sum()),
                  nsens_vel=int((st == 2).sum()), nsens_acc=int((st == 3).sum()), nconvex=len(cv), nrfgeom=len(rf), jc_words=self.sup["jc_words"])
         nH, nI, nF, nD = len(L.H_SCALARS), len(L.I_ARRAYS), len(L.F_ARRAYS), len(L.D_FIELDS)
-        hdr = np.zeros(nH + nI + nF + 2 * nD, dtype=np.int32)
-        ints, pos = [], hdr.size
-        for k, name in enumerate(L.I_ARRAYS):
-            a = I[name]
-            hdr[nH + k] = pos
-            ints.append(a)
-            pos += a.size
-        pos_pad = (pos + 3) // 4 * 4
-        flts, fpos = [], 0
-        for k, name in enumerate(L.F_ARRAYS):
-            a = F[name]
-            hdr[nH + nI + k] = fpos
-            flts.append(a)
-            fpos += a.size
-            if fpos % 2:  # keep every float array 8-byte aligned in f32 / 16-byte pairs in f64
-                flts.append(np.zeros(1))
-                fpos += 1
-        for k, (name, _) in enumerate(L.D_FIELDS):
-            hdr[nH + nI + nF + k] = self.field_off[name]
-            hdr[nH + nI + nF + nD + k] = int(np.prod(self.field_shape[name])) if self.field_shape[name] else 1
-        fl_arr = np.concatenate(flts) if flts else np.zeros(0)
-        fl_bytes = fl_arr.astype(np.float64 if f64 else np.float32).view(np.int32)
-        H["float_base_words"] = pos_pad
-        H["blob_words"] = (pos_pad + fl_bytes.size + 3) // 4 * 4
-        for k, name in enumerate(L.H_SCALARS):
-            hdr[k] = np.int32(np.uint32(H.get(name, 0)).view(np.int32)) if name == "magic" else H.get(name, 0)
-        blob = np.zeros(H["blob_words"], dtype=np.int32)
-        blob[: hdr.size] = hdr
-        ii = np.concatenate(ints) if ints else np.zeros(0, np.int32)
-        blob[hdr.size : hdr.size + ii.size] = ii
-        blob[pos_pad : pos_pad + fl_bytes.size] = fl_bytes
+        def assemble(keep=None, extra=None):
+            """One blob; with ``keep`` only the named arrays carry data (the others get length 0)."""
+            Hh = dict(H)
+            Hh.update(extra or {})
+            hdr = np.zeros(nH + nI + nF + 2 * nD, dtype=np.int32)
+            ints, pos = [], hdr.size
+            for k, name in enumerate(L.I_ARRAYS):
+                a = I[name] if keep is None or name in keep else np.zeros(0, np.int32)
+                hdr[nH + k] = pos
+                ints.append(a)
+                pos += a.size
+            pos_pad = (pos + 3) // 4 * 4
+            flts, fpos = [], 0
+            for k, name in enumerate(L.F_ARRAYS):
+                a = F[name] if keep is None or name in keep else np.zeros(0)
+                hdr[nH + nI + k] = fpos
+                flts.append(a)
+                fpos += a.size
+                if fpos % 2:  # keep every float array 8-byte aligned in f32 / 16-byte pairs in f64
+                    flts.append(np.zeros(1))
+                    fpos += 1
+            for k, (name, _) in enumerate(L.D_FIELDS):
+                hdr[nH + nI + nF + k] = self.field_off[name]
+                hdr[nH + nI + nF + nD + k] = int(np.prod(self.field_shape[name])) if self.field_shape[name] else 1
+            fl_arr = np.concatenate(flts) if flts else np.zeros(0)
+            fl_bytes = fl_arr.astype(np.float64 if f64 else np.float32).view(np.int32)
+            Hh["float_base_words"] = pos_pad
+            Hh["blob_words"] = (pos_pad + fl_bytes.size + 3) // 4 * 4
+            for k, name in enumerate(L.H_SCALARS):
+                hdr[k] = np.int32(np.uint32(Hh.get(name, 0)).view(np.int32)) if name == "magic" else Hh.get(name, 0)
+            out = np.zeros(Hh["blob_words"], dtype=np.int32)
+            out[: hdr.size] = hdr
+            ii = np.concatenate(ints) if ints else np.zeros(0, np.int32)
+            out[hdr.size: hdr.size + ii.size] = ii
+            out[pos_pad: pos_pad + fl_bytes.size] = fl_bytes
+            return out
+
+        # the solver kernel stages a reduced blob (only the tables it reads) so that more envs fit in shared memory
+        solve_keep = set("jnt_type jnt_qposadr jnt_dofadr act_dyntype act_gaintype act_biastype act_actadr act_actnum act_actlimited "
+                         "src_row src_nrows src_nsup src_cadr sup_col row_src row_jadr "
+                         "opt dof_damping act_actrange act_gainprm act_biasprm act_dynprm ten_damping".split())
+        solve_blob = assemble(solve_keep)
+        full = assemble(None, {"solve_blob_words": int(solve_blob.size)})
+        blob = np.concatenate([full, solve_blob])
         self.blob_np = blob
         self.blob = torch.from_numpy(blob.copy())
         self._I, self._F = I, F

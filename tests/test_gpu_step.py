@@ -94,6 +94,12 @@ def _compare(mj, B, dtype, tol, drop):
             outlier |= e_c > torch.clamp(4 * e_o, min=tol)
         else:
             outlier |= _env_err(getattr(dc, k), getattr(do, k)) > tol
+    if mo.nefc:  # the constraint force is the most sensitive witness of a line-search branch flip
+        fscale = max(float(do.qfrc_smooth.abs().max()), 1e-6)
+        ref = truth.qfrc_constraint.double()
+        e_c = (dc.qfrc_constraint.cpu().double() - ref).abs().amax(1) / fscale
+        e_o = (do.qfrc_constraint.double() - ref).abs().amax(1) / fscale
+        outlier |= e_c > torch.clamp(4 * e_o, min=10 * tol)
     n_unst, n_extra = int(unstable.sum()), int((outlier & ~unstable).sum())
     allowed = n_unst + (2 if n_unst else 0) + (B // 20 if f32 else 0)
     assert n_unst <= 0.35 * B, f"too many oracle-unstable envs: {n_unst}/{B}"
