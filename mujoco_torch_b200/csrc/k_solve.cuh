@@ -660,7 +660,7 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
 }
 
 template <typename T, int DPL>
-__global__ void __launch_bounds__(512) k_solve(const int* __restrict__ gfull, const int* __restrict__ gblob, int blob_words, MjtIn in,
+__global__ void __launch_bounds__(512, (sizeof(T) == 4 ? 2 : 1)) k_solve(const int* __restrict__ gfull, const int* __restrict__ gblob, int blob_words, MjtIn in,
                                                T* __restrict__ out, int B, int mode) {
   extern __shared__ __align__(16) int smem_blob[];
   __shared__ uint64_t bar;
@@ -674,27 +674,26 @@ __global__ void __launch_bounds__(512) k_solve(const int* __restrict__ gfull, co
   T* region = reinterpret_cast<T*>(smem_blob + ((blob_words + 3) & ~3));
   const size_t Bs = (size_t)B;
 
-  // ---- cooperative, env-contiguous loads (E consecutive envs share every word's cache line)
+  // ---- cooperative, env-contiguous loads (E consecutive envs share every word's cache line; E is a power of two)
+  const int esh = __ffs(E) - 1, emask = E - 1;
+  const int* tri_src = gfull + gfull[MJT_OFF_I + I_tri_src];   // packed lower index -> dense word i*nv+j (global, L1 resident)
   {
     const int oM = m.D(D_qM);
-    for (int idx = threadIdx.x; idx < nv * nv * E; idx += blockDim.x) {
-      const int e = idx % E, k = idx / E;
-      const int i = k / nv, j = k - i * nv;
-      if (j <= i && env0 + e < B) region[(size_t)e * Lo.words + Lo.oM + tri(i) + j] = out[(size_t)(oM + k) * Bs + env0 + e];
+    for (int idx = threadIdx.x; idx < (Lo.nP << esh); idx += blockDim.x) {
+      const int e = idx & emask, p = idx >> esh;
+      if (env0 + e < B) region[(size_t)e * Lo.words + Lo.oM + p] = out[(size_t)(oM + tri_src[p]) * Bs + env0 + e];
     }
     if (nefc) {
       const int oJ = m.D(D_efc_J), jcw = m.h(H_jc_words);
-      // (row, column) of every compact J entry: read straight from the full blob in global memory (L1/L2 resident)
-      const int* jrow = gfull + gfull[MJT_OFF_I + I_jc_row];
-      const int* jcol = gfull + gfull[MJT_OFF_I + I_jc_col];
-      for (int idx = threadIdx.x; idx < jcw * E; idx += blockDim.x) {
-        const int e = idx % E, k = idx / E;
-        if (env0 + e < B) region[(size_t)e * Lo.words + Lo.oJ + k] = out[(size_t)(oJ + jrow[k] * nv + jcol[k]) * Bs + env0 + e];
+      const int* jsrc = gfull + gfull[MJT_OFF_I + I_jc_src];   // compact J entry -> dense word row*nv+col
+      for (int idx = threadIdx.x; idx < (jcw << esh); idx += blockDim.x) {
+        const int e = idx & emask, k = idx >> esh;
+        if (env0 + e < B) region[(size_t)e * Lo.words + Lo.oJ + k] = out[(size_t)(oJ + jsrc[k]) * Bs + env0 + e];
       }
       const int oD = m.D(D_efc_D), oA = m.D(D_efc_aref), oF = m.D(D_efc_frictionloss);
       const bool hasf = m.h(H_nf) > 0;
-      for (int idx = threadIdx.x; idx < nefc * E; idx += blockDim.x) {
-        const int e = idx % E, k = idx / E;
+      for (int idx = threadIdx.x; idx < (nefc << esh); idx += blockDim.x) {
+        const int e = idx & emask, k = idx >> esh;
         if (env0 + e < B) {
           T* rg = region + (size_t)e * Lo.words;
           rg[Lo.oD + k] = out[(size_t)(oD + k) * Bs + env0 + e];
@@ -728,10 +727,14 @@ __global__ void __launch_bounds__(512) k_solve(const int* __restrict__ gfull, co
   __syncthreads();
   {  // cooperative store of qLD = chol(M) (dense lower, zeros above the diagonal)
     const int oL = m.D(D_qLD);
-    for (int idx = threadIdx.x; idx < nv * nv * E; idx += blockDim.x) {
-      const int e = idx % E, k = idx / E;
-      const int i = k / nv, j = k - i * nv;
-      if (env0 + e < B) out[(size_t)(oL + k) * Bs + env0 + e] = j <= i ? region[(size_t)e * Lo.words + Lo.oL + tri(i) + j] : T(0);
+    const int* triu_src = gfull + gfull[MJT_OFF_I + I_triu_src];
+    for (int idx = threadIdx.x; idx < (Lo.nP << esh); idx += blockDim.x) {
+      const int e = idx & emask, p = idx >> esh;
+      if (env0 + e < B) out[(size_t)(oL + tri_src[p]) * Bs + env0 + e] = region[(size_t)e * Lo.words + Lo.oL + p];
+    }
+    for (int idx = threadIdx.x; idx < ((Lo.nP - nv) << esh); idx += blockDim.x) {
+      const int e = idx & emask, p = idx >> esh;
+      if (env0 + e < B) out[(size_t)(oL + triu_src[p]) * Bs + env0 + e] = T(0);
     }
   }
   __syncthreads();

@@ -109,7 +109,8 @@ extern "C" int mjt_model_create(const void* blob_host, size_t nbytes, int device
     size_t ctas = sm_total / need;
     if (ctas > 32) ctas = 32;
     size_t warps = ctas * e;
-    if (warps > 16) warps = 16;  // the kernel is compiled for <= 128 registers/thread: 16 resident warps per SM
+    const size_t wcap = m->f64 ? 16 : 32;  // f64 kernel: <= 128 regs/thread (16 warps/SM); f32 kernel: <= 64 regs (32 warps/SM)
+    if (warps > wcap) warps = wcap;
     if (warps > best_warps) { best_warps = warps; best_e = e; }
   }
   if (best_e == 0) {

@@ -414,12 +414,13 @@ class Model:
         sp = self.sup
         I["src_cadr"], I["src_nsup"], I["src_nrows"] = i32(sp["src_cadr"]), i32(sp["src_nsup"]), i32(sp["src_nrows"])
         I["sup_col"], I["row_src"], I["row_jadr"] = i32(sp["cols"]), i32(sp["row_src"]), i32(sp["row_jadr"])
-        jc_row, jc_col = [], []
+        jc_src = []
         for r, k in enumerate(sp["row_src"]):
             ca, ns = sp["src_cadr"][k], sp["src_nsup"][k]
-            jc_row += [r] * ns
-            jc_col += sp["cols"][ca: ca + ns]
-        I["jc_row"], I["jc_col"] = i32(jc_row), i32(jc_col)
+            jc_src += [r * self.nv + cc for cc in sp["cols"][ca: ca + ns]]
+        I["jc_src"] = i32(jc_src)
+        I["tri_src"] = i32([i * self.nv + j for i in range(self.nv) for j in range(i + 1)])
+        I["triu_src"] = i32([j * self.nv + i for i in range(self.nv) for j in range(i)])
         I["eq_type"], I["eq_obj1"], I["eq_obj2"] = i32(mj.eq_type), i32(mj.eq_obj1id), i32(mj.eq_obj2id)
         I["sens_type"], I["sens_objid"], I["sens_adr"] = i32(mj.sensor_type), i32(mj.sensor_objid), i32(mj.sensor_adr)
         I["sens_dim"], I["sens_datatype"], I["sens_stage"] = i32(mj.sensor_dim), i32(mj.sensor_datatype), i32(mj.sensor_needstage)
