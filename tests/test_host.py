@@ -1,0 +1,124 @@
+"""CPU tier: C-ABI library surface, layout agreement, host-side static precompute vs the oracle's, Data container API."""
+
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import mujoco_torch_b200 as mt
+from mujoco_torch_b200 import layout as L
+from mujoco_torch_b200 import ops
+from oracle import model as om
+from tests import util
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MODELS = ["cartpole", "humanoid", "halfcheetah", "ant", "ant_zoo", "hopper", "walker2d", "swimmer", "pendula", "frictionloss_dof", "convex"]
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "mjt.h")).read()
+    declared = sorted(set(re.findall(r"\b(mjt_[a-z_]+)\s*\(", hdr)))
+    assert declared, "no declarations found in include/mjt.h"
+    lib = ops.lib()
+    for sym in declared:
+        assert hasattr(lib, sym), f"libmjt_b200.so does not export {sym}"
+    assert sorted(ops.EXPORTS) == declared
+    assert lib.mjt_version() >= 1000
+    assert isinstance(lib.mjt_last_error(), bytes)
+
+
+def test_layout_header_in_sync():
+    path = os.path.join(ROOT, "mujoco_torch_b200", "csrc", "mjt_layout.h")
+    assert open(path).read() == L.header_text(), "run `python -m mujoco_torch_b200.layout`"
+
+
+def test_no_cpu_fallback():
+    mx = mt.device_put(util.load_model("cartpole"), dtype=torch.float64)
+    d = mt.make_data(mx)
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        mt.step(mx, d)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "mujoco_torch_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "import oracle" not in src and "from oracle" not in src, fn
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_static_precompute_matches_oracle(name):
+    """candidate pairs / final contact order / mixed solver params / efc sizes: product packer vs oracle restatement."""
+    mj = util.load_model(name)
+    mx = mt.device_put(mj, dtype=torch.float64)
+    mo = om.OModel(mj, torch.float64)
+    assert (mx.ne, mx.nf, mx.nl, mx.ncon, mx.nefc) == (mo.ne, mo.nf, mo.nl, mo.ncon, mo.nefc)
+    if mo.ncon:
+        c = mo.contact
+        assert mx.con["g1"].tolist() == c["geom1"].tolist() and mx.con["g2"].tolist() == c["geom2"].tolist()
+        assert mx.con["dim"].tolist() == c["dim"].tolist()
+        for k_prod, k_or in (("include", "includemargin"), ("friction", "friction"), ("solref", "solref"),
+                             ("solreffriction", "solreffriction"), ("solimp", "solimp")):
+            np.testing.assert_allclose(mx.con[k_prod], c[k_or].numpy(), rtol=1e-14, atol=0)
+    # blob header round trip
+    w = mx.blob_np
+    assert w[L.h_index("nv")] == mj.nv and w[L.h_index("nefc")] == mo.nefc and w[L.h_index("data_words")] == mx.data_words
+    assert w[L.h_index("blob_words")] + w[L.h_index("solve_blob_words")] == w.size
+
+
+def test_sizes_of_benchmark_configs():
+    """SURVEY.md §8(d) config table."""
+    expect = {"cartpole": (2, 2, 1, 0, 0), "halfcheetah": (9, 9, 6, 16, 70), "humanoid": (28, 27, 21, 8, 53), "ant": (8, 8, 8, 60, 248)}
+    for name, (nq, nv, nu, ncon, nefc) in expect.items():
+        mj = util.load_model(name)
+        mx = mt.device_put(mj, dtype=torch.float64)
+        assert (mj.nq, mj.nv, mj.nu, mx.ncon, mx.nefc) == (nq, nv, nu, ncon, nefc), name
+    mj = util.load_model("ant_zoo", cone=1, solver=1)
+    mx = mt.device_put(mj, dtype=torch.float32)
+    assert (mj.nq, mj.nv, mj.nu, mx.ncon, mx.nefc) == (15, 14, 8, 69, 215)
+
+
+def test_data_container_api():
+    mx = mt.device_put(util.load_model("humanoid"), dtype=torch.float64)
+    d = mt.make_data(mx)
+    assert tuple(d.batch_size) == () and d.qpos.shape == (28,) and d.contact.dist.shape == (8,)
+    assert d.efc_J.shape == (53, 27) and (d.ne, d.nf, d.nl, d.ncon, d.nefc) == (0, 0, 21, 8, 53)
+    b = d.expand(4).clone()
+    assert tuple(b.batch_size) == (4,) and b.qpos.shape == (4, 28) and b.contact.frame.shape == (4, 8, 3, 3)
+    b2 = b.replace(qvel=torch.ones(4, 27, dtype=torch.float64))
+    assert b2.qvel.sum() == 4 * 27 and b.qvel.sum() == 0 and b2.qpos is b.qpos
+    b2.update_(ctrl=torch.full((4, 21), 0.5, dtype=torch.float64))
+    assert float(b2.ctrl[0, 0]) == 0.5
+    b3 = b.tree_replace({"contact.dist": torch.ones(4, 8, dtype=torch.float64)})
+    assert b3.contact.dist.sum() == 32 and b.contact.dist.sum() == 0
+    assert b[1].qpos.shape == (28,) and tuple(b[1:3].batch_size) == (2,)
+    mask = torch.tensor([True, False, True, False])
+    fresh = mt.make_data(mx).expand(2).clone().replace(qvel=torch.full((2, 27), 7.0, dtype=torch.float64))
+    b[mask] = fresh
+    assert float(b.qvel[0, 0]) == 7.0 and float(b.qvel[1, 0]) == 0.0
+    s = torch.stack([d, d, d])
+    assert tuple(s.batch_size) == (3,) and s.contact.pos.shape == (3, 8, 3)
+    f32 = s.to(torch.float32)
+    assert f32.qpos.dtype == torch.float32 and f32.contact.geom1.dtype == torch.int64
+
+
+def test_data_is_a_pytree_for_vmap():
+    mx = mt.device_put(util.load_model("cartpole"), dtype=torch.float64)
+    d = mt.make_data(mx).expand(5).clone()
+    out = torch.vmap(lambda x: x.replace(qvel=x.qvel + x.qpos.sum()))(d)
+    assert isinstance(out, mt.Data) and out.qvel.shape == (5, 2)
+
+
+def test_unsupported_features_raise():
+    mj = util.load_model("cartpole")
+    mj.opt.integrator = 2  # IMPLICIT (full) is not supported by the reference either
+    with pytest.raises(NotImplementedError):
+        mt.device_put(mj)
+    mj = util.load_model("cartpole")
+    mj.opt.solver = 0  # PGS
+    with pytest.raises(NotImplementedError):
+        mt.device_put(mj)

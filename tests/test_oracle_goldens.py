@@ -1,0 +1,155 @@
+"""CPU tier: the oracle against every literal known answer the reference's own tests hold for this path
+(SURVEY.md §8c, g1-g10).  These run without a GPU and without the reference tree."""
+
+import numpy as np
+import pytest
+import torch
+
+from mujoco_torch_b200 import mjcf
+from oracle import collision as ocol
+from oracle import constraint as ocon
+from oracle import forward as of
+from oracle import model as om
+from oracle import omath as M
+from oracle import smooth as osm
+from oracle import solver as osol
+
+
+def _model(xml, dtype=torch.float64, **opt):
+    mj = mjcf.from_xml_string(xml)
+    for k, v in opt.items():
+        setattr(mj.opt, k, v)
+    return mj, om.OModel(mj, dtype)
+
+
+FREE_BODY = '<mujoco><option timestep="0.01"{flag}/><worldbody><body><joint type="free"/><geom size="0.1"/></body></worldbody></mujoco>'
+
+
+def test_g1_free_fall():
+    """reference test/smooth_test.py:181-208: one Euler step of a free body under gravity."""
+    _, m = _model(FREE_BODY.format(flag=""))
+    d = of.step(m, of.make_data(m, 1))
+    np.testing.assert_array_almost_equal(d.qpos[0].numpy(), [0, 0, -9.81e-4, 1, 0, 0, 0], decimal=7)
+
+
+def test_g1_free_fall_gravity_disabled():
+    xml = '<mujoco><option timestep="0.01"><flag gravity="disable"/></option><worldbody><body><joint type="free"/><geom size="0.1"/></body></worldbody></mujoco>'
+    _, m = _model(xml)
+    d = of.step(m, of.make_data(m, 1))
+    assert d.qpos[0].tolist() == [0, 0, 0, 1, 0, 0, 0]
+
+
+@pytest.mark.parametrize("sign", [1.0, -1.0])
+def test_g2_frictionloss_saturation(sign):
+    """reference test/solver_test.py:77-108: 1-dof, J=[[1]], D=[1], aref=[0], frictionloss=[2], M=[[1]]."""
+    xml = '<mujoco><worldbody><body><joint type="slide" frictionloss="2"/><geom size="0.1" mass="1"/></body></worldbody></mujoco>'
+    _, m = _model(xml)
+    assert (m.ne, m.nf, m.nl, m.nefc) == (0, 1, 0, 1)
+    d = of.make_data(m, 1)
+    one = torch.ones((1, 1), dtype=torch.float64)
+    d.efc_J, d.efc_D, d.efc_aref, d.efc_frictionloss = one[:, None, :].clone(), one.clone(), 0 * one, 2 * one
+    d.qM, d.qLD = one[:, None, :].clone(), one[:, None, :].clone()
+    d.qfrc_smooth = d.qacc_smooth = d.qacc_warmstart = sign * 100 * one
+    d = osol.solve(m, d)
+    np.testing.assert_allclose(d.efc_force[0].numpy(), [-sign * 2], atol=1e-9)
+    np.testing.assert_allclose(d.qfrc_constraint[0].numpy(), [-sign * 2], atol=1e-9)
+    np.testing.assert_allclose(d.qacc[0].numpy(), [sign * 100 - sign * 2], atol=1e-9)
+
+
+def test_g3_parallel_capsules():
+    """reference test/collision_driver_test.py:179-204 (same fixture, same tolerances)."""
+    xml = """<mujoco><worldbody>
+      <body><joint type="free"/><geom fromto="-0.5 0.1 0.25 0.5 0.1 0.25" size="0.1" type="capsule"/></body>
+      <body><joint type="free"/><geom fromto="-0.5 0.1 0.1 0.5 0.1 0.1" size="0.1" type="capsule"/></body>
+    </worldbody></mujoco>"""
+    _, m = _model(xml)
+    d = of.make_data(m, 1)
+    d = osm.kinematics(m, d)
+    d = ocol.collision(m, d)
+    assert m.ncon == 1
+    np.testing.assert_allclose(d.contact_dist[0].numpy(), [-0.05], rtol=1e-6)
+    np.testing.assert_allclose(d.contact_pos[0, 0].numpy(), [0.0, 0.1, (0.15 + 0.2) / 2.0], atol=1e-5)
+    np.testing.assert_allclose(d.contact_frame[0, 0, 0].numpy(), [0, 0.0, -1.0], atol=1e-5)
+
+
+def test_g5_ncon_ant(models_dir):
+    """reference test/collision_driver_test.py:451-468: ant.xml has 60 contacts, 0 with contacts disabled."""
+    from mujoco_torch_b200.mjmodel import MjModelLite
+
+    mj = MjModelLite.load_npz(f"{models_dir}/ant.npz")
+    assert om.OModel(mj).ncon == 60
+    mj.opt.disableflags = int(mj.opt.disableflags) | 16
+    assert om.OModel(mj).ncon == 0
+
+
+def test_g5_parent_child_filter():
+    """reference test/collision_driver_test.py:388-445: parent/child geoms never collide unless FILTERPARENT is disabled."""
+    xml = """<mujoco><worldbody><body><joint type="free"/><geom size="0.1"/>
+      <body pos="0.05 0 0"><joint type="hinge"/><geom size="0.1"/></body></body></worldbody></mujoco>"""
+    _, m = _model(xml)
+    assert m.ncon == 0
+    _, m2 = _model(xml, disableflags=1 << 10)
+    assert m2.ncon == 1
+
+
+def test_g6_segment_geometry():
+    """reference test/math_test.py:131-188 (closest points between segments; literals)."""
+    t = lambda *v: torch.tensor([v], dtype=torch.float64)
+    a, b = M.closest_segment_to_segment_points(t(0, 0, -1), t(0, 0, 1), t(-1, 0, 0.5), t(1, 0, 0.5))
+    np.testing.assert_allclose(a[0].numpy(), [0, 0, 0.5], atol=1e-5)
+    np.testing.assert_allclose(b[0].numpy(), [0, 0, 0.5], atol=1e-5)
+    # parallel, overlapping
+    a, b = M.closest_segment_to_segment_points(t(0, 0, -1), t(0, 0, 1), t(1, 0, -1), t(1, 0, 1))
+    assert abs(float((a - b).norm()) - 1.0) < 1e-5
+    b1, c1 = M.orthogonals(M.normalize(t(1.0, 2.0, 3.0)))
+    n = M.normalize(t(1.0, 2.0, 3.0))
+    assert abs(float(M.dot(b1, c1))) < 1e-12 and abs(float(M.dot(b1, n))) < 1e-12 and abs(float(M.dot(c1, n))) < 1e-12
+
+
+@pytest.mark.parametrize("refsafe_disabled", [True, False])
+def test_g7_kbi_refsafe(refsafe_disabled):
+    """reference test/constraint_test.py:128-146: k = 1/(dmax^2 tc^2) with refsafe disabled, 1/(dmax^2 (2dt)^2) enabled."""
+    xml = '<mujoco><option timestep="0.01"/><worldbody><body><joint type="slide"/><geom size="0.1"/></body></worldbody></mujoco>'
+    _, m = _model(xml, disableflags=(1 << 12) if refsafe_disabled else 0)
+    tc, dmax = 0.005, 0.99
+    solref = torch.tensor([tc, 1.0], dtype=torch.float64)
+    solimp = torch.tensor([0.9, dmax, 0.001, 0.5, 2.0], dtype=torch.float64)
+    k, b, imp = ocon.kbi(m, solref, solimp, torch.tensor(1.0, dtype=torch.float64))
+    tce = tc if refsafe_disabled else 2 * 0.01
+    np.testing.assert_allclose(float(k), 1 / (dmax * dmax * tce * tce), rtol=1e-12)
+
+
+def test_g8_euler_without_damping():
+    """reference test/forward_test.py:128-140: EULERDAMP disabled, qvel=qacc=1 -> qvel = 1 + dt."""
+    xml = """<mujoco><option timestep="0.002"><flag eulerdamp="disable" gravity="disable"/></option>
+      <worldbody><body><joint type="slide" damping="5"/><geom size="0.1"/></body></worldbody></mujoco>"""
+    _, m = _model(xml)
+    d = of.make_data(m, 1)
+    d.qvel[:] = 1.0
+    d.qacc, d.act_dot = torch.ones((1, 1), dtype=torch.float64), torch.zeros((1, 0), dtype=torch.float64)
+    d.qfrc_smooth = d.qfrc_constraint = torch.zeros((1, 1), dtype=torch.float64)
+    d = of.euler(m, d)
+    np.testing.assert_allclose(d.qvel[0].numpy(), [1 + 0.002], rtol=1e-12)
+
+
+def test_g9_slide_limit_sign():
+    """reference test/constraint_test.py:108-125: qpos=2.0 beyond range 1.8 -> J[0,0] = -1; an un-ranged joint has no row."""
+    xml = """<mujoco><worldbody><body><joint type="slide" range="-1.8 1.8"/><geom size="0.1"/>
+      <body><joint type="slide" axis="0 1 0"/><geom size="0.1"/></body></body></worldbody></mujoco>"""
+    _, m = _model(xml)
+    assert m.nl == 1 and m.nefc == 1
+    d = of.make_data(m, 1)
+    d.qpos[0, 0] = 2.0
+    d = of.position(m, d)
+    assert d.efc_J[0, 0, 0].item() == -1.0
+
+
+@pytest.mark.parametrize("cone,condim,rows", [(0, 3, 4), (1, 3, 3), (0, 4, 6), (1, 4, 4), (0, 1, 1), (1, 6, 6), (0, 6, 10)])
+def test_g10_rows_per_contact(cone, condim, rows):
+    """reference test/constraint_test.py:536-549, 578-591: elliptic rows = condim, pyramidal = 2(condim-1)."""
+    xml = f"""<mujoco><worldbody><geom type="plane" size="1 1 1" condim="{condim}"/>
+      <body pos="0 0 0.05"><joint type="free"/><geom size="0.1" condim="{condim}"/></body></worldbody></mujoco>"""
+    _, m = _model(xml, cone=cone)
+    assert m.ncon == 1 and m.nefc == rows
+    d = of.step(m, of.make_data(m, 2))
+    assert d.efc_J.shape == (2, rows, 6) and torch.isfinite(d.qpos).all()
