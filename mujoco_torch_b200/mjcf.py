@@ -412,6 +412,7 @@ class Compiler:
         g["mass"] = float(a["mass"]) if "mass" in a else None
         rgba = _f(a.get("rgba"), 4, np.array([0.5, 0.5, 0.5, 1.0]))
         g["rgba"] = rgba
+        g["matid"] = self._materials["index"].get(a.get("material"), -1) if a.get("material") else -1
         g["dataid"] = -1
         if gtype == GeomType.MESH:
             mid = meshes["index"][a["mesh"]]
@@ -487,6 +488,14 @@ class Compiler:
                 meshes["index"][name] = len(meshes["list"])
                 meshes["names"].append(name)
                 meshes["list"].append(_compile_mesh(path, _f(a.get("scale"), 3, np.ones(3))))
+
+        materials = {"index": {}, "rgba": []}
+        if asset is not None:
+            for ma in asset.findall("material"):
+                a = self.defaults.resolve("material", ma, None)
+                materials["index"][a.get("name")] = len(materials["rgba"])
+                materials["rgba"].append(_f(a.get("rgba"), 4, np.ones(4)))
+        self._materials = materials
 
         bodies: list[_Body] = []
         self._parse_body(root.find("worldbody"), None, None, bodies)
@@ -1018,7 +1027,7 @@ class Compiler:
         m.nsite, m.ncam, m.nlight, m.nmesh, m.npair, m.nexclude = nsite, ncam, nlight, len(meshes["list"]), npair, len(excludes)
         m.neq, m.ntendon, m.nwrap, m.nsensor, m.nnumeric, m.nmocap, m.nM = neq, ntendon, nwrap, nsensor, len(numerics), nmocap, nM
         m.nsensordata = nsensordata
-        m.nhfield, m.nmat, m.ntex, m.ntexdata, m.nkey = 0, 0, 0, 0, 0
+        m.nhfield, m.ntex, m.ntexdata, m.nkey = 0, 0, 0, 0
         m.opt = opt
         m.qpos0 = arr(qpos0)
         m.qpos_spring = arr(qpos_spring)
@@ -1056,7 +1065,9 @@ class Compiler:
         m.geom_condim, m.geom_bodyid = garr("condim", dtype=np.int32), garr("bodyid", dtype=np.int32)
         m.geom_dataid, m.geom_group, m.geom_priority = garr("dataid", dtype=np.int32), garr("group", dtype=np.int32), garr("priority", dtype=np.int32)
         m.geom_sameframe = np.zeros(ngeom, np.uint8)
-        m.geom_matid = np.full(ngeom, -1, np.int32)
+        m.geom_matid = garr("matid", dtype=np.int32)
+        m.nmat = len(self._materials["rgba"])
+        m.mat_rgba = arr(self._materials["rgba"], (4,))
         m.geom_solmix, m.geom_solref, m.geom_solimp = garr("solmix"), garr("solref", (2,)), garr("solimp", (5,))
         m.geom_size, m.geom_rbound = garr("size", (3,)), garr("rbound")
         m.geom_aabb = np.zeros((ngeom, 6))

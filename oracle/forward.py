@@ -40,6 +40,10 @@ def make_data(m, B=1):
     d.eq_active = torch.as_tensor(np.asarray(m.mj.eq_active0, dtype=np.int32)).expand(B, m.neq).clone()
     d.sensordata = z(m.nsensordata)
     d.cacc = z(m.nbody, 6)
+    # output buffers that some configurations never write (nefc == 0, nu == 0): zeros, as in the reference's make_data
+    d.efc_J, d.efc_D, d.efc_aref, d.efc_frictionloss, d.efc_force = z(m.nefc, m.nv), z(m.nefc), z(m.nefc), z(m.nefc), z(m.nefc)
+    d.actuator_length, d.actuator_moment, d.actuator_velocity, d.actuator_force = z(m.nu), z(m.nu, m.nv), z(m.nu), z(m.nu)
+    d.qfrc_actuator = z(m.nv)
     d.mocap_pos, d.mocap_quat = z(m.nmocap, 3), z(m.nmocap, 4)
     for b in range(m.nbody):
         mid = int(m.mj.body_mocapid[b])

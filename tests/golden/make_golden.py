@@ -1,0 +1,95 @@
+"""Generate golden input/output vectors by running the REFERENCE'S OWN step code on our compiled models.
+
+    python tests/golden/make_golden.py            # writes tests/golden/*.npz (run in the build container only)
+
+The reference (`/root/reference/mujoco_torch/_src/*.py`, unmodified, imported from where it lies) needs `mujoco`,
+`tensordict`, `pyvers` and `trimesh`; none exist in this image, so the minimal stand-ins of `oracle/refshim/` are put
+on sys.path first (see its README).  `mujoco_torch/__init__.py` is bypassed (it monkey-patches torch internals for
+torch.compile and imports the renderer); the physics modules under `_src` are imported directly.  Each environment is
+stepped single-env, eager, float64 -- the reference's own eager semantics.
+"""
+
+import os
+import sys
+import types
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+REF = os.environ.get("MJT_REFERENCE", "/root/reference")
+sys.path.insert(0, os.path.join(ROOT, "oracle", "refshim"))
+sys.path.insert(0, ROOT)
+pkg = types.ModuleType("mujoco_torch")
+pkg.__path__ = [os.path.join(REF, "mujoco_torch")]
+sys.modules["mujoco_torch"] = pkg
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+torch.set_default_dtype(torch.float64)
+
+import mujoco  # noqa: E402  (the shim)
+from mujoco_torch._src import device as ref_device  # noqa: E402
+from mujoco_torch._src import forward as ref_forward  # noqa: E402
+from mujoco_torch._src import io as ref_io  # noqa: E402
+
+from tests import util  # noqa: E402
+
+OUT_FIELDS = ["qpos", "qvel", "qacc", "qacc_warmstart", "act", "time", "xpos", "xquat", "xmat", "xipos", "ximat", "xanchor", "xaxis",
+              "geom_xpos", "geom_xmat", "subtree_com", "cinert", "crb", "cdof", "cdof_dot", "cvel", "qM", "qLD", "actuator_length",
+              "actuator_moment", "actuator_velocity", "actuator_force", "qfrc_bias", "qfrc_passive", "qfrc_actuator", "qfrc_smooth",
+              "qacc_smooth", "qfrc_constraint", "efc_J", "efc_D", "efc_aref", "efc_frictionloss", "efc_force", "sensordata"]
+CONTACT_FIELDS = ["dist", "pos", "frame", "includemargin", "friction", "solref", "solreffriction", "solimp", "contact_dim", "geom1",
+                  "geom2", "efc_address"]
+
+# (fixture name, model, option overrides, envs, drop height, steps)
+CASES = [
+    ("cartpole", "cartpole", {}, 4, 0.0, 1),
+    ("humanoid", "humanoid", {}, 6, 0.4, 1),
+    # NOTE: ImplicitFast cannot be recorded for actuated models: reference derivative.py:48 does
+    # torch.where(dyn_mask (nu,), d.act (na,), ctrl (nu,)) which raises for na != nu (Humanoid: nu=21, na=0).
+    ("frictionloss_dof_implicitfast", "frictionloss_dof", {"integrator": 3}, 3, 0.0, 1),
+    ("humanoid_converged", "humanoid", {"iterations": 100, "ls_iterations": 50}, 4, 0.4, 1),
+    ("halfcheetah", "halfcheetah", {}, 6, 0.6, 1),
+    ("halfcheetah_3steps", "halfcheetah", {}, 3, 0.6, 3),
+    ("ant", "ant", {}, 3, 0.0, 1),
+    ("ant_zoo_cg_elliptic", "ant_zoo", {"cone": 1, "solver": 1}, 4, 0.5, 1),
+    ("hopper", "hopper", {}, 4, 0.6, 1),
+    ("walker2d_rk4", "walker2d", {"integrator": 1}, 3, 0.8, 1),
+    ("swimmer", "swimmer", {}, 3, 0.0, 1),
+    ("pendula", "pendula", {}, 3, 0.0, 1),
+    ("frictionloss_dof", "frictionloss_dof", {}, 3, 0.0, 1),
+]
+
+
+def run_case(name, model, opt, B, drop, nsteps):
+    lite = util.load_model(model, **opt)
+    qpos, qvel, ctrl = util.seeded_state(lite, B, drop=drop)
+    mx = ref_device.device_put(mujoco.MjModel(lite))
+    dx0 = ref_io.make_data(mx)
+    outs = {k: [] for k in OUT_FIELDS}
+    cons = {k: [] for k in CONTACT_FIELDS}
+    for b in range(B):
+        d = dx0.replace(qpos=torch.as_tensor(qpos[b]), qvel=torch.as_tensor(qvel[b]), ctrl=torch.as_tensor(ctrl[b]))
+        for _ in range(nsteps):
+            d = ref_forward.step(mx, d)
+        for k in OUT_FIELDS:
+            outs[k].append(np.asarray(getattr(d, k)))
+        for k in CONTACT_FIELDS:
+            cons[k].append(np.asarray(getattr(d.contact, k)))
+    save = {"in_qpos": qpos, "in_qvel": qvel, "in_ctrl": ctrl, "nsteps": np.int64(nsteps),
+            "opt_keys": np.array(list(opt.keys()), dtype="U32"), "opt_vals": np.array(list(opt.values()), dtype=np.float64),
+            "model": np.array(model), "torch_version": np.array(torch.__version__)}
+    for k, v in outs.items():
+        save["out_" + k] = np.stack(v)
+    for k, v in cons.items():
+        save["contact_" + k] = np.stack(v)
+    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    np.savez_compressed(path, **save)
+    print(f"{name}: B={B} steps={nsteps} qpos[0,:3]={save['out_qpos'][0, :3]} -> {os.path.relpath(path, ROOT)}")
+
+
+if __name__ == "__main__":
+    only = set(sys.argv[1:])
+    for case in CASES:
+        if only and case[0] not in only:
+            continue
+        run_case(*case)

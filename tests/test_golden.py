@@ -1,0 +1,107 @@
+"""Golden vectors recorded from the REFERENCE'S OWN code (tests/golden/make_golden.py: the unmodified
+`/root/reference/mujoco_torch/_src` step run under import shims, single-env eager float64).
+
+  * CPU tier:  the oracle restatement must reproduce them (this is what pins the oracle).
+  * GPU tier:  the CUDA path, through the C ABI, must reproduce them.
+Tolerance 1e-9 relative per field (field-scale), float64.  Contact frames of coincident-point contacts are arbitrary
+(see test_gpu_step) and skipped; everything else, including contact order, geom ids, efc layout, is compared.
+"""
+
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests import util
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz")))
+FIELDS = ["qpos", "qvel", "qacc", "qacc_warmstart", "act", "time", "xpos", "xquat", "xmat", "xipos", "ximat", "xanchor", "xaxis",
+          "geom_xpos", "geom_xmat", "subtree_com", "cinert", "crb", "cdof", "cdof_dot", "cvel", "qM", "qLD", "actuator_length",
+          "actuator_moment", "actuator_velocity", "actuator_force", "qfrc_bias", "qfrc_passive", "qfrc_actuator", "qfrc_smooth",
+          "qacc_smooth", "qfrc_constraint", "efc_J", "efc_D", "efc_aref", "efc_frictionloss", "efc_force", "sensordata"]
+TOL = 1e-9
+
+
+def _load(path):
+    z = np.load(path)
+    opt = {str(k): (int(v) if float(v).is_integer() else float(v)) for k, v in zip(z["opt_keys"], z["opt_vals"])}
+    mj = util.load_model(str(z["model"]), **opt)
+    return z, mj
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    if a.size == 0:
+        return 0.0
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-6))
+
+
+def _check(z, get, get_contact, label):
+    bad = {}
+    nefc = z["out_efc_J"].shape[1]
+    degenerate = np.zeros(z["in_qpos"].shape[0], dtype=bool)
+    if z["contact_dist"].shape[1]:
+        for k in ("contact_dim", "geom1", "geom2", "efc_address"):
+            got = np.asarray(get_contact(k))
+            assert np.array_equal(got.astype(np.int64), z["contact_" + k].astype(np.int64)), f"{label}: contact.{k} differs"
+        for k in ("includemargin", "friction", "solref", "solreffriction", "solimp", "dist", "pos"):
+            e = _rel(get_contact(k), z["contact_" + k])
+            if e > TOL:
+                bad["contact." + k] = e
+        # frames: skip contacts whose two closest points coincide (normal undefined)
+        fr_ref, fr = z["contact_frame"], np.asarray(get_contact("frame"), dtype=np.float64)
+        diff = np.abs(fr - fr_ref).max(axis=(-1, -2))
+        nondeg = diff < 1e-6
+        degenerate = (~nondeg).any(axis=1)
+        # a differing frame is only acceptable for a coincident-point contact: both frames must still be orthonormal
+        for b, c in zip(*np.nonzero(~nondeg)):
+            assert abs(np.linalg.det(fr[b, c]) - 1) < 1e-6 or np.allclose(fr[b, c], 0), f"{label}: bad frame env {b} contact {c}"
+        if nondeg.any() and diff[nondeg].max() > 10 * TOL:
+            bad["contact.frame"] = float(diff[nondeg].max())
+    for k in FIELDS:
+        ref = z["out_" + k]
+        got = np.asarray(get(k), dtype=np.float64)
+        if k.startswith("efc_") or k in ("qfrc_constraint",):
+            if nefc == 0:
+                continue
+            sel = ~degenerate
+            e = _rel(got[sel], ref[sel]) if sel.any() else 0.0
+            if k == "qfrc_constraint":
+                e = float(np.abs(got[sel] - ref[sel]).max() / max(np.abs(z["out_qfrc_smooth"]).max(), 1e-6)) if sel.any() else 0.0
+        else:
+            e = _rel(got, ref)
+        if e > (10 * TOL if k in ("efc_force", "qfrc_constraint", "qacc", "qacc_warmstart", "qvel") else TOL):
+            bad[k] = e
+    assert not bad, f"{label}: fields beyond {TOL}: {bad}"
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_oracle_matches_reference(path):
+    z, mj = _load(path)
+    mo, do = util.run_oracle(mj, z["in_qpos"], z["in_qvel"], z["in_ctrl"], torch.float64, nsteps=int(z["nsteps"]))
+    ocon = {"dist": "contact_dist", "pos": "contact_pos", "frame": "contact_frame"}
+
+    def get_contact(k):
+        if k in ocon:
+            return getattr(do, ocon[k]).numpy()
+        B = z["in_qpos"].shape[0]
+        if k == "efc_address":
+            dims = mo.contact["dim"].numpy()
+            rows = np.where(dims == 1, 1, dims if mo.cone == 1 else 2 * (dims - 1))
+            adr = mo.ne + mo.nf + mo.nl + np.concatenate([[0], np.cumsum(rows)[:-1]])
+            return np.tile(adr, (B, 1))
+        key = {"contact_dim": "dim"}.get(k, k)
+        v = mo.contact[key].numpy()
+        return np.tile(v, (B,) + (1,) * v.ndim)
+
+    _check(z, lambda k: getattr(do, k).numpy(), get_contact, "oracle")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_cuda_matches_reference(path):
+    z, mj = _load(path)
+    mx, dc = util.run_cuda(mj, z["in_qpos"], z["in_qvel"], z["in_ctrl"], torch.float64, nsteps=int(z["nsteps"]))
+    _check(z, lambda k: getattr(dc, k).cpu().numpy(), lambda k: getattr(dc.contact, k).cpu().numpy(), "cuda")
