@@ -58,17 +58,24 @@ def _ccw_polygon(pts, idx, normal):
     return idx[hull.vertices[::step]]
 
 
+def _plane_key(eq, scale):
+    """Coplanarity bucket of a hull facet: unit normal to 4 decimals, offset to 1e-4 of the mesh size (meshes come
+    from float32 STL files, so exactly coplanar triangles differ at the 1e-7 level)."""
+    return tuple(np.round(eq[:3], 4) + 0.0) + (float(np.round(eq[3] / scale, 4)) + 0.0,)
+
+
 def _mesh_table(vert):
     from scipy.spatial import ConvexHull
 
     hull = ConvexHull(vert)
+    scale = float(np.abs(vert).max()) or 1.0
     used = np.unique(hull.simplices)
     local = np.full(len(vert), -1, dtype=np.int64)
     local[used] = np.arange(len(used))
     v = vert[used]
     planes: dict = {}
     for tri, eq in zip(hull.simplices, hull.equations):
-        planes.setdefault(tuple(np.round(eq, 7)), []).append(local[tri])
+        planes.setdefault(_plane_key(eq, scale), []).append(local[tri])
     polys = []
     for eq in sorted(planes):
         n = np.asarray(eq[:3])

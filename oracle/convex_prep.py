@@ -63,18 +63,22 @@ def _hull_2d(points, normal):
     return c.vertices[::order]
 
 
+def _plane_key(eq, scale):
+    return tuple(np.round(eq[:3], 4) + 0.0) + (float(np.round(eq[3] / scale, 4)) + 0.0,)
+
+
 def _mesh_polygons(vert):
     from scipy.spatial import ConvexHull
 
     hull = ConvexHull(vert)
+    scale = float(np.abs(vert).max()) or 1.0
     used = np.sort(np.unique(hull.simplices))
     remap = -np.ones(vert.shape[0], dtype=np.int64)
     remap[used] = np.arange(used.size)
     v = vert[used]
     groups: dict = {}
     for simplex, eq in zip(hull.simplices, hull.equations):
-        key = tuple(np.round(eq, 7))
-        groups.setdefault(key, []).append(remap[simplex])
+        groups.setdefault(_plane_key(eq, scale), []).append(remap[simplex])
     faces = []
     for key in sorted(groups):
         normal = np.array(key[:3])

@@ -31,7 +31,34 @@ from mujoco_torch._src import device as ref_device  # noqa: E402
 from mujoco_torch._src import forward as ref_forward  # noqa: E402
 from mujoco_torch._src import io as ref_io  # noqa: E402
 
+from mujoco_torch._src import mesh as ref_mesh  # noqa: E402
+from mujoco_torch._src import types as ref_types  # noqa: E402
+
+from mujoco_torch_b200 import convex as prod_convex  # noqa: E402
 from tests import util  # noqa: E402
+
+
+# The reference builds its convex-geom tables with trimesh (absent here).  Like the MJCF->MjModel boundary, this
+# preprocessing is therefore supplied by our own host code: the reference's collision code then runs unmodified on it.
+def _mesh_get(m):
+    tabs = prod_convex.build(m._lite)
+    pick = lambda f: [None if t is None else f(t) for t in tabs]
+    return {"geom_convex_face": pick(lambda t: t.face), "geom_convex_vert": pick(lambda t: t.vert),
+            "geom_convex_edge": pick(lambda t: t.edge), "geom_convex_facenormal": pick(lambda t: t.norm)}
+
+
+def _mesh_convex(m, data_id):
+    tabs = prod_convex.build(m._lite)
+    g = next(i for i in range(m.ngeom) if int(m.geom_dataid[i]) == data_id)
+    t = tabs[g]
+    return ref_types.ConvexMesh(torch.tensor(t.vert), torch.tensor(t.vert[t.face]), torch.tensor(t.norm), torch.tensor(t.edge),
+                                torch.zeros((len(t.edge), 2, 3)), batch_size=[])
+
+
+ref_mesh.get = _mesh_get
+ref_mesh.convex = _mesh_convex
+ref_device.mesh.get = _mesh_get
+ref_device.mesh.convex = _mesh_convex
 
 OUT_FIELDS = ["qpos", "qvel", "qacc", "qacc_warmstart", "act", "time", "xpos", "xquat", "xmat", "xipos", "ximat", "xanchor", "xaxis",
               "geom_xpos", "geom_xmat", "subtree_com", "cinert", "crb", "cdof", "cdof_dot", "cvel", "qM", "qLD", "actuator_length",
@@ -57,12 +84,18 @@ CASES = [
     ("swimmer", "swimmer", {}, 3, 0.0, 1),
     ("pendula", "pendula", {}, 3, 0.0, 1),
     ("frictionloss_dof", "frictionloss_dof", {}, 3, 0.0, 1),
+    ("convex", "convex", {}, 4, -1.0, 1),
+    ("shapes", "shapes", {}, 4, -1.0, 1),
+    ("shapes_2steps_elliptic", "shapes", {"cone": 1}, 3, -1.0, 2),
+    ("stack_rk4", "stack", {}, 3, -2.0, 1),
 ]
 
 
 def run_case(name, model, opt, B, drop, nsteps):
     lite = util.load_model(model, **opt)
     qpos, qvel, ctrl = util.seeded_state(lite, B, drop=drop)
+    if drop < 0:  # pile-up state: every free body lowered and tilted so that convex pairs interpenetrate
+        qpos, qvel, ctrl = util.pile_state(lite, B) if drop > -1.5 else util.stack_state(lite, B)
     mx = ref_device.device_put(mujoco.MjModel(lite))
     dx0 = ref_io.make_data(mx)
     outs = {k: [] for k in OUT_FIELDS}

@@ -33,6 +33,43 @@ def seeded_state(mj, B, seed=42, qpos_noise=0.05, qvel_scale=0.5, drop=0.0, ctrl
     return qpos, qvel, c
 
 
+def pile_state(mj, B, seed=3):
+    """Free bodies dropped into a loose pile above the floor: exercises plane-convex and convex-convex contacts."""
+    rng = np.random.RandomState(seed)
+    qpos = np.tile(np.asarray(mj.qpos0), (B, 1))
+    k = 0
+    for j in range(mj.njnt):
+        if int(mj.jnt_type[j]) != 0:
+            continue
+        a = int(mj.jnt_qposadr[j])
+        qpos[:, a:a + 2] += rng.uniform(-0.15, 0.15, size=(B, 2))
+        qpos[:, a + 2] = 0.15 + 0.22 * k + rng.uniform(-0.05, 0.05, size=B)
+        q = rng.randn(B, 4) * 0.3 + np.array([1.0, 0, 0, 0])
+        qpos[:, a + 3:a + 7] = q / np.linalg.norm(q, axis=1, keepdims=True)
+        k += 1
+    qvel = 0.3 * rng.randn(B, mj.nv)
+    return qpos, qvel, rng.uniform(-1, 1, size=(B, mj.nu))
+
+
+def stack_state(mj, B, seed=5):
+    """The model's own resting arrangement, squeezed: each free body sunk a few mm into the one below and yawed/tilted
+    slightly, so that stacked convex pairs are in multi-point face contact."""
+    rng = np.random.RandomState(seed)
+    qpos = np.tile(np.asarray(mj.qpos0), (B, 1))
+    k = 0
+    for j in range(mj.njnt):
+        if int(mj.jnt_type[j]) != 0:
+            continue
+        a = int(mj.jnt_qposadr[j])
+        k += 1
+        qpos[:, a:a + 2] += rng.uniform(-0.01, 0.01, size=(B, 2))
+        qpos[:, a + 2] -= 0.004 * k + rng.uniform(0.0, 0.002, size=B)
+        q = qpos[:, a + 3:a + 7] + rng.randn(B, 4) * 0.01
+        qpos[:, a + 3:a + 7] = q / np.linalg.norm(q, axis=1, keepdims=True)
+    qvel = 0.1 * rng.randn(B, mj.nv)
+    return qpos, qvel, rng.uniform(-1, 1, size=(B, mj.nu))
+
+
 def run_oracle(mj, qpos, qvel, ctrl, dtype=torch.float64, nsteps=1, warm=None):
     from oracle import forward as of
     from oracle import model as om
