@@ -60,6 +60,12 @@ def check_state(m, d):
     return d
 
 
+# Test hook: when set, called as CONTACT_HOOK(m, d) right after the narrowphase.  Parity tests use it to replay the
+# constraint/solver stages on a given contact manifold (the reference's manifold point selection breaks exact ties
+# by rounding noise, see DESIGN.md "Discontinuities"), so downstream stages can be compared on identical contacts.
+CONTACT_HOOK = None
+
+
 def position(m, d):
     d = smooth.kinematics(m, d)
     d = smooth.com_pos(m, d)
@@ -68,6 +74,8 @@ def position(m, d):
     d = smooth.tendon_armature(m, d)
     smooth.factor_m(m, d)
     d = collision.collision(m, d)
+    if CONTACT_HOOK is not None:
+        d = CONTACT_HOOK(m, d)
     d = constraint.make_constraint(m, d)
     d = smooth.transmission(m, d)
     return d

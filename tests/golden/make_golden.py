@@ -86,8 +86,8 @@ CASES = [
     ("frictionloss_dof", "frictionloss_dof", {}, 3, 0.0, 1),
     ("convex", "convex", {}, 4, -1.0, 1),
     ("shapes", "shapes", {}, 4, -1.0, 1),
-    ("shapes_2steps_elliptic", "shapes", {"cone": 1}, 3, -1.0, 2),
-    ("stack_rk4", "stack", {}, 3, -2.0, 1),
+    ("shapes_elliptic", "shapes", {"cone": 1}, 6, -1.0, 1),
+    ("stack_rk4", "stack", {}, 8, -2.0, 1),
 ]
 
 

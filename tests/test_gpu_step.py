@@ -45,6 +45,12 @@ CASES = [
     ("swimmer", {}, 0.0),
     ("pendula", {}, 0.0),
     ("frictionloss_dof", {}, 0.0),
+    # convex narrowphase (drop -1: loose pile of free bodies, drop -2: the model's own stack, squeezed)
+    ("convex", {}, -1.0),
+    ("shapes", {}, -1.0),
+    ("shapes", {"cone": 1}, -1.0),
+    ("stack", {"integrator": 0}, -2.0),
+    ("stack", {"integrator": 0}, -1.0),
 ]
 NPERT = 6
 
@@ -58,19 +64,80 @@ def _env_err(a, b):
     return (a - b).abs().reshape(a.shape[0], -1).amax(1) / scale
 
 
+def _perturbed(qpos, qvel, eps, rng):
+    return qpos * (1 + 16 * eps * rng.randn(*qpos.shape)), qvel * (1 + 16 * eps * rng.randn(*qvel.shape))
+
+
+def _check_manifolds(mj, dc, qpos, qvel, ctrl, tol, eps, min_match):
+    """Convex narrowphase, tie-aware.  The reference picks the 4 manifold points by argmax over quantities that are
+    exactly tied for symmetric polygons (a rectangle: both off-diagonal corners are equally far from the diagonal), so
+    rounding noise decides and the oracle's own manifolds change under few-ulp input changes.  Each CUDA (env, pair)
+    manifold must equal the manifold of the oracle or of one of its perturbed re-runs; primitive pairs must match the
+    unperturbed oracle.  Returns the matched fraction over convex pairs."""
+    rng = np.random.RandomState(11)
+    runs = [util.run_oracle(mj, qpos, qvel, ctrl, torch.float64)]
+    for i in range(2 * NPERT):
+        pq, pv = _perturbed(qpos, qvel, eps, rng)
+        # an f32 kernel sees ties at f32 resolution: half of its comparison runs are the oracle computed in f32
+        runs.append(util.run_oracle(mj, pq, pv, ctrl, torch.float32 if (eps > 1e-10 and i % 2) else torch.float64))
+    mo = runs[0][0]
+    g1, g2 = mo.contact["geom1"], mo.contact["geom2"]
+    gt = torch.as_tensor(np.asarray(mj.geom_type))
+    cd, cp, cf = dc.contact.dist.cpu().double(), dc.contact.pos.cpu().double(), dc.contact.frame.cpu().double()
+    pair_key = g1 * mj.ngeom + g2
+    matched = total = 0
+    for key in pair_key.unique():
+        sl = (pair_key == key).nonzero()[:, 0]
+        convex = bool(gt[g2[sl[0]]] >= 6)
+        ok_any = torch.zeros(cd.shape[0], dtype=torch.bool)
+        for _, dv in (runs if convex else runs[:1]):
+            act = dv.contact_dist[:, sl] < 0
+            e = (cd[:, sl] - dv.contact_dist[:, sl].double()).abs()
+            ep = (cp[:, sl] - dv.contact_pos[:, sl].double()).abs().amax(-1)
+            ef = (cf[:, sl] - dv.contact_frame[:, sl].double()).abs().amax((-1, -2))
+            e = torch.maximum(e, torch.where(act, torch.maximum(ep, ef), torch.zeros_like(ep)))
+            ok_any |= e.amax(1) < 10 * tol
+        if convex:
+            matched += int(ok_any.sum())
+            total += cd.shape[0]
+        else:
+            assert bool(ok_any.all()), f"primitive pair {int(g1[sl[0]])}-{int(g2[sl[0]])} differs from the oracle"
+    frac = matched / max(total, 1)
+    assert frac >= min_match, f"only {matched}/{total} convex manifolds equal an oracle manifold"
+    return frac
+
+
 def _compare(mj, B, dtype, tol, drop):
+    from oracle import forward as oforward
+
     f32 = dtype == torch.float32
     eps = 1e-7 if f32 else 2e-16
-    qpos, qvel, ctrl = util.seeded_state(mj, B, drop=drop)
-    mo, do = util.run_oracle(mj, qpos, qvel, ctrl, dtype)
-    truth = util.run_oracle(mj, qpos, qvel, ctrl, torch.float64)[1] if f32 else do
-    rng = np.random.RandomState(7)
-    variants = [do]
-    for _ in range(NPERT):
-        pq = qpos * (1 + 16 * eps * rng.randn(*qpos.shape))
-        pv = qvel * (1 + 16 * eps * rng.randn(*qvel.shape))
-        variants.append(util.run_oracle(mj, pq, pv, ctrl, dtype)[1])
+    if drop >= 0:
+        qpos, qvel, ctrl = util.seeded_state(mj, B, drop=drop)
+    else:
+        qpos, qvel, ctrl = util.pile_state(mj, B) if drop > -1.5 else util.stack_state(mj, B)
     mx, dc = util.run_cuda(mj, qpos, qvel, ctrl, dtype)
+    if drop < 0:
+        # convex scenes: (A) the manifolds themselves, tie-aware; (B) everything downstream of the narrowphase with the
+        # oracle replaying the CUDA manifolds, so that a tie broken the other way does not mask a real difference
+        _check_manifolds(mj, dc, qpos, qvel, ctrl, tol, eps, 0.8 if f32 else 0.9)
+        cd, cp, cf = dc.contact.dist.cpu(), dc.contact.pos.cpu(), dc.contact.frame.cpu()
+
+        def replay(m, d):
+            d.contact_dist, d.contact_pos, d.contact_frame = (x.to(d.qpos.dtype) for x in (cd, cp, cf))
+            return d
+
+        oforward.CONTACT_HOOK = replay
+    try:
+        mo, do = util.run_oracle(mj, qpos, qvel, ctrl, dtype)
+        truth = util.run_oracle(mj, qpos, qvel, ctrl, torch.float64)[1] if f32 else do
+        rng = np.random.RandomState(7)
+        variants = [do]
+        for _ in range(NPERT):
+            pq, pv = _perturbed(qpos, qvel, eps, rng)
+            variants.append(util.run_oracle(mj, pq, pv, ctrl, dtype)[1])
+    finally:
+        oforward.CONTACT_HOOK = None
 
     # ---- structure: sizes -- exact
     assert (mx.ne, mx.nf, mx.nl, mx.ncon, mx.nefc) == (mo.ne, mo.nf, mo.nl, mo.ncon, mo.nefc)
@@ -93,13 +160,14 @@ def _compare(mj, B, dtype, tol, drop):
             e_c, e_o = _env_err(getattr(dc, k), getattr(truth, k)), _env_err(getattr(do, k), getattr(truth, k))
             outlier |= e_c > torch.clamp(4 * e_o, min=tol)
         else:
-            outlier |= _env_err(getattr(dc, k), getattr(do, k)) > tol
+            # an env whose oracle answer already moves by `spread` under few-ulp input changes is allowed 10x that
+            outlier |= _env_err(getattr(dc, k), getattr(do, k)) > torch.clamp(10 * spread, min=tol)
     if mo.nefc:  # the constraint force is the most sensitive witness of a line-search branch flip
         fscale = max(float(do.qfrc_smooth.abs().max()), 1e-6)
         ref = truth.qfrc_constraint.double()
         e_c = (dc.qfrc_constraint.cpu().double() - ref).abs().amax(1) / fscale
         e_o = (do.qfrc_constraint.double() - ref).abs().amax(1) / fscale
-        outlier |= e_c > torch.clamp(4 * e_o, min=10 * tol)
+        outlier |= e_c > torch.maximum(torch.clamp(4 * e_o, min=10 * tol), 100 * spread)
     n_unst, n_extra = int(unstable.sum()), int((outlier & ~unstable).sum())
     allowed = n_unst + (2 if n_unst else 0) + (B // 20 if f32 else 0)
     assert n_unst <= 0.35 * B, f"too many oracle-unstable envs: {n_unst}/{B}"
@@ -119,8 +187,9 @@ def _compare(mj, B, dtype, tol, drop):
                 bad[name] = (float(e_c[over].max()), float(e_o[over].max()))
         else:
             e = _env_err(a, b)
-            if float(e[sel].max()) > tol * factor:
-                bad[name] = float(e[sel].max())
+            over = (e > torch.clamp(10 * spread, min=tol * factor)) & sel
+            if over.any():
+                bad[name] = float(e[over].max())
 
     degenerate_env = torch.zeros(B, dtype=torch.bool)
     if mo.ncon:
@@ -134,10 +203,15 @@ def _compare(mj, B, dtype, tol, drop):
         near = (do.contact_dist - inc).abs() < 32 * eps * (1 + do.contact_dist.abs())
         assert torch.equal(act_o | near, act_c | near), "active contact set differs"
         check("contact.dist", dc.contact.dist, do.contact_dist)
-        check("contact.pos", dc.contact.pos, do.contact_pos)
+        gt = torch.as_tensor(np.asarray(mj.geom_type))
+        # slots of convex pairs that are inactive carry an arbitrary (tie-broken) manifold point: compare active ones only
+        convex_slot = gt[mo.contact["geom2"]] >= 6
+        pe = (dc.contact.pos.cpu().double() - do.contact_pos.double()).abs().amax(-1) / max(float(do.contact_pos.abs().max()), 1e-6)
+        pe = torch.where(convex_slot[None, :] & ~act_o, torch.zeros_like(pe), pe).amax(1)
+        if float(pe[ok].max()) > 10 * tol:
+            bad["contact.pos"] = float(pe[ok].max())
         gs = torch.as_tensor(np.asarray(mj.geom_size))[:, 0]
         rsum = gs[mo.contact["geom1"]] + gs[mo.contact["geom2"]]
-        gt = torch.as_tensor(np.asarray(mj.geom_type))
         round_pair = (gt[mo.contact["geom1"]] >= 2) & (gt[mo.contact["geom1"]] <= 3) & (gt[mo.contact["geom2"]] >= 2) & (gt[mo.contact["geom2"]] <= 3)
         degen = round_pair[None, :] & ((do.contact_dist.double() + rsum[None, :]).abs() < 1e-5)
         fe = (dc.contact.frame.cpu().double() - do.contact_frame.double()).abs().amax((-1, -2))
@@ -163,7 +237,7 @@ def _compare(mj, B, dtype, tol, drop):
         ref = truth.qfrc_constraint.double()
         e_c = (dc.qfrc_constraint.cpu().double() - ref).abs().amax(1) / fscale
         e_o = (do.qfrc_constraint.double() - ref).abs().amax(1) / fscale
-        lim = torch.clamp(4 * e_o, min=10 * tol)
+        lim = torch.maximum(torch.clamp(4 * e_o, min=10 * tol), 100 * spread)
         if ((e_c > lim) & ok).any():
             bad["qfrc_constraint"] = float(e_c[(e_c > lim) & ok].max())
     for k in FIELDS_STATE:
@@ -179,3 +253,23 @@ def test_step_f64(name, opt, drop):
 @pytest.mark.parametrize("name,opt,drop", CASES, ids=[f"{c[0]}-{i}" for i, c in enumerate(CASES)])
 def test_step_f32(name, opt, drop):
     _compare(util.load_model(name, **opt), 64, torch.float32, 1e-4, drop)
+
+
+def test_stack_rk4_step():
+    """BASELINE config 5 (box stack, RK4): four narrowphase passes per step, so the oracle cannot replay the CUDA manifolds.
+    Every env must land on the trajectory of the oracle or of one of its few-ulp perturbed re-runs (see _check_manifolds)."""
+    mj = util.load_model("stack")
+    B = 48
+    qpos, qvel, ctrl = util.stack_state(mj, B)
+    mx, dc = util.run_cuda(mj, qpos, qvel, ctrl, torch.float64)
+    rng = np.random.RandomState(3)
+    best = torch.full((B,), float("inf"), dtype=torch.float64)
+    for i in range(2 * NPERT + 1):
+        pq, pv = (qpos, qvel) if i == 0 else _perturbed(qpos, qvel, 2e-16, rng)
+        dv = util.run_oracle(mj, pq, pv, ctrl, torch.float64)[1]
+        e = torch.zeros(B, dtype=torch.float64)
+        for k in ("qpos", "qvel", "qacc"):
+            e = torch.maximum(e, _env_err(getattr(dc, k), getattr(dv, k)))
+        best = torch.minimum(best, e)
+    frac = float((best < 1e-8).float().mean())
+    assert frac >= 0.75, f"only {frac:.2f} of envs follow an oracle trajectory; worst {float(best.max()):.2e}"
