@@ -29,7 +29,6 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 PUBLISHED = {("humanoid", "f64", 65536): 2333178.0}  # H200, compile tuned (reference README.md:190)
-RESET_NOISE = {"humanoid": 0.01, "ant": 0.1, "ant_zoo": 0.1, "halfcheetah": 0.1}
 # minimal state I/O words per env-step: read qpos,qvel,ctrl,warmstart,time(+act); write qpos,qvel,qacc,warmstart,time(+act)
 
 
@@ -52,18 +51,20 @@ def load_model(name, args):
     return mj
 
 
-def initial_state(mj, name, B, seed):
-    """Synthetic randomised initial states: qpos0 + U(-s, s), qvel = 0.01 N(0,1); half of the envs of
-    free-root models start lowered so that contacts are active from the first step."""
-    rng = np.random.RandomState(seed)
-    s = RESET_NOISE.get(name, 0.05)
-    qpos = np.tile(np.asarray(mj.qpos0), (B, 1)) + rng.uniform(-s, s, size=(B, mj.nq))
-    qvel = 0.01 * rng.randn(B, mj.nv)
-    if mj.njnt and int(mj.jnt_type[0]) == 0:
-        drop = rng.uniform(0.0, 0.35, size=B) * (rng.rand(B) < 0.5)
-        qpos[:, 2] -= drop
-    ctrl = rng.uniform(-1, 1, size=(4, B, mj.nu))
-    return qpos, qvel, ctrl
+def initial_state(mj, name, B, rank=0):
+    """Synthetic randomised initial states of this rank's env shard (mujoco_torch_b200/sharding.py)."""
+    from mujoco_torch_b200 import sharding
+
+    return sharding.initial_state(mj, name, rank * B, (rank + 1) * B, seed=42)
+
+
+def measured_traffic(kernel, model, dtype, B):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/traffic.json), or None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return t.get(f"{kernel}:{model}:{dtype}:{B}")
+    except Exception:  # noqa: BLE001
+        return None
 
 
 class ClockSampler:
@@ -116,7 +117,7 @@ def oracle_rate(mj, name, B, nsteps, threads):
 
     torch.set_num_threads(threads)
     m = om.OModel(mj, torch.float64)
-    qpos, qvel, ctrl = initial_state(mj, name, B, 42)
+    qpos, qvel, ctrl = initial_state(mj, name, B)
     d = of.make_data(m, B)
     d.qpos, d.qvel = torch.as_tensor(qpos), torch.as_tensor(qvel)
     d.ctrl = torch.as_tensor(ctrl[0])
@@ -204,7 +205,7 @@ def main():
     mj = load_model(args.model, args)
     B = args.batch
     mx = mt.device_put(mj, dtype=dtype).to(dev)
-    qpos, qvel, ctrl = initial_state(mj, args.model, B, 42 + rank)  # seeds offset by rank: the union is one big batch
+    qpos, qvel, ctrl = initial_state(mj, args.model, B, rank)  # rank r owns global envs [r*B, (r+1)*B)
     d0 = mt.make_data(mx).expand(B).clone()
     d0 = d0.replace(qpos=torch.as_tensor(qpos, device=dev).to(dtype), qvel=torch.as_tensor(qvel, device=dev).to(dtype))
     ctrls = [torch.as_tensor(c, device=dev).to(dtype).t().contiguous().t() for c in ctrl]  # env-minor resident ctrl
@@ -232,10 +233,9 @@ def main():
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
     finite = bool(torch.isfinite(d.qpos).all())
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if dist:
-        td.all_reduce(t, op=td.ReduceOp.MAX)
-    ms_max = float(t.item())
+    from mujoco_torch_b200 import sharding
+
+    ms_max = sharding.max_over_ranks(ms, dev)
     value = world * B * args.steps / (ms_max * 1e-3)
 
     # ---- per-kernel device timing for the roofline (same state, a few extra steps)
@@ -256,7 +256,7 @@ def main():
     abytes = algorithmic_bytes(mj, tsize) * B
     ach = abytes / (per_step[top] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
+                "traffic": measured_traffic(top, args.model, args.dtype, B), "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
                 "algorithmic_bytes_per_env_step": algorithmic_bytes(mj, tsize),
                 "kernel_ms_per_step": per_step, "kernel_share": {k: v / sum(per_step.values()) for k, v in per_step.items()}}
 
@@ -281,15 +281,14 @@ def main():
             e2e_step()
         barrier()
         n_e2e = max(5, min(args.steps, 30))
-        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         for _ in range(n_e2e):
             e2e_step()
+        e1.record()
         barrier()
-        el = time.perf_counter() - t0
-        te = torch.tensor([el], device=dev, dtype=torch.float64)
-        if dist:
-            td.all_reduce(te, op=td.ReduceOp.MAX)
-        e2e = {"value": world * B * n_e2e / float(te.item()), "unit": "env-steps/s", "h2d_bytes_per_step": nb_in,
+        el = sharding.max_over_ranks(e0.elapsed_time(e1), dev) * 1e-3
+        e2e = {"value": world * B * n_e2e / el, "unit": "env-steps/s", "h2d_bytes_per_step": nb_in,
                "d2h_bytes_per_step": nb_out, "steps": n_e2e}
 
     if rank != 0:
@@ -309,7 +308,7 @@ def main():
     line = {
         "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": (value / pub / world) if pub else None, "dtype": args.dtype, "data": "synthetic",
+        "vs_baseline": (value / pub) if pub else None, "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": workload_name(args, mj), "batch_per_gpu": B, "parallelism": f"dp{world} (envs sharded, no collective)",
                    "l2": f"per-step working set {mx.data_words * B * tsize / 1e6:.0f} MB > 126 MB L2 (inputs larger than L2)",
                    "nv": mj.nv, "ncon": mx.ncon, "nefc": mx.nefc},

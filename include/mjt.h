@@ -29,7 +29,8 @@ typedef struct mjtModel mjtModel;
  * ctrl (nu), qfrc_applied (nv), xfrc_applied (6*nbody), mocap_pos (3*nmocap), mocap_quat (4*nmocap),
  * sensordata (nsensordata; slots of sensor types without an implementation pass through), qfrc_constraint (nv;
  * only read when the model has no constraint rows), eq_active (neq, int32).  qacc is accepted for symmetry with
- * the reference's _check_state but never influences the result. */
+ * the reference's _check_state but never influences the result.  qpos, qvel, time (and ctrl when nu > 0) are
+ * required; any other pointer may be NULL, which reads as zeros (eq_active: as "every equality active"). */
 typedef struct mjtStateIn {
   const void* qpos;
   const void* qvel;

@@ -142,7 +142,7 @@ __device__ void constraint_source(const ModelView<T>& m, const MjtIn& in, const 
       const int j2 = j2raw < 0 ? njnt + j2raw : j2raw;
       const T has2 = j2raw > -1 ? T(1) : T(0);
       const T* data = m.F(F_eq_data) + 11 * id;
-      const T active = T(in.eq_active[(size_t)id * B + env]);
+      const T active = in.eq_active ? T(in.eq_active[(size_t)id * B + env]) : T(1);
       const int qa1 = m.I(I_jnt_qposadr)[j1], da1 = m.I(I_jnt_dofadr)[j1], qa2 = m.I(I_jnt_qposadr)[j2], da2 = m.I(I_jnt_dofadr)[j2];
       const T pos1 = d.get(oQpos + qa1), pos2 = d.get(oQpos + qa2) * has2;
       const T ref1 = m.F(F_qpos0)[qa1], ref2 = m.F(F_qpos0)[qa2] * has2;
@@ -166,7 +166,7 @@ __device__ void constraint_source(const ModelView<T>& m, const MjtIn& in, const 
       const bool weld = type == SRC_EQ_WELD;
       const int b1 = m.I(I_eq_obj1)[id], b2 = m.I(I_eq_obj2)[id];
       const T* data = m.F(F_eq_data) + 11 * id;
-      const T active = T(in.eq_active[(size_t)id * B + env]);
+      const T active = in.eq_active ? T(in.eq_active[(size_t)id * B + env]) : T(1);
       const V3<T> anchor1(data[0], data[1], data[2]), anchor2(data[3], data[4], data[5]);
       V3<T> x1, x2;
       T R1[9], R2[9];

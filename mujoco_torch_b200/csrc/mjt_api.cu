@@ -264,6 +264,8 @@ static int run_step(const mjtModel* m, const MjtIn& in, T* out, T* scratch, int 
 static int check_args(const mjtModel* m, const mjtStateIn* in, void* out, int nenv) {
   if (!m || !in || !out) return fail("mjt: null argument");
   if (nenv <= 0) return fail("mjt: nenv must be positive");
+  if (!in->qpos || !in->qvel || !in->time) return fail("mjt: qpos, qvel and time are required inputs");
+  if (m->hv(H_nu) > 0 && !in->ctrl) return fail("mjt: ctrl is required for a model with actuators");
   cudaError_t e = cudaSetDevice(m->device);
   if (e != cudaSuccess) return fail(std::string("cudaSetDevice: ") + cudaGetErrorString(e));
   return 0;

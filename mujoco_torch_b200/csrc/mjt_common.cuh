@@ -105,7 +105,8 @@ struct EnvBuf {
 
 template <typename T>
 __device__ __forceinline__ T in_get(const void* base, size_t B, int env, int k) {
-  return reinterpret_cast<const T*>(base)[(size_t)k * B + env];
+  // optional inputs may be NULL: they read as zero (include/mjt.h)
+  return base ? reinterpret_cast<const T*>(base)[(size_t)k * B + env] : T(0);
 }
 
 // ---------------------------------------------------------------------------------------------------------
