@@ -1,4 +1,4 @@
-// k_collision: one thread per (candidate pair, env); grid.y walks the static pair table.
+// k_collision: one thread per (candidate pair, env); grid.x walks the static pair table, grid.y the env blocks.
 // Narrowphase for plane/sphere/capsule primitives (reference collision_primitive.py:29-75,172-221 and the
 // geometry helpers math.py:496-569).  Each pair writes its contacts straight to their final slots: the
 // reference's concat + argsort-by-condim (collision_driver.py:815-850) is a static permutation baked into
@@ -140,13 +140,14 @@ __device__ void collide_pair(const ModelView<T>& m, const EnvBuf<T>& d, int p) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(128) k_collision(const int* __restrict__ gblob, int blob_words, T* __restrict__ out, int B) {
+__global__ void __launch_bounds__(MJT_ENV_THREADS) k_collision(const int* __restrict__ gblob, int blob_words, T* __restrict__ out, int B) {
   extern __shared__ __align__(16) int smem_blob[];
   __shared__ uint64_t bar;
   stage_blob(smem_blob, &bar, gblob, blob_words);
   const ModelView<T> m = make_view<T>(smem_blob);
-  const int env = blockIdx.x * blockDim.x + threadIdx.x;
-  if (env >= B) return;
-  EnvBuf<T> d{out + env, (size_t)B};
-  for (int p = blockIdx.y; p < m.h(H_npair_cand); p += gridDim.y) collide_pair<T>(m, d, p);
+  // grid.x walks the candidate pairs (fastest), grid.y the env blocks (see k_constraint)
+  for (int env = blockIdx.y * blockDim.x + threadIdx.x; env < B; env += gridDim.y * blockDim.x) {
+    EnvBuf<T> d{out + env, (size_t)B};
+    for (int p = blockIdx.x; p < m.h(H_npair_cand); p += gridDim.x) collide_pair<T>(m, d, p);
+  }
 }

@@ -307,13 +307,15 @@ __device__ void constraint_source(const ModelView<T>& m, const MjtIn& in, const 
 }
 
 template <typename T>
-__global__ void __launch_bounds__(128) k_constraint(const int* __restrict__ gblob, int blob_words, MjtIn in, T* __restrict__ out, int B) {
+__global__ void __launch_bounds__(MJT_ENV_THREADS, MJT_CONSTRAINT_MINB) k_constraint(const int* __restrict__ gblob, int blob_words, MjtIn in, T* __restrict__ out, int B) {
   extern __shared__ __align__(16) int smem_blob[];
   __shared__ uint64_t bar;
   stage_blob(smem_blob, &bar, gblob, blob_words);
   const ModelView<T> m = make_view<T>(smem_blob);
-  const int env = blockIdx.x * blockDim.x + threadIdx.x;
-  if (env >= B) return;
-  EnvBuf<T> d{out + env, (size_t)B};
-  for (int s = blockIdx.y; s < m.h(H_nsrc); s += gridDim.y) constraint_source<T>(m, in, d, (size_t)B, env, s);
+  // grid.x walks the row sources (fastest), grid.y the env blocks: all sources of one env block are co-resident, so
+  // the kinematic quantities they share (cdof, xpos, contact frames) are read from DRAM once and then hit in L2
+  for (int env = blockIdx.y * blockDim.x + threadIdx.x; env < B; env += gridDim.y * blockDim.x) {
+    EnvBuf<T> d{out + env, (size_t)B};
+    for (int s = blockIdx.x; s < m.h(H_nsrc); s += gridDim.x) constraint_source<T>(m, in, d, (size_t)B, env, s);
+  }
 }

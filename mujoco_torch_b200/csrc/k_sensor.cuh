@@ -154,7 +154,7 @@ __device__ void sensor_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<
 }
 
 template <typename T>
-__global__ void __launch_bounds__(128) k_sensor(const int* __restrict__ gblob, int blob_words, MjtIn in, T* __restrict__ out, int B, int stage_mask) {
+__global__ void __launch_bounds__(MJT_ENV_THREADS) k_sensor(const int* __restrict__ gblob, int blob_words, MjtIn in, T* __restrict__ out, int B, int stage_mask) {
   extern __shared__ __align__(16) int smem_blob[];
   __shared__ uint64_t bar;
   stage_blob(smem_blob, &bar, gblob, blob_words);
@@ -192,7 +192,7 @@ __device__ __forceinline__ void integrate_pos(const ModelView<T>& m, const EnvBu
 }
 
 template <typename T>
-__global__ void __launch_bounds__(128) k_rk4_stage(const int* __restrict__ gblob, int blob_words, T* __restrict__ t0, T* __restrict__ prev,
+__global__ void __launch_bounds__(MJT_ENV_THREADS) k_rk4_stage(const int* __restrict__ gblob, int blob_words, T* __restrict__ t0, T* __restrict__ prev,
                                                    T* __restrict__ tail, int B, int stage) {
   extern __shared__ __align__(16) int smem_blob[];
   __shared__ uint64_t bar;

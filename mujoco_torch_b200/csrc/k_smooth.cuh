@@ -633,7 +633,7 @@ __device__ void smooth_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<
 }
 
 template <typename T>
-__global__ void __launch_bounds__(128) k_smooth(const int* __restrict__ gblob, int blob_words, MjtIn in, T* __restrict__ out, int B) {
+__global__ void __launch_bounds__(MJT_ENV_THREADS, MJT_SMOOTH_MINB) k_smooth(const int* __restrict__ gblob, int blob_words, MjtIn in, T* __restrict__ out, int B) {
   extern __shared__ __align__(16) int smem_blob[];
   __shared__ uint64_t bar;
   stage_blob(smem_blob, &bar, gblob, blob_words);

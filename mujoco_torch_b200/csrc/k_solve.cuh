@@ -12,6 +12,13 @@
 // every data-dependent branch (active rows, line-search bracketing, early exit) is warp-uniform: inactive rows and
 // converged envs cost nothing -- the per-env early exit the reference's masked while_loop emulates.
 #pragma once
+// f64 launch shape of k_solve: threads per CTA (= 32 x envs per CTA) and minimum CTAs per SM (caps registers/thread)
+#ifndef MJT_SOLVE_F64_THREADS
+#define MJT_SOLVE_F64_THREADS 256
+#endif
+#ifndef MJT_SOLVE_F64_MINB
+#define MJT_SOLVE_F64_MINB 2
+#endif
 #include "mjt_common.cuh"
 #include "k_smooth.cuh"
 
@@ -41,6 +48,15 @@ __host__ __device__ inline SolveLayout solve_layout(int nv, int nefc, int jc_wor
   return s;
 }
 
+// 4/8-byte asynchronous global->shared copy (LDGSTS): no staging register, so a thread keeps all its copies in flight
+template <typename T>
+__device__ __forceinline__ void cp_async_word(T* smem_dst, const T* gsrc) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  if (sizeof(T) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 template <typename T, int DPL>
 struct Vec {
   T v[DPL];
@@ -69,6 +85,7 @@ struct SolveCtx {
   const int* src_row;
   const int* src_nrows;
   const int* sup_col;
+  const int* tri_ab;
 
   __device__ __forceinline__ T* Jc() const { return s + L.oJ; }
   __device__ __forceinline__ T* Mp() const { return s + L.oM; }
@@ -159,7 +176,41 @@ struct SolveCtx {
   // In-place Cholesky of a packed lower triangle; reciprocal pivots go to dinv().
   // Numeric conventions of reference math.small_cholesky :87-129: n <= 16 clamps each pivot at 1e-12,
   // n > 16 adds 1e-10 to the diagonal (the torch.linalg.cholesky fallback path).
+  // n <= 32 (one row per lane): lane i keeps row i of L in registers, so the inner product reads only row j from
+  // shared memory (a broadcast) instead of two strided rows
+  __device__ __forceinline__ void cholesky_rows(T* A) const {
+    const int n = nv;
+    const bool big = n > 16;
+    T* di = dinv();
+    T r[32];
+    const bool mine = lane < n;
+    T* rowi = A + tri(mine ? lane : 0);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j < n) {
+        const T* rowj = A + tri(j);
+        T acc = (mine && lane >= j) ? rowi[j] : T(0), acc2 = T(0);
+#pragma unroll
+        for (int k = 0; k + 1 < j; k += 2) {
+          acc -= r[k] * rowj[k];
+          acc2 -= r[k + 1] * rowj[k + 1];
+        }
+        if (j & 1) acc -= r[j - 1] * rowj[j - 1];
+        acc += acc2;
+        T sdiag = __shfl_sync(0xffffffffu, acc, j);
+        if (big) sdiag += T(1e-10); else sdiag = t_max(sdiag, T(1e-12));
+        const T inv = t_rsqrt(sdiag);
+        const T lij = (lane == j) ? sdiag * inv : acc * inv;
+        r[j] = lane >= j ? lij : T(0);
+        __syncwarp();
+        if (mine && lane >= j) rowi[j] = lij;
+        if (lane == 0) di[j] = inv;
+        __syncwarp();
+      }
+    }
+  }
   __device__ __forceinline__ void cholesky(T* A) const {
+    if (DPL == 1) { cholesky_rows(A); return; }
     const int n = nv;
     const bool big = n > 16;
     T* di = dinv();
@@ -217,6 +268,14 @@ struct SolveCtx {
     }
     return x;
   }
+  // bits r0 .. r0+nr-1 (nr <= 32) of the active-row mask
+  __device__ __forceinline__ unsigned active_bits(int r0, int nr) const {
+    const unsigned* am = amask();
+    const int w = r0 >> 5, sh = r0 & 31;
+    const unsigned lo = am[w], hi = (sh && w + 1 < L.nchunk) ? am[w + 1] : 0u;
+    const unsigned v = __funnelshift_r(lo, hi, sh);
+    return nr >= 32 ? v : (v & ((1u << nr) - 1u));
+  }
   // Lp <- Mp + sum over active rows r of D_r J_r^T J_r, source by source over the packed support pairs
   __device__ __forceinline__ void hessian(const T* D) const {
     T* H = Lp();
@@ -226,23 +285,31 @@ struct SolveCtx {
     const int nsrc = m.h(H_nsrc);
     for (int sidx = 0; sidx < nsrc; ++sidx) {
       const int r0 = src_row[sidx], nr = src_nrows[sidx];
-      bool any = false;
-      for (int e = 0; e < nr; ++e) any |= row_active(r0 + e);
-      if (!any) continue;
+      unsigned act = 0;
+      if (nr <= 32) act = active_bits(r0, nr);
+      else for (int e = 0; e < nr; ++e) act |= row_active(r0 + e) ? 1u : 0u;
+      if (!act) continue;
       const int ns = src_nsup[sidx];
       const int* col = sup_col + src_cadr[sidx];
       const int npair = (ns * (ns + 1)) >> 1;
+      const T* j0 = Jc() + row_jadr[r0];   // rows of one source are stored back to back, ns entries each
       for (int p = lane; p < npair; p += 32) {
-        int a = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
-        while (tri(a + 1) <= p) ++a;
-        while (tri(a) > p) --a;
-        const int b = p - tri(a);
+        const int ab = tri_ab[p], a = ab & 0xffff, b = ab >> 16;
         T acc = 0;
-        for (int e = 0; e < nr; ++e) {
-          const int r = r0 + e;
-          if (!row_active(r)) continue;
-          const T* jr = Jc() + row_jadr[r];
-          acc += D[r] * jr[a] * jr[b];
+        if (nr <= 32) {
+          unsigned mk = act;
+          while (mk) {
+            const int e = __ffs(mk) - 1;
+            mk &= mk - 1;
+            const T* jr = j0 + e * ns;
+            acc += D[r0 + e] * jr[a] * jr[b];
+          }
+        } else {
+          for (int e = 0; e < nr; ++e) {
+            if (!row_active(r0 + e)) continue;
+            const T* jr = j0 + e * ns;
+            acc += D[r0 + e] * jr[a] * jr[b];
+          }
         }
         H[tri(col[a]) + col[b]] += acc;  // support columns are sorted ascending: col[a] >= col[b]
       }
@@ -660,7 +727,7 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
 }
 
 template <typename T, int DPL>
-__global__ void __launch_bounds__(512, (sizeof(T) == 4 ? 2 : 1)) k_solve(const int* __restrict__ gfull, const int* __restrict__ gblob, int blob_words, MjtIn in,
+__global__ void __launch_bounds__((sizeof(T) == 4 ? 512 : MJT_SOLVE_F64_THREADS), (sizeof(T) == 4 ? 2 : MJT_SOLVE_F64_MINB)) k_solve(const int* __restrict__ gfull, const int* __restrict__ gblob, int blob_words, MjtIn in,
                                                T* __restrict__ out, int B, int mode) {
   extern __shared__ __align__(16) int smem_blob[];
   __shared__ uint64_t bar;
@@ -674,42 +741,39 @@ __global__ void __launch_bounds__(512, (sizeof(T) == 4 ? 2 : 1)) k_solve(const i
   T* region = reinterpret_cast<T*>(smem_blob + ((blob_words + 3) & ~3));
   const size_t Bs = (size_t)B;
 
-  // ---- cooperative, env-contiguous loads (E consecutive envs share every word's cache line; E is a power of two)
-  const int esh = __ffs(E) - 1, emask = E - 1;
+  // ---- cooperative, env-contiguous loads: thread t serves env t % E, so E consecutive envs share every word's cache line
+  const int ce = threadIdx.x % E, ck0 = threadIdx.x / E, cks = blockDim.x / E;
+  const bool cvalid = env0 + ce < B;
+  T* const crg = region + (size_t)ce * Lo.words;
+  T* const cout = out + env0 + ce;
   const int* tri_src = gfull + gfull[MJT_OFF_I + I_tri_src];   // packed lower index -> dense word i*nv+j (global, L1 resident)
   {
     const int oM = m.D(D_qM);
-    for (int idx = threadIdx.x; idx < (Lo.nP << esh); idx += blockDim.x) {
-      const int e = idx & emask, p = idx >> esh;
-      if (env0 + e < B) region[(size_t)e * Lo.words + Lo.oM + p] = out[(size_t)(oM + tri_src[p]) * Bs + env0 + e];
-    }
+    if (cvalid)
+      for (int p = ck0; p < Lo.nP; p += cks) cp_async_word(crg + Lo.oM + p, cout + (size_t)(oM + tri_src[p]) * Bs);
     if (nefc) {
       const int oJ = m.D(D_efc_J), jcw = m.h(H_jc_words);
       const int* jsrc = gfull + gfull[MJT_OFF_I + I_jc_src];   // compact J entry -> dense word row*nv+col
-      for (int idx = threadIdx.x; idx < (jcw << esh); idx += blockDim.x) {
-        const int e = idx & emask, k = idx >> esh;
-        if (env0 + e < B) region[(size_t)e * Lo.words + Lo.oJ + k] = out[(size_t)(oJ + jsrc[k]) * Bs + env0 + e];
-      }
+      if (cvalid)
+        for (int k = ck0; k < jcw; k += cks) cp_async_word(crg + Lo.oJ + k, cout + (size_t)(oJ + jsrc[k]) * Bs);
       const int oD = m.D(D_efc_D), oA = m.D(D_efc_aref), oF = m.D(D_efc_frictionloss);
       const bool hasf = m.h(H_nf) > 0;
-      for (int idx = threadIdx.x; idx < (nefc << esh); idx += blockDim.x) {
-        const int e = idx & emask, k = idx >> esh;
-        if (env0 + e < B) {
-          T* rg = region + (size_t)e * Lo.words;
-          rg[Lo.oD + k] = out[(size_t)(oD + k) * Bs + env0 + e];
-          rg[Lo.oAref + k] = out[(size_t)(oA + k) * Bs + env0 + e];
-          if (hasf) rg[Lo.oFloss + k] = out[(size_t)(oF + k) * Bs + env0 + e];
+      if (cvalid)
+        for (int k = ck0; k < nefc; k += cks) {
+          cp_async_word(crg + Lo.oD + k, cout + (size_t)(oD + k) * Bs);
+          cp_async_word(crg + Lo.oAref + k, cout + (size_t)(oA + k) * Bs);
+          if (hasf) cp_async_word(crg + Lo.oFloss + k, cout + (size_t)(oF + k) * Bs);
         }
-      }
     }
   }
+  cp_async_wait_all();
   __syncthreads();
 
   const int env = env0 + warp;
   const bool valid = env < B;
   EnvBuf<T> d{out + (valid ? env : 0), Bs};
   SolveCtx<T, DPL> c{m, region + (size_t)warp * Lo.words, Lo, nv, nefc, lane,
-                     m.I(I_row_src), m.I(I_row_jadr), m.I(I_src_nsup), m.I(I_src_cadr), m.I(I_src_row), m.I(I_src_nrows), m.I(I_sup_col)};
+                     m.I(I_row_src), m.I(I_row_jadr), m.I(I_src_nsup), m.I(I_src_cadr), m.I(I_src_row), m.I(I_src_nrows), m.I(I_sup_col), m.I(I_tri_ab)};
   Vec<T, DPL> qfrc_smooth = c.zero(), qacc_smooth = c.zero();
   if (valid) {
     // ---- factor_m + qacc_smooth
@@ -728,13 +792,9 @@ __global__ void __launch_bounds__(512, (sizeof(T) == 4 ? 2 : 1)) k_solve(const i
   {  // cooperative store of qLD = chol(M) (dense lower, zeros above the diagonal)
     const int oL = m.D(D_qLD);
     const int* triu_src = gfull + gfull[MJT_OFF_I + I_triu_src];
-    for (int idx = threadIdx.x; idx < (Lo.nP << esh); idx += blockDim.x) {
-      const int e = idx & emask, p = idx >> esh;
-      if (env0 + e < B) out[(size_t)(oL + tri_src[p]) * Bs + env0 + e] = region[(size_t)e * Lo.words + Lo.oL + p];
-    }
-    for (int idx = threadIdx.x; idx < ((Lo.nP - nv) << esh); idx += blockDim.x) {
-      const int e = idx & emask, p = idx >> esh;
-      if (env0 + e < B) out[(size_t)(oL + triu_src[p]) * Bs + env0 + e] = T(0);
+    if (cvalid) {
+      for (int p = ck0; p < Lo.nP; p += cks) cout[(size_t)(oL + tri_src[p]) * Bs] = crg[Lo.oL + p];
+      for (int p = ck0; p < Lo.nP - nv; p += cks) cout[(size_t)(oL + triu_src[p]) * Bs] = T(0);
     }
   }
   __syncthreads();

@@ -103,15 +103,21 @@ extern "C" int mjt_model_create(const void* blob_host, size_t nbytes, int device
   const size_t sm_total = (size_t)prop.sharedMemPerMultiprocessor;
   int best_e = 0;
   size_t best_warps = 0;
-  for (int e = 16; e >= 1; e >>= 1) {
+  // f64 kernel: MJT_SOLVE_F64_THREADS x MJT_SOLVE_F64_MINB threads fit the register file; f32 kernel: 2 x 512
+  const int emax = m->f64 ? MJT_SOLVE_F64_THREADS / 32 : 16;
+  const size_t wcap = m->f64 ? (size_t)(MJT_SOLVE_F64_THREADS / 32) * MJT_SOLVE_F64_MINB : 32;
+  for (int e = emax; e >= 1; e = (e > 4 && (e & (e - 1))) ? e - 2 : e >> 1) {   // 16 8 4 2 1 or 12 10 8 4 2 1 ...
     const size_t need = sblob_b + region * e + 1024;
     if (need > (size_t)m->max_smem) continue;
     size_t ctas = sm_total / need;
     if (ctas > 32) ctas = 32;
     size_t warps = ctas * e;
-    const size_t wcap = m->f64 ? 16 : 32;  // f64 kernel: <= 128 regs/thread (16 warps/SM); f32 kernel: <= 64 regs (32 warps/SM)
     if (warps > wcap) warps = wcap;
     if (warps > best_warps) { best_warps = warps; best_e = e; }
+  }
+  if (const char* force = getenv("MJT_SOLVE_E")) {   // tuning knob: force envs per CTA
+    const int e = atoi(force);
+    if (e >= 1 && e <= emax && sblob_b + region * e + 1024 <= (size_t)m->max_smem) best_e = e;
   }
   if (best_e == 0) {
     delete m;
@@ -170,7 +176,7 @@ static int set_smem(const void* fn, size_t bytes) {
 // one forward pass (optionally followed by the in-kernel integrator) into `out`
 template <typename T>
 static int run_forward(const mjtModel* m, const MjtIn& in, T* out, int B, int mode, cudaStream_t st, int* launches) {
-  const int threads = 128;
+  const int threads = MJT_ENV_THREADS;
   const int gx = (B + threads - 1) / threads;
   const size_t blob_b = ((size_t)m->blob_words + 3) / 4 * 16;
   const int nsens = m->hv(H_nsensordata);
@@ -180,13 +186,13 @@ static int run_forward(const mjtModel* m, const MjtIn& in, T* out, int B, int mo
   ++n;
   if (m->hv(H_npair_cand) > 0) {
     if (set_smem<T>((const void*)k_collision<T>, blob_b)) return 1;
-    dim3 grid(gx, m->hv(H_npair_cand) < 65535 ? m->hv(H_npair_cand) : 65535);
+    dim3 grid(m->hv(H_npair_cand), gx < 65535 ? gx : 65535);
     LAUNCH("k_collision", st, k_collision<T><<<grid, threads, blob_b, st>>>(m->d_blob, m->blob_words, out, B));
     ++n;
   }
   if (m->hv(H_nsrc) > 0) {
     if (set_smem<T>((const void*)k_constraint<T>, blob_b)) return 1;
-    dim3 grid(gx, m->hv(H_nsrc) < 65535 ? m->hv(H_nsrc) : 65535);
+    dim3 grid(m->hv(H_nsrc), gx < 65535 ? gx : 65535);
     LAUNCH("k_constraint", st, k_constraint<T><<<grid, threads, blob_b, st>>>(m->d_blob, m->blob_words, in, out, B));
     ++n;
   }
@@ -229,7 +235,7 @@ static int run_step(const mjtModel* m, const MjtIn& in, T* out, T* scratch, int 
     return 0;
   }
   if (!scratch) return fail("mjt_step: RK4 needs a scratch buffer (mjt_model_scratch_words)");
-  const int threads = 128, gx = (B + threads - 1) / threads;
+  const int threads = MJT_ENV_THREADS, gx = (B + threads - 1) / threads;
   const size_t blob_b = ((size_t)m->blob_words + 3) / 4 * 16;
   const int nq = m->hv(H_nq), nv = m->hv(H_nv), na = m->hv(H_na);
   T* stage_buf = scratch;

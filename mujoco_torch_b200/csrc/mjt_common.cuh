@@ -5,6 +5,16 @@
 // Per-env state and derived quantities live in an env-minor (W, B) buffer: word k of env e is buf[k*B + e],
 // so a warp of 32 consecutive envs touches 128 contiguous bytes per access.
 #pragma once
+// thread-per-env kernels: threads per CTA and minimum resident CTAs per SM (register cap) -- tuning knobs
+#ifndef MJT_ENV_THREADS
+#define MJT_ENV_THREADS 128
+#endif
+#ifndef MJT_SMOOTH_MINB
+#define MJT_SMOOTH_MINB 4
+#endif
+#ifndef MJT_CONSTRAINT_MINB
+#define MJT_CONSTRAINT_MINB 4
+#endif
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "mjt_layout.h"

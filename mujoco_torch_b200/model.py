@@ -421,6 +421,8 @@ class Model:
         I["jc_src"] = i32(jc_src)
         I["tri_src"] = i32([i * self.nv + j for i in range(self.nv) for j in range(i + 1)])
         I["triu_src"] = i32([j * self.nv + i for i in range(self.nv) for j in range(i)])
+        # packed lower-triangle index p -> (row a, col b) as a | b << 16 (Hessian assembly walks support pairs by p)
+        I["tri_ab"] = i32([a | (b << 16) for a in range(self.nv) for b in range(a + 1)])
         I["eq_type"], I["eq_obj1"], I["eq_obj2"] = i32(mj.eq_type), i32(mj.eq_obj1id), i32(mj.eq_obj2id)
         I["sens_type"], I["sens_objid"], I["sens_adr"] = i32(mj.sensor_type), i32(mj.sensor_objid), i32(mj.sensor_adr)
         I["sens_dim"], I["sens_datatype"], I["sens_stage"] = i32(mj.sensor_dim), i32(mj.sensor_datatype), i32(mj.sensor_needstage)
@@ -548,7 +550,7 @@ class Model:
 
         # the solver kernel stages a reduced blob (only the tables it reads) so that more envs fit in shared memory
         solve_keep = set("jnt_type jnt_qposadr jnt_dofadr act_dyntype act_gaintype act_biastype act_actadr act_actnum act_actlimited "
-                         "src_row src_nrows src_nsup src_cadr sup_col row_src row_jadr "
+                         "src_row src_nrows src_nsup src_cadr sup_col row_src row_jadr tri_ab "
                          "opt dof_damping act_actrange act_gainprm act_biasprm act_dynprm ten_damping".split())
         solve_blob = assemble(solve_keep)
         full = assemble(None, {"solve_blob_words": int(solve_blob.size)})

@@ -13,7 +13,8 @@ import weakref
 
 import torch
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libmjt_b200.so")
+# MJT_LIB selects another build of the same library (tuning variants, scripts/build_variants.sh); there is still no fallback
+_LIB_PATH = os.environ.get("MJT_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libmjt_b200.so")
 _lib = None
 
 MODE_STEP, MODE_FORWARD = 1, 2

@@ -1,0 +1,7 @@
+#!/bin/bash
+# usage: scripts/run_variants.sh "<bench args>" v1 v2 ...   (prints per-kernel ms for each build variant)
+args=$1; shift
+for v in "$@"; do
+  out=$(MJT_LIB=$PWD/build_variants/libmjt_$v.so python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-e2e $args 2>&1 | tail -1)
+  echo "$v $args :: $(echo "$out" | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value']/1e6,2),'M/s', round(d['ms_per_step'],3),'ms', {k:round(v,3) for k,v in d['roofline']['kernel_ms_per_step'].items()})" 2>&1 | tail -1)"
+done
