@@ -16,6 +16,9 @@
 #ifndef MJT_SOLVE_F64_THREADS
 #define MJT_SOLVE_F64_THREADS 256
 #endif
+#ifndef MJT_CHOL_ROWS
+#define MJT_CHOL_ROWS 1   // n <= 32: keep each lane's row of L in registers during the factorisation
+#endif
 #ifndef MJT_SOLVE_F64_MINB
 #define MJT_SOLVE_F64_MINB 2
 #endif
@@ -86,6 +89,8 @@ struct SolveCtx {
   const int* src_nrows;
   const int* sup_col;
   const int* tri_ab;
+  const int* dof_sadr;
+  const int* dof_sent;
 
   __device__ __forceinline__ T* Jc() const { return s + L.oJ; }
   __device__ __forceinline__ T* Mp() const { return s + L.oM; }
@@ -149,33 +154,27 @@ struct SolveCtx {
     }
     __syncwarp();
   }
-  // y = J^T f over rows whose force is non-zero (bitmask fmask), scattered through shared memory
+  // y = J^T f as a per-dof gather: lane i walks the (source, support position) pairs of dof i; rows of a source are
+  // stored back to back (ns entries each).  f must be exactly zero on rows that carry no force.
   __device__ __forceinline__ Vec<T, DPL> jtmul(const T* f) const {
-    T* y = ys();
-    for (int i = lane; i < nv; i += 32) y[i] = T(0);
-    __syncwarp();
-    for (int c = 0; c < L.nchunk; ++c) {
-      unsigned mk = fmask()[c];
-      while (mk) {
-        const int r = (c << 5) + __ffs(mk) - 1;
-        mk &= mk - 1;
-        const int sidx = row_src[r];
-        const int ns = src_nsup[sidx];
-        const int* col = sup_col + src_cadr[sidx];
-        const T* jr = Jc() + row_jadr[r];
-        const T fr = f[r];
-        for (int k = lane; k < ns; k += 32) y[col[k]] += jr[k] * fr;
-        __syncwarp();
-      }
-    }
     Vec<T, DPL> out;
 #pragma unroll
-    for (int k = 0; k < DPL; ++k) { const int i = lane + 32 * k; out.v[k] = i < nv ? y[i] : T(0); }
+    for (int k = 0; k < DPL; ++k) {
+      const int i = lane + 32 * k;
+      T acc = T(0);
+      if (i < nv) {
+        for (int q = dof_sadr[i], qe = dof_sadr[i + 1]; q < qe; ++q) {
+          const int ent = dof_sent[q], sidx = ent & 0xffff, pos = ent >> 16;
+          const int r0 = src_row[sidx], nr = src_nrows[sidx], ns = src_nsup[sidx];
+          const T* jp = Jc() + row_jadr[r0] + pos;
+          const T* fp = f + r0;
+          for (int e = 0; e < nr; ++e) acc += jp[e * ns] * fp[e];
+        }
+      }
+      out.v[k] = acc;
+    }
     return out;
   }
-  // In-place Cholesky of a packed lower triangle; reciprocal pivots go to dinv().
-  // Numeric conventions of reference math.small_cholesky :87-129: n <= 16 clamps each pivot at 1e-12,
-  // n > 16 adds 1e-10 to the diagonal (the torch.linalg.cholesky fallback path).
   // n <= 32 (one row per lane): lane i keeps row i of L in registers, so the inner product reads only row j from
   // shared memory (a broadcast) instead of two strided rows
   __device__ __forceinline__ void cholesky_rows(T* A) const {
@@ -210,7 +209,7 @@ struct SolveCtx {
     }
   }
   __device__ __forceinline__ void cholesky(T* A) const {
-    if (DPL == 1) { cholesky_rows(A); return; }
+    if (DPL == 1 && MJT_CHOL_ROWS) { cholesky_rows(A); return; }
     const int n = nv;
     const bool big = n > 16;
     T* di = dinv();
@@ -282,8 +281,23 @@ struct SolveCtx {
     const T* M0 = Mp();
     for (int p = lane; p < L.nP; p += 32) H[p] = M0[p];
     __syncwarp();
+    // sources that touch a single dof (joint limits, dof friction): one lane per dof adds their diagonal terms
+    for (int i = lane; i < nv; i += 32) {
+      T acc = T(0);
+      for (int q = dof_sadr[i], qe = dof_sadr[i + 1]; q < qe; ++q) {
+        const int sidx = dof_sent[q] & 0xffff;
+        if (src_nsup[sidx] != 1) continue;
+        const int r0 = src_row[sidx], nr = src_nrows[sidx];
+        const T* jp = Jc() + row_jadr[r0];
+        for (int e = 0; e < nr; ++e)
+          if (row_active(r0 + e)) acc += D[r0 + e] * jp[e] * jp[e];
+      }
+      H[tri(i) + i] += acc;
+    }
+    __syncwarp();
     const int nsrc = m.h(H_nsrc);
     for (int sidx = 0; sidx < nsrc; ++sidx) {
+      if (src_nsup[sidx] == 1) continue;
       const int r0 = src_row[sidx], nr = src_nrows[sidx];
       unsigned act = 0;
       if (nr <= 32) act = active_bits(r0, nr);
@@ -773,7 +787,7 @@ __global__ void __launch_bounds__((sizeof(T) == 4 ? 512 : MJT_SOLVE_F64_THREADS)
   const bool valid = env < B;
   EnvBuf<T> d{out + (valid ? env : 0), Bs};
   SolveCtx<T, DPL> c{m, region + (size_t)warp * Lo.words, Lo, nv, nefc, lane,
-                     m.I(I_row_src), m.I(I_row_jadr), m.I(I_src_nsup), m.I(I_src_cadr), m.I(I_src_row), m.I(I_src_nrows), m.I(I_sup_col), m.I(I_tri_ab)};
+                     m.I(I_row_src), m.I(I_row_jadr), m.I(I_src_nsup), m.I(I_src_cadr), m.I(I_src_row), m.I(I_src_nrows), m.I(I_sup_col), m.I(I_tri_ab), m.I(I_dof_sadr), m.I(I_dof_sent)};
   Vec<T, DPL> qfrc_smooth = c.zero(), qacc_smooth = c.zero();
   if (valid) {
     // ---- factor_m + qacc_smooth

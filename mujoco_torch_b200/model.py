@@ -381,8 +381,16 @@ class Model:
                 row_src.append(k)
                 row_jadr.append(jadr)
                 jadr += src_nsup[k]
+        # transpose of the support table: for every dof the (source, position inside that source's support) pairs, so
+        # that J^T f is a per-dof gather (one lane per dof, no scatter)
+        per_dof = [[] for _ in range(self.nv)]
+        for k in range(len(self.src)):
+            for pos in range(src_nsup[k]):
+                per_dof[cols[src_cadr[k] + pos]].append(k | (pos << 16))
+        dof_sadr = np.concatenate([[0], np.cumsum([len(x) for x in per_dof])]).astype(np.int64)
+        dof_sent = [e for x in per_dof for e in x]
         self.sup = dict(src_cadr=src_cadr, src_nsup=src_nsup, src_nrows=src_nrows, cols=cols, row_src=row_src, row_jadr=row_jadr,
-                        jc_words=jadr)
+                        jc_words=jadr, dof_sadr=dof_sadr, dof_sent=dof_sent)
 
     # ---- blob
     def _pack(self):
@@ -419,6 +427,7 @@ class Model:
             ca, ns = sp["src_cadr"][k], sp["src_nsup"][k]
             jc_src += [r * self.nv + cc for cc in sp["cols"][ca: ca + ns]]
         I["jc_src"] = i32(jc_src)
+        I["dof_sadr"], I["dof_sent"] = i32(sp["dof_sadr"]), i32(sp["dof_sent"])
         I["tri_src"] = i32([i * self.nv + j for i in range(self.nv) for j in range(i + 1)])
         I["triu_src"] = i32([j * self.nv + i for i in range(self.nv) for j in range(i)])
         # packed lower-triangle index p -> (row a, col b) as a | b << 16 (Hessian assembly walks support pairs by p)
@@ -550,7 +559,7 @@ class Model:
 
         # the solver kernel stages a reduced blob (only the tables it reads) so that more envs fit in shared memory
         solve_keep = set("jnt_type jnt_qposadr jnt_dofadr act_dyntype act_gaintype act_biastype act_actadr act_actnum act_actlimited "
-                         "src_row src_nrows src_nsup src_cadr sup_col row_src row_jadr tri_ab "
+                         "src_row src_nrows src_nsup src_cadr sup_col row_src row_jadr tri_ab dof_sadr dof_sent "
                          "opt dof_damping act_actrange act_gainprm act_biasprm act_dynprm ten_damping".split())
         solve_blob = assemble(solve_keep)
         full = assemble(None, {"solve_blob_words": int(solve_blob.size)})
