@@ -64,105 +64,103 @@ __device__ void smooth_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<
   for (int i = 0; i < na; ++i) d.set(m.D(D_act) + i, in_get<T>(in.act, B, env, i));
   d.set(m.D(D_time), in_get<T>(in.time, B, env, 0));
 
-  // ---- kinematics (smooth.py:34-207)
-  for (int b = 0; b < nbody; ++b) {
-    V3<T> pos = f3(m.F(F_body_pos) + 3 * b);
-    Q4<T> quat = f4(m.F(F_body_quat) + 4 * b);
-    if (b > 0) {
-      const int p = body_parent[b];
-      V3<T> ppos;
-      ld3(d, oXpos + 3 * p, ppos);
-      Q4<T> pq(d.get(oXquat + 4 * p), d.get(oXquat + 4 * p + 1), d.get(oXquat + 4 * p + 2), d.get(oXquat + 4 * p + 3));
-      pos = ppos + qrot(pos, pq);
-      quat = qmul(pq, quat);
-    }
-    for (int j = body_jntadr[b], je = j + body_jntnum[b]; j < je; ++j) {
-      const int jt = jnt_type[j], qa = jnt_qposadr[j];
-      const V3<T> jpos = f3(m.F(F_jnt_pos) + 3 * j), jaxis = f3(m.F(F_jnt_axis) + 3 * j);
-      V3<T> anchor, axis;
-      if (jt == JNT_FREE) {
-        ld3(d, oQpos + qa, anchor);
-        axis = V3<T>(0, 0, 1);
-      } else {
-        anchor = qrot(jpos, quat) + pos;
-        axis = qrot(jaxis, quat);
-      }
-      st3(d, oAnchor + 3 * j, anchor);
-      st3(d, oAxis + 3 * j, axis);
-      if (jt == JNT_FREE) {
-        ld3(d, oQpos + qa, pos);
-        quat = qnormalize(Q4<T>(d.get(oQpos + qa + 3), d.get(oQpos + qa + 4), d.get(oQpos + qa + 5), d.get(oQpos + qa + 6)));
-        d.set(oQpos + qa + 3, quat.w); d.set(oQpos + qa + 4, quat.x); d.set(oQpos + qa + 5, quat.y); d.set(oQpos + qa + 6, quat.z);
-      } else if (jt == JNT_BALL) {
-        Q4<T> ql = qnormalize(Q4<T>(d.get(oQpos + qa), d.get(oQpos + qa + 1), d.get(oQpos + qa + 2), d.get(oQpos + qa + 3)));
-        d.set(oQpos + qa, ql.w); d.set(oQpos + qa + 1, ql.x); d.set(oQpos + qa + 2, ql.y); d.set(oQpos + qa + 3, ql.z);
-        quat = qmul(quat, ql);
-        pos = anchor - qrot(jpos, quat);
-      } else if (jt == JNT_HINGE) {
-        const T angle = d.get(oQpos + qa) - qpos0[qa];
-        quat = qmul(quat, axis_angle_q(jaxis, angle));
-        pos = anchor - qrot(jpos, quat);
-      } else {
-        pos = pos + axis * (d.get(oQpos + qa) - qpos0[qa]);
-      }
-    }
-    st3(d, oXpos + 3 * b, pos);
-    d.set(oXquat + 4 * b, quat.w); d.set(oXquat + 4 * b + 1, quat.x); d.set(oXquat + 4 * b + 2, quat.y); d.set(oXquat + 4 * b + 3, quat.z);
-  }
-  // mocap overrides are applied after the tree pass, as in the reference (smooth.py:105-113)
-  for (int b = 0; b < nbody; ++b) {
-    const int mid = m.I(I_body_mocapid)[b];
-    V3<T> pos;
-    Q4<T> quat;
-    if (mid >= 0) {
-      pos = V3<T>(in_get<T>(in.mocap_pos, B, env, 3 * mid), in_get<T>(in.mocap_pos, B, env, 3 * mid + 1), in_get<T>(in.mocap_pos, B, env, 3 * mid + 2));
-      quat = qnormalize(Q4<T>(in_get<T>(in.mocap_quat, B, env, 4 * mid), in_get<T>(in.mocap_quat, B, env, 4 * mid + 1),
-                              in_get<T>(in.mocap_quat, B, env, 4 * mid + 2), in_get<T>(in.mocap_quat, B, env, 4 * mid + 3)));
-      st3(d, oXpos + 3 * b, pos);
-      d.set(oXquat + 4 * b, quat.w); d.set(oXquat + 4 * b + 1, quat.x); d.set(oXquat + 4 * b + 2, quat.y); d.set(oXquat + 4 * b + 3, quat.z);
-    } else {
-      ld3(d, oXpos + 3 * b, pos);
-      quat = Q4<T>(d.get(oXquat + 4 * b), d.get(oXquat + 4 * b + 1), d.get(oXquat + 4 * b + 2), d.get(oXquat + 4 * b + 3));
-    }
-    T mat[9];
-    q2mat(quat, mat);
-#pragma unroll
-    for (int k = 0; k < 9; ++k) d.set(oXmat + 9 * b + k, mat[k]);
-    // inertial frame
-    V3<T> ipos = pos + qrot(f3(m.F(F_body_ipos) + 3 * b), quat);
-    st3(d, oXipos + 3 * b, ipos);
-    q2mat(qmul(quat, f4(m.F(F_body_iquat) + 4 * b)), mat);
-#pragma unroll
-    for (int k = 0; k < 9; ++k) d.set(oXimat + 9 * b + k, mat[k]);
-  }
-  // geoms and sites (local_to_global, support.py:99-108)
-  for (int pass = 0; pass < 2; ++pass) {
-    const int n = pass == 0 ? ngeom : nsite;
-    const int* bid = m.I(pass == 0 ? I_geom_bodyid : I_site_bodyid);
-    const T* lpos = m.F(pass == 0 ? F_geom_pos : F_site_pos);
-    const T* lquat = m.F(pass == 0 ? F_geom_quat : F_site_quat);
-    const int oP = m.D(pass == 0 ? D_geom_xpos : D_site_xpos), oR = m.D(pass == 0 ? D_geom_xmat : D_site_xmat);
-    for (int g = 0; g < n; ++g) {
-      const int b = bid[g];
-      V3<T> bp;
-      ld3(d, oXpos + 3 * b, bp);
-      Q4<T> bq(d.get(oXquat + 4 * b), d.get(oXquat + 4 * b + 1), d.get(oXquat + 4 * b + 2), d.get(oXquat + 4 * b + 3));
-      st3(d, oP + 3 * g, bp + qrot(f3(lpos + 3 * g), bq));
-      T mat[9];
-      q2mat(qmul(bq, f4(lquat + 4 * g)), mat);
-#pragma unroll
-      for (int k = 0; k < 9; ++k) d.set(oR + 9 * g + k, mat[k]);
-    }
-  }
-
-  // ---- com_pos (smooth.py:210-288)
+  const int* body_mocap = m.I(I_body_mocapid);
   const T* body_mass = m.F(F_body_mass);
   const T* body_submass = m.F(F_body_subtreemass);
-  for (int b = 0; b < nbody; ++b) {
-    V3<T> ip;
-    ld3(d, oXipos + 3 * b, ip);
-    st3(d, oCom + 3 * b, ip * body_mass[b]);
+
+  // ---- pass 1, bodies root -> leaves: kinematics (smooth.py:34-207).  Everything that depends only on the body's
+  // pose is produced while the pose is in registers: xmat, xipos, ximat, joint anchors/axes, the body's geoms and
+  // sites (support.local_to_global :99-108) and the subtree-COM numerator (smooth.py:215-221).
+  {
+    V3<T> lpos(0, 0, 0);   // tree pose of body b-1 (what its children see)
+    Q4<T> lquat(1, 0, 0, 0);
+    for (int b = 0; b < nbody; ++b) {
+      V3<T> pos = f3(m.F(F_body_pos) + 3 * b);
+      Q4<T> quat = f4(m.F(F_body_quat) + 4 * b);
+      if (b > 0) {
+        const int p = body_parent[b];
+        V3<T> ppos;
+        Q4<T> pq;
+        if (p == b - 1) {
+          ppos = lpos;
+          pq = lquat;
+        } else if (body_mocap[p] >= 0) {   // mocap overrides are not seen by the tree pass (smooth.py:105-113)
+          ppos = f3(m.F(F_body_pos) + 3 * p);
+          pq = f4(m.F(F_body_quat) + 4 * p);
+        } else {
+          ld3(d, oXpos + 3 * p, ppos);
+          pq = Q4<T>(d.get(oXquat + 4 * p), d.get(oXquat + 4 * p + 1), d.get(oXquat + 4 * p + 2), d.get(oXquat + 4 * p + 3));
+        }
+        pos = ppos + qrot(pos, pq);
+        quat = qmul(pq, quat);
+      }
+      for (int j = body_jntadr[b], je = j + body_jntnum[b]; j < je; ++j) {
+        const int jt = jnt_type[j], qa = jnt_qposadr[j];
+        const V3<T> jpos = f3(m.F(F_jnt_pos) + 3 * j), jaxis = f3(m.F(F_jnt_axis) + 3 * j);
+        V3<T> anchor, axis;
+        if (jt == JNT_FREE) {
+          ld3(d, oQpos + qa, anchor);
+          axis = V3<T>(0, 0, 1);
+        } else {
+          anchor = qrot(jpos, quat) + pos;
+          axis = qrot(jaxis, quat);
+        }
+        st3(d, oAnchor + 3 * j, anchor);
+        st3(d, oAxis + 3 * j, axis);
+        if (jt == JNT_FREE) {
+          pos = anchor;
+          quat = qnormalize(Q4<T>(d.get(oQpos + qa + 3), d.get(oQpos + qa + 4), d.get(oQpos + qa + 5), d.get(oQpos + qa + 6)));
+          d.set(oQpos + qa + 3, quat.w); d.set(oQpos + qa + 4, quat.x); d.set(oQpos + qa + 5, quat.y); d.set(oQpos + qa + 6, quat.z);
+        } else if (jt == JNT_BALL) {
+          Q4<T> ql = qnormalize(Q4<T>(d.get(oQpos + qa), d.get(oQpos + qa + 1), d.get(oQpos + qa + 2), d.get(oQpos + qa + 3)));
+          d.set(oQpos + qa, ql.w); d.set(oQpos + qa + 1, ql.x); d.set(oQpos + qa + 2, ql.y); d.set(oQpos + qa + 3, ql.z);
+          quat = qmul(quat, ql);
+          pos = anchor - qrot(jpos, quat);
+        } else if (jt == JNT_HINGE) {
+          const T angle = d.get(oQpos + qa) - qpos0[qa];
+          quat = qmul(quat, axis_angle_q(jaxis, angle));
+          pos = anchor - qrot(jpos, quat);
+        } else {
+          pos = pos + axis * (d.get(oQpos + qa) - qpos0[qa]);
+        }
+      }
+      lpos = pos;
+      lquat = quat;
+      const int mid = body_mocap[b];
+      if (mid >= 0) {
+        pos = V3<T>(in_get<T>(in.mocap_pos, B, env, 3 * mid), in_get<T>(in.mocap_pos, B, env, 3 * mid + 1), in_get<T>(in.mocap_pos, B, env, 3 * mid + 2));
+        quat = qnormalize(Q4<T>(in_get<T>(in.mocap_quat, B, env, 4 * mid), in_get<T>(in.mocap_quat, B, env, 4 * mid + 1),
+                                in_get<T>(in.mocap_quat, B, env, 4 * mid + 2), in_get<T>(in.mocap_quat, B, env, 4 * mid + 3)));
+      }
+      st3(d, oXpos + 3 * b, pos);
+      d.set(oXquat + 4 * b, quat.w); d.set(oXquat + 4 * b + 1, quat.x); d.set(oXquat + 4 * b + 2, quat.y); d.set(oXquat + 4 * b + 3, quat.z);
+      T mat[9];
+      q2mat(quat, mat);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) d.set(oXmat + 9 * b + k, mat[k]);
+      const V3<T> ipos = pos + qrot(f3(m.F(F_body_ipos) + 3 * b), quat);
+      st3(d, oXipos + 3 * b, ipos);
+      q2mat(qmul(quat, f4(m.F(F_body_iquat) + 4 * b)), mat);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) d.set(oXimat + 9 * b + k, mat[k]);
+      st3(d, oCom + 3 * b, ipos * body_mass[b]);
+      for (int pass = 0; pass < 2; ++pass) {
+        const int* list = m.I(pass == 0 ? I_body_geom : I_body_site) + m.I(pass == 0 ? I_body_geomadr : I_body_siteadr)[b];
+        const int n = m.I(pass == 0 ? I_body_geomnum : I_body_sitenum)[b];
+        const T* lp = m.F(pass == 0 ? F_geom_pos : F_site_pos);
+        const T* lq = m.F(pass == 0 ? F_geom_quat : F_site_quat);
+        const int oP = m.D(pass == 0 ? D_geom_xpos : D_site_xpos), oR = m.D(pass == 0 ? D_geom_xmat : D_site_xmat);
+        for (int k = 0; k < n; ++k) {
+          const int g = list[k];
+          st3(d, oP + 3 * g, pos + qrot(f3(lp + 3 * g), quat));
+          q2mat(qmul(quat, f4(lq + 4 * g)), mat);
+#pragma unroll
+          for (int c = 0; c < 9; ++c) d.set(oR + 9 * g + c, mat[c]);
+        }
+      }
+    }
   }
+  // ---- pass 2, leaves -> root: subtree-COM numerators (smooth.py:222-226)
   for (int b = nbody - 1; b > 0; --b) {
     const int p = body_parent[b];
     V3<T> a, c;
@@ -170,74 +168,137 @@ __device__ void smooth_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<
     ld3(d, oCom + 3 * b, c);
     st3(d, oCom + 3 * p, a + c);
   }
-  for (int b = 0; b < nbody; ++b) {
-    V3<T> s, ip;
-    ld3(d, oCom + 3 * b, s);
-    const T ms = body_submass[b];
-    if (ms < T(MJT_MINVAL)) {
-      ld3(d, oXipos + 3 * b, ip);
-      s = ip;
-    } else {
-      const T dm = t_max(ms, T(MJT_MINVAL));
-      s = V3<T>(s.x / dm, s.y / dm, s.z / dm);
-    }
-    st3(d, oCom + 3 * b, s);
-  }
-  for (int b = 0; b < nbody; ++b) {
-    V3<T> ip, rc;
-    ld3(d, oXipos + 3 * b, ip);
-    ld3(d, oCom + 3 * body_root[b], rc);
-    const V3<T> off = ip - rc;
-    T R[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) R[k] = d.get(oXimat + 9 * b + k);
-    const T* I3 = m.F(F_body_inertia) + 3 * b;
-    const T ms = body_mass[b];
-    // inert = R diag(I) R^T + m (|o|^2 E - o o^T)
-    T in6[6];
-    const int ti[6] = {0, 1, 2, 0, 0, 1}, tj[6] = {0, 1, 2, 1, 2, 2};
-    const T o[3] = {off.x, off.y, off.z};
-    const T oo = dot(off, off);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      const int a = ti[k], c = tj[k];
-      T v = R[3 * a] * I3[0] * R[3 * c] + R[3 * a + 1] * I3[1] * R[3 * c + 1] + R[3 * a + 2] * I3[2] * R[3 * c + 2];
-      v += ((a == c ? oo : T(0)) - o[a] * o[c]) * ms;
-      in6[k] = v;
-    }
-#pragma unroll
-    for (int k = 0; k < 6; ++k) d.set(oCinert + 10 * b + k, in6[k]);
-    d.set(oCinert + 10 * b + 6, off.x * ms); d.set(oCinert + 10 * b + 7, off.y * ms); d.set(oCinert + 10 * b + 8, off.z * ms);
-    d.set(oCinert + 10 * b + 9, ms);
-  }
-  for (int j = 0; j < njnt; ++j) {
-    const int jt = jnt_type[j], da = jnt_dofadr[j], b = jnt_bodyid[j];
-    V3<T> rc, an;
-    ld3(d, oCom + 3 * body_root[b], rc);
-    ld3(d, oAnchor + 3 * j, an);
-    const V3<T> off = rc - an;
-    if (jt == JNT_FREE || jt == JNT_BALL) {
-      int base = da;
-      if (jt == JNT_FREE) {
-        for (int k = 0; k < 3; ++k)
-          for (int c = 0; c < 6; ++c) d.set(oCdof + 6 * (da + k) + c, (c == 3 + k) ? T(1) : T(0));
-        base = da + 3;
+
+  // ---- pass 3, root -> leaves: subtree_com, cinert, cdof (smooth.py:227-288), com_vel (smooth.py:385-424) and the
+  // forward half of rne (smooth.py:427-452).  Each body's spatial quantities are consumed from registers.
+  const int oCacc = m.D(D_scr_cacc), oCfrc = m.D(D_scr_cfrc), oBias = m.D(D_qfrc_bias);
+  {
+    V3<T> rc(0, 0, 0);
+    int rc_root = -1;
+    T lv[6], la[6];   // cvel / cacc of body b-1
+    for (int b = 0; b < nbody; ++b) {
+      V3<T> pos;
+      ld3(d, oXpos + 3 * b, pos);
+      const Q4<T> quat(d.get(oXquat + 4 * b), d.get(oXquat + 4 * b + 1), d.get(oXquat + 4 * b + 2), d.get(oXquat + 4 * b + 3));
+      const V3<T> ipos = pos + qrot(f3(m.F(F_body_ipos) + 3 * b), quat);
+      V3<T> s;
+      ld3(d, oCom + 3 * b, s);
+      const T msub = body_submass[b];
+      if (msub < T(MJT_MINVAL)) {
+        ld3(d, oXipos + 3 * b, s);
+      } else {
+        const T dm = t_max(msub, T(MJT_MINVAL));
+        s = V3<T>(s.x / dm, s.y / dm, s.z / dm);
       }
-      for (int k = 0; k < 3; ++k) {  // body axes = columns of xmat
-        V3<T> a(d.get(oXmat + 9 * b + k), d.get(oXmat + 9 * b + 3 + k), d.get(oXmat + 9 * b + 6 + k));
-        st3(d, oCdof + 6 * (base + k), a);
-        st3(d, oCdof + 6 * (base + k) + 3, cross(a, off));
+      st3(d, oCom + 3 * b, s);
+      const int root = body_root[b];
+      if (root == b) { rc = s; rc_root = b; }
+      else if (root != rc_root) { ld3(d, oCom + 3 * root, rc); rc_root = root; }
+      // cinert = R diag(I) R^T + m (|o|^2 E - o o^T), [m o, m]
+      T ci[10];
+      {
+        const V3<T> off = ipos - rc;
+        T R[9];
+        q2mat(qmul(quat, f4(m.F(F_body_iquat) + 4 * b)), R);
+        const T* I3 = m.F(F_body_inertia) + 3 * b;
+        const T ms = body_mass[b];
+        const int ti[6] = {0, 1, 2, 0, 0, 1}, tj[6] = {0, 1, 2, 1, 2, 2};
+        const T o[3] = {off.x, off.y, off.z};
+        const T oo = dot(off, off);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          const int a = ti[k], c = tj[k];
+          T v = R[3 * a] * I3[0] * R[3 * c] + R[3 * a + 1] * I3[1] * R[3 * c + 1] + R[3 * a + 2] * I3[2] * R[3 * c + 2];
+          v += ((a == c ? oo : T(0)) - o[a] * o[c]) * ms;
+          ci[k] = v;
+        }
+        ci[6] = off.x * ms; ci[7] = off.y * ms; ci[8] = off.z * ms; ci[9] = ms;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) { d.set(oCinert + 10 * b + k, ci[k]); d.set(oCrb + 10 * b + k, ci[k]); }
       }
-    } else if (jt == JNT_HINGE) {
-      V3<T> a;
-      ld3(d, oAxis + 3 * j, a);
-      st3(d, oCdof + 6 * da, a);
-      st3(d, oCdof + 6 * da + 3, cross(a, off));
-    } else {
-      V3<T> a;
-      ld3(d, oAxis + 3 * j, a);
-      st3(d, oCdof + 6 * da, V3<T>(0, 0, 0));
-      st3(d, oCdof + 6 * da + 3, a);
+      // parent's cvel / cacc
+      T v[6], a[6];
+      if (b == 0) {
+        const bool nograv = flags & DSBL_GRAVITY;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { v[k] = T(0); a[k] = T(0); }
+        if (!nograv) { a[3] = -m.opt(OPT_gravity0); a[4] = -m.opt(OPT_gravity1); a[5] = -m.opt(OPT_gravity2); }
+      } else {
+        const int p = body_parent[b];
+        if (p == b - 1) {
+#pragma unroll
+          for (int k = 0; k < 6; ++k) { v[k] = lv[k]; a[k] = la[k]; }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 6; ++k) { v[k] = d.get(oCvel + 6 * p + k); a[k] = d.get(oCacc + 6 * p + k); }
+        }
+      }
+      T xm[9];
+      q2mat(quat, xm);
+      for (int j = body_jntadr[b], je = j + body_jntnum[b]; j < je; ++j) {
+        const int jt = jnt_type[j], da = jnt_dofadr[j];
+        V3<T> an, ax;
+        ld3(d, oAnchor + 3 * j, an);
+        const V3<T> off = rc - an;
+        int first = da, cnt = 1;
+        T cd[3][6];
+        if (jt == JNT_FREE) {
+          for (int k = 0; k < 3; ++k) {   // translational dofs: unit twists; their cdof_dot is zero (smooth.py:400-404)
+            const T qv = d.get(oQvel + da + k);
+            for (int c = 0; c < 6; ++c) {
+              const T e = (c == 3 + k) ? T(1) : T(0);
+              d.set(oCdof + 6 * (da + k) + c, e);
+              d.set(oCdofdot + 6 * (da + k) + c, T(0));
+              v[c] += e * qv;
+            }
+          }
+          first = da + 3;
+        }
+        if (jt == JNT_FREE || jt == JNT_BALL) {
+          cnt = 3;
+          for (int k = 0; k < 3; ++k) {   // body axes = columns of xmat
+            const V3<T> w(xm[k], xm[3 + k], xm[6 + k]);
+            const V3<T> l = cross(w, off);
+            cd[k][0] = w.x; cd[k][1] = w.y; cd[k][2] = w.z; cd[k][3] = l.x; cd[k][4] = l.y; cd[k][5] = l.z;
+          }
+        } else {
+          ld3(d, oAxis + 3 * j, ax);
+          if (jt == JNT_HINGE) {
+            const V3<T> l = cross(ax, off);
+            cd[0][0] = ax.x; cd[0][1] = ax.y; cd[0][2] = ax.z; cd[0][3] = l.x; cd[0][4] = l.y; cd[0][5] = l.z;
+          } else {
+            cd[0][0] = T(0); cd[0][1] = T(0); cd[0][2] = T(0); cd[0][3] = ax.x; cd[0][4] = ax.y; cd[0][5] = ax.z;
+          }
+        }
+        for (int k = 0; k < cnt; ++k) {
+          T dd[6];
+          motion_cross(v, cd[k], dd);
+          const T qv = d.get(oQvel + first + k);
+#pragma unroll
+          for (int c = 0; c < 6; ++c) {
+            d.set(oCdof + 6 * (first + k) + c, cd[k][c]);
+            d.set(oCdofdot + 6 * (first + k) + c, dd[c]);
+            a[c] += dd[c] * qv;
+          }
+        }
+        for (int k = 0; k < cnt; ++k) {
+          const T qv = d.get(oQvel + first + k);
+#pragma unroll
+          for (int c = 0; c < 6; ++c) v[c] += cd[k][c] * qv;
+        }
+      }
+      T f1[6], f2[6], f3v[6];
+      inert_mul(ci, a, f1);
+      inert_mul(ci, v, f2);
+      motion_cross_force(v, f2, f3v);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        d.set(oCvel + 6 * b + k, v[k]);
+        d.set(oCacc + 6 * b + k, a[k]);
+        d.set(oCfrc + 6 * b + k, f1[k] + f3v[k]);
+        lv[k] = v[k];
+        la[k] = a[k];
+      }
     }
   }
 
@@ -258,30 +319,98 @@ __device__ void smooth_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<
     }
   }
 
-  // ---- crb + dense M (smooth.py:291-308, support.make_m :50-69)
-  for (int b = 0; b < nbody; ++b)
-    for (int k = 0; k < 10; ++k) d.set(oCrb + 10 * b + k, d.get(oCinert + 10 * b + k));
-  for (int b = nbody - 1; b > 0; --b) {
-    const int p = body_parent[b];
-    for (int k = 0; k < 10; ++k) d.set(oCrb + 10 * p + k, d.get(oCrb + 10 * p + k) + d.get(oCrb + 10 * b + k));
-  }
-  for (int k = 0; k < 10; ++k) d.set(oCrb + k, T(0));
-  for (int i = 0; i < nv * nv; ++i) d.set(oM + i, T(0));
-  for (int i = 0; i < nv; ++i) {
-    T c[10], v[6], f[6];
-    const int b = dof_bodyid[i];
+  // ---- pass 4, leaves -> root: composite inertia (smooth.py:291-308), the backward half of rne (:453-467) and,
+  // while a body's crb / cfrc are in registers, its rows of the dense M (support.make_m :50-69) and qfrc_bias.
+  // A child that directly follows its parent hands its sums over in registers; every entry of M is written once.
+  {
+    T hc[10], hf[6];   // crb / cfrc of body b+1 when that body's parent is b
+    bool have = false;
+    for (int b = nbody - 1; b >= 0; --b) {
+      T cb[10], cf[6];
 #pragma unroll
-    for (int k = 0; k < 10; ++k) c[k] = d.get(oCrb + 10 * b + k);
+      for (int k = 0; k < 10; ++k) cb[k] = d.get(oCrb + 10 * b + k);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) v[k] = d.get(oCdof + 6 * i + k);
-    inert_mul(c, v, f);
-    for (int j = i; j >= 0; j = dof_parent[j]) {
-      T s = 0;
+      for (int k = 0; k < 6; ++k) cf[k] = d.get(oCfrc + 6 * b + k);
+      if (have) {
 #pragma unroll
-      for (int k = 0; k < 6; ++k) s += f[k] * d.get(oCdof + 6 * j + k);
-      if (j == i) s += m.F(F_dof_armature)[i];
-      d.set(oM + i * nv + j, s);
-      d.set(oM + j * nv + i, s);
+        for (int k = 0; k < 10; ++k) cb[k] += hc[k];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) cf[k] += hf[k];
+      }
+      if (b == 0) {
+#pragma unroll
+        for (int k = 0; k < 10; ++k) d.set(oCrb + k, T(0));   // reference zeroes the world body's crb (smooth.py:306)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) d.set(oCfrc + k, cf[k]);
+        break;
+      }
+#pragma unroll
+      for (int k = 0; k < 10; ++k) d.set(oCrb + 10 * b + k, cb[k]);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) d.set(oCfrc + 6 * b + k, cf[k]);
+      const int p = body_parent[b];
+      if (p == b - 1) {
+#pragma unroll
+        for (int k = 0; k < 10; ++k) hc[k] = cb[k];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) hf[k] = cf[k];
+        have = true;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 10; ++k) d.set(oCrb + 10 * p + k, d.get(oCrb + 10 * p + k) + cb[k]);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) d.set(oCfrc + 6 * p + k, d.get(oCfrc + 6 * p + k) + cf[k]);
+        have = false;
+      }
+      // rows of M for this body's dofs, in groups of up to 3 consecutive dofs that share their ancestor walk
+      const int i0 = body_dofadr[b], nd = body_dofnum[b];
+      for (int g0 = i0; g0 < i0 + nd; g0 += 3) {
+        const int gn = (i0 + nd - g0) < 3 ? (i0 + nd - g0) : 3;
+        T cd[3][6], f[3][6];
+        for (int k = 0; k < 3; ++k) {
+          if (k < gn) {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) cd[k][c] = d.get(oCdof + 6 * (g0 + k) + c);
+            inert_mul(cb, cd[k], f[k]);
+            T sb = 0;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) sb += cd[k][c] * cf[c];
+            d.set(oBias + g0 + k, sb);
+          }
+        }
+        // pairs inside the group (dofs of one body form a chain: every earlier dof is an ancestor)
+        for (int k = 0; k < 3; ++k)
+          for (int l = 0; l <= k; ++l)
+            if (k < gn) {
+              T sm = 0;
+#pragma unroll
+              for (int c = 0; c < 6; ++c) sm += f[k][c] * cd[l][c];
+              if (l == k) sm += m.F(F_dof_armature)[g0 + k];
+              d.set(oM + (g0 + k) * nv + g0 + l, sm);
+              if (l != k) d.set(oM + (g0 + l) * nv + g0 + k, sm);
+            }
+        // ancestors below the group, zero-filling the gaps between them
+        int prev = g0;
+        for (int j = dof_parent[g0]; ; j = dof_parent[j]) {
+          const int stop = j < 0 ? -1 : j;
+          for (int z = prev - 1; z > stop; --z)
+            for (int k = 0; k < 3; ++k)
+              if (k < gn) { d.set(oM + (g0 + k) * nv + z, T(0)); d.set(oM + z * nv + g0 + k, T(0)); }
+          if (j < 0) break;
+          T cj[6];
+#pragma unroll
+          for (int c = 0; c < 6; ++c) cj[c] = d.get(oCdof + 6 * j + c);
+          for (int k = 0; k < 3; ++k)
+            if (k < gn) {
+              T sm = 0;
+#pragma unroll
+              for (int c = 0; c < 6; ++c) sm += f[k][c] * cj[c];
+              d.set(oM + (g0 + k) * nv + j, sm);
+              d.set(oM + j * nv + g0 + k, sm);
+            }
+          prev = j;
+        }
+      }
     }
   }
   // tendon_armature (smooth.py:500-521): M += J^T diag(armature) J
@@ -295,6 +424,13 @@ __device__ void smooth_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<
         if (ji == T(0)) continue;
         for (int j = 0; j < nv; ++j) d.set(oM + i * nv + j, d.get(oM + i * nv + j) + ji * arm * d.get(oJ + t * nv + j));
       }
+    }
+  }
+  if (ntendon) {
+    for (int t = 0; t < ntendon; ++t) {
+      T v = 0;
+      for (int i = 0; i < nv; ++i) v += d.get(m.D(D_ten_J) + t * nv + i) * d.get(oQvel + i);
+      d.set(m.D(D_ten_velocity) + t, v);
     }
   }
 
@@ -337,53 +473,6 @@ __device__ void smooth_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<
     }
     d.set(oAlen + u, len);
     d.set(oAvel + u, vel);
-  }
-  if (ntendon) {
-    for (int t = 0; t < ntendon; ++t) {
-      T v = 0;
-      for (int i = 0; i < nv; ++i) v += d.get(m.D(D_ten_J) + t * nv + i) * d.get(oQvel + i);
-      d.set(m.D(D_ten_velocity) + t, v);
-    }
-  }
-
-  // ---- com_vel (smooth.py:385-424)
-  for (int k = 0; k < 6; ++k) d.set(oCvel + k, T(0));
-  for (int b = 1; b < nbody; ++b) {
-    T v[6];
-    const int p = body_parent[b];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) v[k] = d.get(oCvel + 6 * p + k);
-    for (int j = body_jntadr[b], je = j + body_jntnum[b]; j < je; ++j) {
-      const int jt = jnt_type[j], da = jnt_dofadr[j];
-      int first = da, cnt = (jt == JNT_BALL) ? 3 : 1;
-      if (jt == JNT_FREE) {
-        for (int k = 0; k < 3; ++k) {
-          const T qv = d.get(oQvel + da + k);
-          for (int c = 0; c < 6; ++c) {
-            v[c] += d.get(oCdof + 6 * (da + k) + c) * qv;
-            d.set(oCdofdot + 6 * (da + k) + c, T(0));
-          }
-        }
-        first = da + 3;
-        cnt = 3;
-      }
-      T cd[3][6];
-      for (int k = 0; k < cnt; ++k) {
-        T out[6];
-#pragma unroll
-        for (int c = 0; c < 6; ++c) cd[k][c] = d.get(oCdof + 6 * (first + k) + c);
-        motion_cross(v, cd[k], out);
-#pragma unroll
-        for (int c = 0; c < 6; ++c) d.set(oCdofdot + 6 * (first + k) + c, out[c]);
-      }
-      for (int k = 0; k < cnt; ++k) {
-        const T qv = d.get(oQvel + first + k);
-#pragma unroll
-        for (int c = 0; c < 6; ++c) v[c] += cd[k][c] * qv;
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 6; ++k) d.set(oCvel + 6 * b + k, v[k]);
   }
 
   // ---- passive (passive.py:80-200)
@@ -493,55 +582,6 @@ __device__ void smooth_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<
         d.set(oPassive + i, d.get(oPassive + i) + dot(l + cross(a, off), force) + dot(a, torque));
       });
     }
-  }
-
-  // ---- rne (smooth.py:427-467)
-  const int oCacc = m.D(D_scr_cacc), oCfrc = m.D(D_scr_cfrc), oBias = m.D(D_qfrc_bias);
-  {
-    const bool nograv = flags & DSBL_GRAVITY;
-    d.set(oCacc, T(0)); d.set(oCacc + 1, T(0)); d.set(oCacc + 2, T(0));
-    d.set(oCacc + 3, nograv ? T(0) : -m.opt(OPT_gravity0));
-    d.set(oCacc + 4, nograv ? T(0) : -m.opt(OPT_gravity1));
-    d.set(oCacc + 5, nograv ? T(0) : -m.opt(OPT_gravity2));
-  }
-  for (int b = 0; b < nbody; ++b) {
-    T a[6], ci[10], cv[6], f1[6], f2[6], f3v[6];
-    if (b > 0) {
-      const int p = body_parent[b];
-#pragma unroll
-      for (int k = 0; k < 6; ++k) a[k] = d.get(oCacc + 6 * p + k);
-      for (int i = body_dofadr[b], ie = i + body_dofnum[b]; i < ie; ++i) {
-        const T qv = d.get(oQvel + i);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) a[k] += d.get(oCdofdot + 6 * i + k) * qv;
-      }
-#pragma unroll
-      for (int k = 0; k < 6; ++k) d.set(oCacc + 6 * b + k, a[k]);
-    } else {
-#pragma unroll
-      for (int k = 0; k < 6; ++k) a[k] = d.get(oCacc + k);
-    }
-#pragma unroll
-    for (int k = 0; k < 10; ++k) ci[k] = d.get(oCinert + 10 * b + k);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) cv[k] = d.get(oCvel + 6 * b + k);
-    inert_mul(ci, a, f1);
-    inert_mul(ci, cv, f2);
-    motion_cross_force(cv, f2, f3v);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) d.set(oCfrc + 6 * b + k, f1[k] + f3v[k]);
-  }
-  for (int b = nbody - 1; b > 0; --b) {
-    const int p = body_parent[b];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) d.set(oCfrc + 6 * p + k, d.get(oCfrc + 6 * p + k) + d.get(oCfrc + 6 * b + k));
-  }
-  for (int i = 0; i < nv; ++i) {
-    const int b = dof_bodyid[i];
-    T s = 0;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) s += d.get(oCdof + 6 * i + k) * d.get(oCfrc + 6 * b + k);
-    d.set(oBias + i, s);
   }
 
   // ---- actuation (forward.py:102-219)

@@ -14,13 +14,13 @@
 #pragma once
 // f64 launch shape of k_solve: threads per CTA (= 32 x envs per CTA) and minimum CTAs per SM (caps registers/thread)
 #ifndef MJT_SOLVE_F64_THREADS
-#define MJT_SOLVE_F64_THREADS 256
+#define MJT_SOLVE_F64_THREADS 512
 #endif
 #ifndef MJT_CHOL_ROWS
 #define MJT_CHOL_ROWS 1   // n <= 32: keep each lane's row of L in registers during the factorisation
 #endif
 #ifndef MJT_SOLVE_F64_MINB
-#define MJT_SOLVE_F64_MINB 2
+#define MJT_SOLVE_F64_MINB 1
 #endif
 #include "mjt_common.cuh"
 #include "k_smooth.cuh"
@@ -760,14 +760,17 @@ __global__ void __launch_bounds__((sizeof(T) == 4 ? 512 : MJT_SOLVE_F64_THREADS)
   const bool cvalid = env0 + ce < B;
   T* const crg = region + (size_t)ce * Lo.words;
   T* const cout = out + env0 + ce;
-  const int* tri_src = gfull + gfull[MJT_OFF_I + I_tri_src];   // packed lower index -> dense word i*nv+j (global, L1 resident)
+  const int* tri_ab = m.I(I_tri_ab);   // packed lower index p -> (a, b): dense word a*nv+b, mirrored word b*nv+a
   {
     const int oM = m.D(D_qM);
     if (cvalid)
-      for (int p = ck0; p < Lo.nP; p += cks) cp_async_word(crg + Lo.oM + p, cout + (size_t)(oM + tri_src[p]) * Bs);
+      for (int p = ck0; p < Lo.nP; p += cks) {
+        const int ab = tri_ab[p];
+        cp_async_word(crg + Lo.oM + p, cout + (size_t)(oM + (ab & 0xffff) * nv + (ab >> 16)) * Bs);
+      }
     if (nefc) {
       const int oJ = m.D(D_efc_J), jcw = m.h(H_jc_words);
-      const int* jsrc = gfull + gfull[MJT_OFF_I + I_jc_src];   // compact J entry -> dense word row*nv+col
+      const int* jsrc = m.I(I_jc_src);   // compact J entry -> dense word row*nv+col
       if (cvalid)
         for (int k = ck0; k < jcw; k += cks) cp_async_word(crg + Lo.oJ + k, cout + (size_t)(oJ + jsrc[k]) * Bs);
       const int oD = m.D(D_efc_D), oA = m.D(D_efc_aref), oF = m.D(D_efc_frictionloss);
@@ -805,10 +808,12 @@ __global__ void __launch_bounds__((sizeof(T) == 4 ? 512 : MJT_SOLVE_F64_THREADS)
   __syncthreads();
   {  // cooperative store of qLD = chol(M) (dense lower, zeros above the diagonal)
     const int oL = m.D(D_qLD);
-    const int* triu_src = gfull + gfull[MJT_OFF_I + I_triu_src];
     if (cvalid) {
-      for (int p = ck0; p < Lo.nP; p += cks) cout[(size_t)(oL + tri_src[p]) * Bs] = crg[Lo.oL + p];
-      for (int p = ck0; p < Lo.nP - nv; p += cks) cout[(size_t)(oL + triu_src[p]) * Bs] = T(0);
+      for (int p = ck0; p < Lo.nP; p += cks) {
+        const int ab = tri_ab[p], a = ab & 0xffff, b = ab >> 16;
+        cout[(size_t)(oL + a * nv + b) * Bs] = crg[Lo.oL + p];
+        if (a != b) cout[(size_t)(oL + b * nv + a) * Bs] = T(0);
+      }
     }
   }
   __syncthreads();

@@ -106,7 +106,7 @@ extern "C" int mjt_model_create(const void* blob_host, size_t nbytes, int device
   // f64 kernel: MJT_SOLVE_F64_THREADS x MJT_SOLVE_F64_MINB threads fit the register file; f32 kernel: 2 x 512
   const int emax = m->f64 ? MJT_SOLVE_F64_THREADS / 32 : 16;
   const size_t wcap = m->f64 ? (size_t)(MJT_SOLVE_F64_THREADS / 32) * MJT_SOLVE_F64_MINB : 32;
-  for (int e = emax; e >= 1; e = (e > 4 && (e & (e - 1))) ? e - 2 : e >> 1) {   // 16 8 4 2 1 or 12 10 8 4 2 1 ...
+  for (int e = emax; e >= 1; --e) {   // most resident warps per SM wins; ties go to the larger CTA
     const size_t need = sblob_b + region * e + 1024;
     if (need > (size_t)m->max_smem) continue;
     size_t ctas = sm_total / need;

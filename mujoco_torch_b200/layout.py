@@ -41,6 +41,7 @@ src_type src_id src_row src_cadr src_nsup src_nrows sup_col row_src row_jadr jc_
 eq_type eq_obj1 eq_obj2
 sens_type sens_objid sens_adr sens_dim sens_datatype sens_stage
 rf_geom
+body_geomadr body_geomnum body_geom body_siteadr body_sitenum body_site
 cvx_geom cvx_nvert cvx_nface cvx_nfv cvx_nedge cvx_vertadr cvx_faceadr cvx_edgeadr cvx_normadr geom_cvx cvx_face cvx_edge
 """.split()
 

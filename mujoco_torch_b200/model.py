@@ -404,6 +404,13 @@ class Model:
                   "jnt_actfrclimited jnt_actgravcomp").split():
             I[k] = i32(getattr(mj, k))
         I["body_dofmask"] = self.body_dofmask.view(np.int32).reshape(-1)
+        # geoms / sites grouped by body (k_smooth places them while the body's pose is still in registers)
+        for kind, ids in (("geom", np.asarray(mj.geom_bodyid).reshape(-1)), ("site", np.asarray(mj.site_bodyid).reshape(-1))):
+            order = np.argsort(ids, kind="stable")
+            num = np.bincount(ids.astype(np.int64), minlength=self.nbody) if ids.size else np.zeros(self.nbody, np.int64)
+            I[f"body_{kind}adr"] = i32(np.concatenate([[0], np.cumsum(num)[:-1]]))
+            I[f"body_{kind}num"] = i32(num)
+            I[f"body_{kind}"] = i32(order)
         for k in ("trntype dyntype gaintype biastype actadr actnum ctrllimited forcelimited actlimited").split():
             I["act_" + k] = i32(getattr(mj, "actuator_" + k))
         I["act_trnid"] = i32(np.asarray(mj.actuator_trnid).reshape(-1, 2)[:, 0]) if self.nu else i32([])
@@ -559,7 +566,7 @@ class Model:
 
         # the solver kernel stages a reduced blob (only the tables it reads) so that more envs fit in shared memory
         solve_keep = set("jnt_type jnt_qposadr jnt_dofadr act_dyntype act_gaintype act_biastype act_actadr act_actnum act_actlimited "
-                         "src_row src_nrows src_nsup src_cadr sup_col row_src row_jadr tri_ab dof_sadr dof_sent "
+                         "src_row src_nrows src_nsup src_cadr sup_col row_src row_jadr tri_ab dof_sadr dof_sent jc_src "
                          "opt dof_damping act_actrange act_gainprm act_biasprm act_dynprm ten_damping".split())
         solve_blob = assemble(solve_keep)
         full = assemble(None, {"solve_blob_words": int(solve_blob.size)})
