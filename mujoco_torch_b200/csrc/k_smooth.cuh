@@ -434,45 +434,57 @@ __device__ void smooth_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<
     }
   }
 
-  // ---- transmission (smooth.py:535-591) and actuator_velocity (forward.py:87-95)
+  // ---- transmission (smooth.py:535-591) and actuator_velocity (forward.py:87-95).  The non-zero entries of an
+  // actuator's moment row are a short run (joint transmissions) or a scaled tendon Jacobian row; each row of the
+  // dense actuator_moment is written exactly once and never read back.
   const int oAlen = m.D(D_actuator_length), oAmom = m.D(D_actuator_moment), oAvel = m.D(D_actuator_velocity);
-  for (int u = 0; u < nu; ++u) {
+  auto transmission = [&](int u, int* first, int* cnt, T* mom, T* len_out, T* vel_out) {
     const int trn = m.I(I_act_trntype)[u], id = m.I(I_act_trnid)[u];
     const T* gear = m.F(F_act_gear) + 6 * u;
-    for (int i = 0; i < nv; ++i) d.set(oAmom + u * nv + i, T(0));
     T len = 0, vel = 0;
+    *first = 0;
+    *cnt = 0;
     if (trn == TRN_TENDON) {
       len = d.get(m.D(D_ten_length) + id) * gear[0];
-      for (int i = 0; i < nv; ++i) {
-        const T mm = d.get(m.D(D_ten_J) + id * nv + i) * gear[0];
-        d.set(oAmom + u * nv + i, mm);
-        vel += mm * d.get(oQvel + i);
-      }
+      *cnt = -1;   // dense row: ten_J[id] * gear[0]
+      for (int i = 0; i < nv; ++i) vel += d.get(m.D(D_ten_J) + id * nv + i) * gear[0] * d.get(oQvel + i);
     } else {
       const int jt = jnt_type[id], da = jnt_dofadr[id], qa = jnt_qposadr[id];
+      *first = da;
       if (jt == JNT_FREE) {
-        T g6[6] = {gear[0], gear[1], gear[2], gear[3], gear[4], gear[5]};
+        *cnt = 6;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) mom[k] = gear[k];
         if (trn == TRN_JOINTINPARENT) {
           Q4<T> q(d.get(oQpos + qa + 3), d.get(oQpos + qa + 4), d.get(oQpos + qa + 5), d.get(oQpos + qa + 6));
           V3<T> ga = qrot(V3<T>(gear[3], gear[4], gear[5]), qconj(q));
-          g6[3] = ga.x; g6[4] = ga.y; g6[5] = ga.z;
+          mom[3] = ga.x; mom[4] = ga.y; mom[5] = ga.z;
         }
-        for (int k = 0; k < 6; ++k) { d.set(oAmom + u * nv + da + k, g6[k]); vel += g6[k] * d.get(oQvel + da + k); }
+        for (int k = 0; k < 6; ++k) vel += mom[k] * d.get(oQvel + da + k);
       } else if (jt == JNT_BALL) {
+        *cnt = 3;
         Q4<T> q(d.get(oQpos + qa), d.get(oQpos + qa + 1), d.get(oQpos + qa + 2), d.get(oQpos + qa + 3));
         V3<T> ga(gear[0], gear[1], gear[2]);
         if (trn == TRN_JOINTINPARENT) ga = qrot(ga, qconj(q));
         len = dot(q2axisangle(q), ga);
-        d.set(oAmom + u * nv + da, ga.x); d.set(oAmom + u * nv + da + 1, ga.y); d.set(oAmom + u * nv + da + 2, ga.z);
+        mom[0] = ga.x; mom[1] = ga.y; mom[2] = ga.z;
         vel = ga.x * d.get(oQvel + da) + ga.y * d.get(oQvel + da + 1) + ga.z * d.get(oQvel + da + 2);
       } else {
+        *cnt = 1;
         len = d.get(oQpos + qa) * gear[0];
-        d.set(oAmom + u * nv + da, gear[0]);
+        mom[0] = gear[0];
         vel = gear[0] * d.get(oQvel + da);
       }
     }
-    d.set(oAlen + u, len);
-    d.set(oAvel + u, vel);
+    *len_out = len;
+    *vel_out = vel;
+  };
+  if (ntendon) {
+    for (int t = 0; t < ntendon; ++t) {
+      T v = 0;
+      for (int i = 0; i < nv; ++i) v += d.get(m.D(D_ten_J) + t * nv + i) * d.get(oQvel + i);
+      d.set(m.D(D_ten_velocity) + t, v);
+    }
   }
 
   // ---- passive (passive.py:80-200)
@@ -588,8 +600,27 @@ __device__ void smooth_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<
   const int oAct = m.D(D_act), oActdot = m.D(D_act_dot), oQfa = m.D(D_qfrc_actuator), oForce = m.D(D_actuator_force);
   for (int i = 0; i < nv; ++i) d.set(oQfa + i, T(0));
   for (int i = 0; i < na; ++i) d.set(oActdot + i, T(0));
-  if (nu && !(flags & DSBL_ACTUATION)) {
-    for (int u = 0; u < nu; ++u) {
+  const bool actuate = nu && !(flags & DSBL_ACTUATION);
+  for (int u = 0; u < nu; ++u) {   // transmission outputs exist even when actuation is disabled
+    int mfirst, mcnt;
+    T mom[6], len, vel;
+    transmission(u, &mfirst, &mcnt, mom, &len, &vel);
+    d.set(oAlen + u, len);
+    d.set(oAvel + u, vel);
+    if (mcnt < 0) {
+      const T g0 = m.F(F_act_gear)[6 * u];
+      const int id = m.I(I_act_trnid)[u];
+      for (int i = 0; i < nv; ++i) d.set(oAmom + u * nv + i, d.get(m.D(D_ten_J) + id * nv + i) * g0);
+    } else {
+      for (int i = 0; i < nv; ++i) {
+        const int k = i - mfirst;
+        T v = T(0);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) if (c == k && c < mcnt) v = mom[c];
+        d.set(oAmom + u * nv + i, v);
+      }
+    }
+    if (actuate) {
       T ctrl = in_get<T>(in.ctrl, B, env, u);
       if (!(flags & DSBL_CLAMPCTRL) && m.I(I_act_ctrllimited)[u])
         ctrl = t_min(t_max(ctrl, m.F(F_act_ctrlrange)[2 * u]), m.F(F_act_ctrlrange)[2 * u + 1]);
@@ -624,7 +655,6 @@ __device__ void smooth_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<
       const int gt = m.I(I_act_gaintype)[u], bt = m.I(I_act_biastype)[u];
       const T* gp = m.F(F_act_gainprm) + 10 * u;
       const T* bp = m.F(F_act_biasprm) + 10 * u;
-      const T len = d.get(oAlen + u), vel = d.get(oAvel + u);
       T gain = gp[0], bias = 0;
       if (gt == GAIN_AFFINE) gain = gp[0] + gp[1] * len + gp[2] * vel;
       // TODO(muscle gain/bias): refused at device_put
@@ -632,12 +662,25 @@ __device__ void smooth_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<
       T force = gain * ctrl_act + bias;
       if (m.I(I_act_forcelimited)[u]) force = t_min(t_max(force, m.F(F_act_forcerange)[2 * u]), m.F(F_act_forcerange)[2 * u + 1]);
       d.set(oForce + u, force);
-      if (force != T(0))
-        for (int i = 0; i < nv; ++i) {
-          const T mm = d.get(oAmom + u * nv + i);
-          if (mm != T(0)) d.set(oQfa + i, d.get(oQfa + i) + mm * force);
+      if (force != T(0)) {
+        if (mcnt < 0) {
+          const T g0 = m.F(F_act_gear)[6 * u];
+          const int id = m.I(I_act_trnid)[u];
+          for (int i = 0; i < nv; ++i) {
+            const T mm = d.get(m.D(D_ten_J) + id * nv + i) * g0;
+            if (mm != T(0)) d.set(oQfa + i, d.get(oQfa + i) + mm * force);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 6; ++c)
+            if (c < mcnt && mom[c] != T(0)) d.set(oQfa + mfirst + c, d.get(oQfa + mfirst + c) + mom[c] * force);
         }
+      }
+    } else {
+      d.set(oForce + u, T(0));
     }
+  }
+  if (actuate) {
     for (int i = 0; i < nv; ++i) {
       const int j = m.I(I_dof_jntid)[i];
       T q = d.get(oQfa + i);
@@ -645,8 +688,6 @@ __device__ void smooth_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<
       if (m.I(I_jnt_actfrclimited)[j]) q = t_min(t_max(q, m.F(F_jnt_actfrcrange)[2 * j]), m.F(F_jnt_actfrcrange)[2 * j + 1]);
       d.set(oQfa + i, q);
     }
-  } else {
-    for (int u = 0; u < nu; ++u) d.set(oForce + u, T(0));
   }
 
   // ---- qfrc_smooth (forward.py:222-228; qacc_smooth is solved in k_solve where M is factorised)
