@@ -97,7 +97,7 @@ def _run(m: Model, d: Data, mode: int) -> Data:
     for name in _OUT_FIELDS:
         shp = m.field_shape[name]
         v = sl(name)
-        new[name] = v.reshape(*lead, *shp) if shp else v.reshape(*lead)
+        new[name] = v.reshape(tuple(lead) + tuple(shp))
     # model-constant contact fields (reference collision_driver._compute_static_contact_dict :691-793); efc_address is
     # re-derived cone-aware every step by the reference (constraint.py:636-646), so it always comes from the model
     key = (lead, str(out.device))

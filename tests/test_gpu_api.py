@@ -1,0 +1,150 @@
+"""GPU tests of the public API surface (reference call forms): vmap(step), stage functions, immutability, streams,
+the C ABI called directly with raw device pointers, and loud failure on CPU tensors."""
+
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _batch(name="humanoid", B=32, dtype=torch.float64, drop=0.4):
+    import mujoco_torch_b200 as mt
+
+    mj = util.load_model(name)
+    qpos, qvel, ctrl = util.seeded_state(mj, B, drop=drop)
+    mx = mt.device_put(mj, dtype=dtype).to("cuda:0")
+    d = mt.make_data(mx).expand(B).clone()
+    d = d.replace(qpos=torch.as_tensor(qpos, device="cuda:0").to(dtype), qvel=torch.as_tensor(qvel, device="cuda:0").to(dtype),
+                  ctrl=torch.as_tensor(ctrl, device="cuda:0").to(dtype))
+    return mt, mj, mx, d
+
+
+def test_vmap_call_form_equals_batched_step():
+    """reference README: ``torch.vmap(lambda d: mujoco_torch.step(mx, d))(batch)``."""
+    mt, mj, mx, d = _batch()
+    direct = mt.step(mx, d)
+    vm = torch.vmap(lambda x: mt.step(mx, x))(d)
+    for k in ("qpos", "qvel", "qacc", "qacc_warmstart", "efc_force", "xpos", "sensordata"):
+        assert torch.equal(getattr(direct, k), getattr(vm, k)), k
+    assert torch.equal(direct.contact.dist, vm.contact.dist)
+
+
+def test_stack_of_single_env_data_equals_expand():
+    mt, mj, mx, d = _batch(B=4)
+    singles = [d[i] for i in range(4)]
+    stacked = torch.stack(singles)
+    a, b = mt.step(mx, d), mt.step(mx, stacked)
+    assert torch.equal(a.qpos, b.qpos) and torch.equal(a.qacc, b.qacc)
+    one = mt.step(mx, singles[2])          # unbatched Data, like the reference's eager call
+    assert one.qpos.shape == (mj.nq,)
+    assert torch.equal(one.qpos, a.qpos[2])
+
+
+def test_step_never_mutates_its_input():
+    mt, mj, mx, d = _batch()
+    before = {k: getattr(d, k).clone() for k in ("qpos", "qvel", "ctrl", "qacc_warmstart", "time")}
+    out = mt.step(mx, d)
+    for k, v in before.items():
+        assert torch.equal(getattr(d, k), v), k
+    assert out.qpos.data_ptr() != d.qpos.data_ptr()
+    assert float((out.time - d.time).min()) > 0
+
+
+def test_stage_functions_match_forward():
+    mt, mj, mx, d = _batch()
+    full = mt.forward(mx, d)
+    k = mt.kinematics(mx, d)
+    assert torch.equal(k.xpos, full.xpos) and torch.equal(k.geom_xmat, full.geom_xmat)
+    assert torch.equal(k.qvel, d.qvel)
+    c = mt.make_constraint(mx, mt.collision(mx, mt.crb(mx, mt.com_pos(mx, k))))
+    # the chain restarts from kinematics' renormalised quaternions: equal up to a second normalisation's rounding
+    assert torch.allclose(c.efc_J, full.efc_J, rtol=0, atol=1e-12) and torch.allclose(c.contact.dist, full.contact.dist, rtol=0, atol=1e-12)
+    s = mt.solve(mx, full)
+    assert torch.equal(s.qacc, full.qacc) and torch.equal(s.efc_force, full.efc_force)
+
+
+def test_forward_then_step_are_consistent():
+    mt, mj, mx, d = _batch(name="halfcheetah", drop=0.6)
+    f = mt.forward(mx, d)
+    s = mt.step(mx, d)
+    dt = float(mj.opt.timestep)
+    # semi-implicit Euler without damping terms would be qvel + dt*qacc; halfcheetah has damping, so only check direction
+    assert torch.isfinite(s.qvel).all() and torch.isfinite(f.qacc).all()
+    assert torch.equal(f.qpos, d.qpos)
+    assert float((s.qvel - d.qvel).abs().max()) <= dt * float(f.qacc.abs().max()) * 1.0001 + 1e-12
+
+
+def test_side_stream_launch():
+    mt, mj, mx, d = _batch()
+    ref = mt.step(mx, d)
+    st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(st):
+        out = mt.step(mx, d)
+    st.synchronize()
+    assert torch.equal(out.qpos, ref.qpos) and torch.equal(out.qacc, ref.qacc)
+
+
+def test_cpu_tensors_fail_loudly():
+    mt, mj, mx, d = _batch(B=2)
+    with pytest.raises(Exception):
+        mt.step(mx, d.to("cpu"))
+
+
+def test_c_abi_direct_call_with_raw_pointers():
+    """include/mjt.h used the way a foreign binding would: raw env-minor device buffers, no torch types in the call."""
+    from mujoco_torch_b200 import ops
+
+    mt, mj, mx, d = _batch(B=16)
+    L = ops.lib()
+    h = ops.model_handle(mx)
+    W = L.mjt_model_data_words(h)
+    assert W == mx.data_words and L.mjt_model_dtype_size(h) == 8
+    B = 16
+    em = lambda x: x.reshape(B, -1).t().contiguous()          # (n, B): env-minor
+    bufs = {k: em(getattr(d, k)) for k in ("qpos", "qvel", "ctrl", "qacc_warmstart", "time")}
+    s = ops.StateIn()
+    for k, v in bufs.items():
+        setattr(s, k, v.data_ptr())                            # everything else stays NULL (= zeros)
+    out = torch.empty((W, B), dtype=torch.float64, device="cuda:0")
+    rc = L.mjt_step(h, ctypes.byref(s), out.data_ptr(), None, B, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0, L.mjt_last_error()
+    torch.cuda.synchronize()
+    off, n = ctypes.c_int(), ctypes.c_int()
+    assert L.mjt_model_field(h, b"qpos", ctypes.byref(off), ctypes.byref(n)) == 0
+    got = out[off.value: off.value + n.value].t()
+    ref = mt.step(mx, d)
+    assert torch.equal(got, ref.qpos)
+    assert L.mjt_model_field(h, b"no_such_field", ctypes.byref(off), ctypes.byref(n)) != 0
+    # required inputs are validated
+    s2 = ops.StateIn()
+    assert L.mjt_step(h, ctypes.byref(s2), out.data_ptr(), None, B, None) != 0
+    assert b"required" in L.mjt_last_error()
+
+
+def test_thousand_step_rollout_stays_finite_and_tracks_f64():
+    """BASELINE: 1000-step drift reported.  f32 and f64 rollouts of the same envs; report and bound the divergence of
+    the root height (chaotic contact dynamics: only boundedness is asserted, the drift is printed)."""
+    import mujoco_torch_b200 as mt
+
+    mj = util.load_model("halfcheetah")
+    B = 64
+    qpos, qvel, ctrl = util.seeded_state(mj, B, drop=0.0)
+    outs = {}
+    for dtype in (torch.float64, torch.float32):
+        mx = mt.device_put(mj, dtype=dtype).to("cuda:0")
+        d = mt.make_data(mx).expand(B).clone()
+        d = d.replace(qpos=torch.as_tensor(qpos, device="cuda:0").to(dtype), qvel=torch.as_tensor(qvel, device="cuda:0").to(dtype),
+                      ctrl=torch.as_tensor(0.3 * ctrl, device="cuda:0").to(dtype))
+        for _ in range(1000):
+            d = mt.step(mx, d)
+        assert torch.isfinite(d.qpos).all() and torch.isfinite(d.qvel).all()
+        outs[dtype] = d.qpos.double().cpu()
+    drift = (outs[torch.float32] - outs[torch.float64]).abs()
+    print(f"1000-step f32-vs-f64 drift: median {float(drift.median()):.3e} max {float(drift.max()):.3e}")
+    assert float(outs[torch.float64][:, 1].abs().max()) < 5.0   # root z stays near the floor
