@@ -132,10 +132,12 @@ struct SolveCtx {
       const int i = lane + 32 * k;
       if (i < nv) {
         const T* row = A + tri(i);
-        T acc = 0;
-        for (int c = 0; c <= i; ++c) acc += row[c] * xs()[c];
-        for (int c = i + 1; c < nv; ++c) acc += A[tri(c) + i] * xs()[c];
-        y.v[k] = acc;
+        const T* x = xs();
+        T acc = 0, acc2 = 0;   // two independent chains: row part (contiguous) and column part (strided)
+        for (int c = 0; c <= i; ++c) acc += row[c] * x[c];
+        const T* colp = A + tri(i + 1) + i;
+        for (int c = i + 1; c < nv; ++c) { acc2 += colp[0] * x[c]; colp += c + 1; }
+        y.v[k] = acc + acc2;
       }
     }
     return y;
@@ -148,8 +150,12 @@ struct SolveCtx {
       const int ns = src_nsup[sidx];
       const int* col = sup_col + src_cadr[sidx];
       const T* jr = Jc() + row_jadr[r];
-      T acc = 0;
-      for (int k = 0; k < ns; ++k) acc += jr[k] * xs()[col[k]];
+      const T* x = xs();
+      T acc = 0, acc2 = 0;
+      int k = 0;
+      for (; k + 1 < ns; k += 2) { acc += jr[k] * x[col[k]]; acc2 += jr[k + 1] * x[col[k + 1]]; }
+      if (k < ns) acc += jr[k] * x[col[k]];
+      acc += acc2;
       out[r] = sub ? acc - sub[r] : acc;
     }
     __syncwarp();
@@ -201,8 +207,7 @@ struct SolveCtx {
         const T inv = t_rsqrt(sdiag);
         const T lij = (lane == j) ? sdiag * inv : acc * inv;
         r[j] = lane >= j ? lij : T(0);
-        __syncwarp();
-        if (mine && lane >= j) rowi[j] = lij;
+        if (mine && lane >= j) rowi[j] = lij;   // column j of other rows is not read during this step: no hazard
         if (lane == 0) di[j] = inv;
         __syncwarp();
       }
