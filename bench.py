@@ -263,19 +263,13 @@ def main():
     # ---- end to end through the public API from pinned host buffers
     e2e = None
     if not args.no_e2e:
-        keys_in = ("qpos", "qvel", "qacc_warmstart", "ctrl")
-        keys_out = ("qpos", "qvel", "qacc_warmstart")
-        host = {k: getattr(d, k).detach().cpu().contiguous().pin_memory() for k in keys_in}
-        base = d
-        nb_in = sum(host[k].numel() * host[k].element_size() for k in keys_in)
-        nb_out = sum(host[k].numel() * host[k].element_size() for k in keys_out)
+        # public API for host-resident state: HostPipeline keeps qpos/qvel/qacc_warmstart/ctrl in pinned host memory and
+        # runs H2D -> step -> D2H chunk by chunk on separate streams (2 chunks by default) (transfers of one chunk overlap kernels of another)
+        pipe = mt.HostPipeline(mx, d, nchunk=int(os.environ.get("MJT_E2E_CHUNKS", "2")))
+        nb_in, nb_out = pipe.h2d_bytes, pipe.d2h_bytes
 
         def e2e_step():
-            dev_in = {k: host[k].to(dev, non_blocking=True) for k in keys_in}
-            out = mt.step(mx, base.replace(**dev_in))
-            for k in keys_out:
-                host[k].copy_(getattr(out, k), non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            pipe.step()
 
         for _ in range(3):
             e2e_step()

@@ -1,0 +1,70 @@
+"""Host-resident stepping: ``HostPipeline`` keeps the batch state in pinned host memory and runs
+``host -> device copy, step(m, d), device -> host copy`` chunk by chunk on separate CUDA streams, so that one chunk's
+PCIe transfers overlap another chunk's kernels.
+
+This is the end-to-end form of :func:`mujoco_torch_b200.step` for callers whose simulation state lives on the host
+(an external policy or logger that consumes ``qpos`` / ``qvel`` every step).  Environments are independent, so the
+chunks are too; the result is identical to one ``step`` over the whole batch.
+"""
+
+from __future__ import annotations
+
+import torch
+
+from . import api
+from .data import Data
+from .model import Model
+
+IN_FIELDS = ("qpos", "qvel", "qacc_warmstart", "ctrl")
+OUT_FIELDS = ("qpos", "qvel", "qacc_warmstart")
+
+
+class HostPipeline:
+    """``pipe = HostPipeline(mx, d0, nchunk=4)``; ``pipe.step()`` advances the host-resident state by one timestep.
+
+    * ``pipe.host[c][name]`` -- pinned ``(n, B_c)`` tensors (env-minor, the layout the kernels read) per chunk ``c``;
+      the caller writes ``ctrl`` (and may rewrite any state field) there between steps.
+    * ``step()`` copies the inputs of every chunk to the device, steps it, and copies ``qpos, qvel, qacc_warmstart``
+      back into the same pinned buffers.  It returns after all streams have drained.
+    """
+
+    def __init__(self, m: Model, d: Data, nchunk: int = 4, in_fields=IN_FIELDS, out_fields=OUT_FIELDS):
+        if d.qpos.dim() != 2:
+            raise ValueError("HostPipeline expects a batched Data with one leading batch dim")
+        if not d.qpos.is_cuda:
+            raise RuntimeError("HostPipeline needs the template Data on the model's CUDA device (there is no CPU path)")
+        self.m, self.in_fields, self.out_fields = m, tuple(in_fields), tuple(out_fields)
+        B = d.qpos.shape[0]
+        nchunk = max(1, min(nchunk, B))
+        bounds = [(B * c) // nchunk for c in range(nchunk + 1)]
+        self.slices = [slice(bounds[c], bounds[c + 1]) for c in range(nchunk)]
+        self.streams = [torch.cuda.Stream(device=d.qpos.device) for _ in range(nchunk)]
+        self.base = [d[s] for s in self.slices]       # per-chunk template (fields that never travel stay on the device)
+        self.host = []
+        for s in self.slices:
+            bufs = {}
+            for k in set(self.in_fields) | set(self.out_fields):
+                v = getattr(d, k)[s]
+                bufs[k] = v.reshape(v.shape[0], -1).t().contiguous().cpu().pin_memory()   # (n, B_c)
+            self.host.append(bufs)
+        self.h2d_bytes = sum(b[k].numel() * b[k].element_size() for b in self.host for k in self.in_fields)
+        self.d2h_bytes = sum(b[k].numel() * b[k].element_size() for b in self.host for k in self.out_fields)
+
+    def step(self, synchronize: bool = True):
+        cur = torch.cuda.current_stream()
+        for st in self.streams:
+            st.wait_stream(cur)
+        for c, st in enumerate(self.streams):
+            with torch.cuda.stream(st):
+                dev = {k: self.host[c][k].to(self.base[c].qpos.device, non_blocking=True).t() for k in self.in_fields}
+                out = api.step(self.m, self.base[c].replace(**dev))
+                for k in self.out_fields:
+                    v = getattr(out, k)
+                    self.host[c][k].copy_(v.reshape(v.shape[0], -1).t(), non_blocking=True)
+        if synchronize:
+            for st in self.streams:
+                st.synchronize()
+
+    def gather(self, name: str) -> torch.Tensor:
+        """Host state field as one ``(B, n)`` tensor (a copy)."""
+        return torch.cat([b[name].t() for b in self.host], dim=0)

@@ -90,6 +90,19 @@ def test_side_stream_launch():
     assert torch.equal(out.qpos, ref.qpos) and torch.equal(out.qacc, ref.qacc)
 
 
+def test_host_pipeline_equals_direct_step():
+    """Chunked host<->device pipeline (bench.py's e2e path) == one step over the whole batch, for two steps."""
+    mt, mj, mx, d = _batch(B=48)
+    pipe = mt.HostPipeline(mx, d, nchunk=4)
+    ref = d
+    for _ in range(2):
+        pipe.step()
+        ref = mt.step(mx, ref.replace(ctrl=d.ctrl))
+        for k in ("qpos", "qvel", "qacc_warmstart"):
+            assert torch.equal(pipe.gather(k), getattr(ref, k).cpu()), k
+    assert pipe.h2d_bytes == 48 * (mj.nq + 2 * mj.nv + mj.nu) * 8 and pipe.d2h_bytes == 48 * (mj.nq + 2 * mj.nv) * 8
+
+
 def test_cpu_tensors_fail_loudly():
     mt, mj, mx, d = _batch(B=2)
     with pytest.raises(Exception):
