@@ -84,6 +84,7 @@ CASES = [
     ("swimmer", "swimmer", {}, 3, 0.0, 1),
     ("pendula", "pendula", {}, 3, 0.0, 1),
     ("frictionloss_dof", "frictionloss_dof", {}, 3, 0.0, 1),
+    ("equality_bodies", "equality_bodies", {}, 4, 0.0, 1),
     ("convex", "convex", {}, 4, -1.0, 1),
     ("shapes", "shapes", {}, 4, -1.0, 1),
     ("shapes_elliptic", "shapes", {"cone": 1}, 6, -1.0, 1),

@@ -45,6 +45,7 @@ CASES = [
     ("swimmer", {}, 0.0),
     ("pendula", {}, 0.0),
     ("frictionloss_dof", {}, 0.0),
+    ("equality_bodies", {}, 0.0),          # connect / weld / joint equalities + contacts
     # convex narrowphase (drop -1: loose pile of free bodies, drop -2: the model's own stack, squeezed)
     ("convex", {}, -1.0),
     ("shapes", {}, -1.0),
@@ -204,16 +205,19 @@ def _compare(mj, B, dtype, tol, drop):
         assert torch.equal(act_o | near, act_c | near), "active contact set differs"
         check("contact.dist", dc.contact.dist, do.contact_dist)
         gt = torch.as_tensor(np.asarray(mj.geom_type))
-        # slots of convex pairs that are inactive carry an arbitrary (tie-broken) manifold point: compare active ones only
-        convex_slot = gt[mo.contact["geom2"]] >= 6
-        pe = (dc.contact.pos.cpu().double() - do.contact_pos.double()).abs().amax(-1) / max(float(do.contact_pos.abs().max()), 1e-6)
-        pe = torch.where(convex_slot[None, :] & ~act_o, torch.zeros_like(pe), pe).amax(1)
-        if float(pe[ok].max()) > 10 * tol:
-            bad["contact.pos"] = float(pe[ok].max())
         gs = torch.as_tensor(np.asarray(mj.geom_size))[:, 0]
         rsum = gs[mo.contact["geom1"]] + gs[mo.contact["geom2"]]
         round_pair = (gt[mo.contact["geom1"]] >= 2) & (gt[mo.contact["geom1"]] <= 3) & (gt[mo.contact["geom2"]] >= 2) & (gt[mo.contact["geom2"]] <= 3)
         degen = round_pair[None, :] & ((do.contact_dist.double() + rsum[None, :]).abs() < 1e-5)
+        # slots of convex pairs that are inactive carry an arbitrary (tie-broken) manifold point: compare active ones only
+        convex_slot = gt[mo.contact["geom2"]] >= 6
+        pe = (dc.contact.pos.cpu().double() - do.contact_pos.double()).abs().amax(-1) / max(float(do.contact_pos.abs().max()), 1e-6)
+        # f32: the closest-point formulas are ill-conditioned for (near-)parallel segments (1e-6 regulariser vs f32 rounding of
+        # 1 - cos^2); a far-apart inactive pair may place its witness point anywhere along the segment -- it is never used
+        far = (do.contact_dist.double() > 0.1) if f32 else torch.zeros_like(degen)
+        pe = torch.where((convex_slot[None, :] & ~act_o) | degen | far, torch.zeros_like(pe), pe).amax(1)
+        if float(pe[ok].max()) > 10 * tol:
+            bad["contact.pos"] = float(pe[ok].max())
         fe = (dc.contact.frame.cpu().double() - do.contact_frame.double()).abs().amax((-1, -2))
         fe = torch.where(degen, torch.zeros_like(fe), fe).amax(1)
         if float(fe[ok].max()) > 10 * tol:
