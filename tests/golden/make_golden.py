@@ -85,6 +85,8 @@ CASES = [
     ("pendula", "pendula", {}, 3, 0.0, 1),
     ("frictionloss_dof", "frictionloss_dof", {}, 3, 0.0, 1),
     ("equality_bodies", "equality_bodies", {}, 4, 0.0, 1),
+    ("sink", "sink", {}, 6, -3.0, 1),
+    ("sink_elliptic", "sink", {"cone": 1}, 4, -3.0, 1),
     ("convex", "convex", {}, 4, -1.0, 1),
     ("shapes", "shapes", {}, 4, -1.0, 1),
     ("shapes_elliptic", "shapes", {"cone": 1}, 6, -1.0, 1),
@@ -95,7 +97,10 @@ CASES = [
 def run_case(name, model, opt, B, drop, nsteps):
     lite = util.load_model(model, **opt)
     qpos, qvel, ctrl = util.seeded_state(lite, B, drop=drop)
-    if drop < 0:  # pile-up state: every free body lowered and tilted so that convex pairs interpenetrate
+    act = None
+    if drop < -2.5:
+        qpos, qvel, ctrl, act = util.sink_state(lite, B)
+    elif drop < 0:  # pile-up state: every free body lowered and tilted so that convex pairs interpenetrate
         qpos, qvel, ctrl = util.pile_state(lite, B) if drop > -1.5 else util.stack_state(lite, B)
     mx = ref_device.device_put(mujoco.MjModel(lite))
     dx0 = ref_io.make_data(mx)
@@ -103,13 +108,15 @@ def run_case(name, model, opt, B, drop, nsteps):
     cons = {k: [] for k in CONTACT_FIELDS}
     for b in range(B):
         d = dx0.replace(qpos=torch.as_tensor(qpos[b]), qvel=torch.as_tensor(qvel[b]), ctrl=torch.as_tensor(ctrl[b]))
+        if act is not None:
+            d = d.replace(act=torch.as_tensor(act[b]))
         for _ in range(nsteps):
             d = ref_forward.step(mx, d)
         for k in OUT_FIELDS:
             outs[k].append(np.asarray(getattr(d, k)))
         for k in CONTACT_FIELDS:
             cons[k].append(np.asarray(getattr(d.contact, k)))
-    save = {"in_qpos": qpos, "in_qvel": qvel, "in_ctrl": ctrl, "nsteps": np.int64(nsteps),
+    save = {"in_qpos": qpos, "in_qvel": qvel, "in_ctrl": ctrl, **({"in_act": act} if act is not None else {}), "nsteps": np.int64(nsteps),
             "opt_keys": np.array(list(opt.keys()), dtype="U32"), "opt_vals": np.array(list(opt.values()), dtype=np.float64),
             "model": np.array(model), "torch_version": np.array(torch.__version__)}
     for k, v in outs.items():

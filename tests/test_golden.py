@@ -106,7 +106,8 @@ def _recorded_branch(z, mj, get_contact, get):
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
 def test_oracle_matches_reference(path):
     z, mj = _load(path)
-    mo, do = util.run_oracle(mj, z["in_qpos"], z["in_qvel"], z["in_ctrl"], torch.float64, nsteps=int(z["nsteps"]))
+    mo, do = util.run_oracle(mj, z["in_qpos"], z["in_qvel"], z["in_ctrl"], torch.float64, nsteps=int(z["nsteps"]),
+                             act=z["in_act"] if "in_act" in z.files else None)
     ocon = {"dist": "contact_dist", "pos": "contact_pos", "frame": "contact_frame"}
 
     def get_contact(k):
@@ -130,6 +131,7 @@ def test_oracle_matches_reference(path):
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
 def test_cuda_matches_reference(path):
     z, mj = _load(path)
-    mx, dc = util.run_cuda(mj, z["in_qpos"], z["in_qvel"], z["in_ctrl"], torch.float64, nsteps=int(z["nsteps"]))
+    mx, dc = util.run_cuda(mj, z["in_qpos"], z["in_qvel"], z["in_ctrl"], torch.float64, nsteps=int(z["nsteps"]),
+                           act=z["in_act"] if "in_act" in z.files else None)
     sel, zs = _recorded_branch(z, mj, lambda k: getattr(dc.contact, k).cpu().numpy(), lambda k: getattr(dc, k).cpu().numpy())
     _check(zs, lambda k: getattr(dc, k).cpu().numpy()[sel], lambda k: getattr(dc.contact, k).cpu().numpy()[sel], "cuda")

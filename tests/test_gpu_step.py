@@ -46,6 +46,11 @@ CASES = [
     ("pendula", {}, 0.0),
     ("frictionloss_dof", {}, 0.0),
     ("equality_bodies", {}, 0.0),          # connect / weld / joint equalities + contacts
+    # drop -3: assets/xml/sink.xml -- ball / slide / tendon limits, friction loss, gravcomp, actuator dynamics, condim 1/4/6
+    ("sink", {}, -3.0),
+    ("sink", {"cone": 1}, -3.0),
+    ("sink", {"integrator": 3}, -3.0),     # ImplicitFast with na != nu: the reference crashes here, oracle only
+    ("sink", {"integrator": 1}, -3.0),
     # convex narrowphase (drop -1: loose pile of free bodies, drop -2: the model's own stack, squeezed)
     ("convex", {}, -1.0),
     ("shapes", {}, -1.0),
@@ -113,12 +118,15 @@ def _compare(mj, B, dtype, tol, drop):
 
     f32 = dtype == torch.float32
     eps = 1e-7 if f32 else 2e-16
+    act = None
     if drop >= 0:
         qpos, qvel, ctrl = util.seeded_state(mj, B, drop=drop)
+    elif drop < -2.5:
+        qpos, qvel, ctrl, act = util.sink_state(mj, B)
     else:
         qpos, qvel, ctrl = util.pile_state(mj, B) if drop > -1.5 else util.stack_state(mj, B)
-    mx, dc = util.run_cuda(mj, qpos, qvel, ctrl, dtype)
-    if drop < 0:
+    mx, dc = util.run_cuda(mj, qpos, qvel, ctrl, dtype, act=act)
+    if -2.5 < drop < 0:
         # convex scenes: (A) the manifolds themselves, tie-aware; (B) everything downstream of the narrowphase with the
         # oracle replaying the CUDA manifolds, so that a tie broken the other way does not mask a real difference
         _check_manifolds(mj, dc, qpos, qvel, ctrl, tol, eps, 0.8 if f32 else 0.9)
@@ -130,13 +138,13 @@ def _compare(mj, B, dtype, tol, drop):
 
         oforward.CONTACT_HOOK = replay
     try:
-        mo, do = util.run_oracle(mj, qpos, qvel, ctrl, dtype)
-        truth = util.run_oracle(mj, qpos, qvel, ctrl, torch.float64)[1] if f32 else do
+        mo, do = util.run_oracle(mj, qpos, qvel, ctrl, dtype, act=act)
+        truth = util.run_oracle(mj, qpos, qvel, ctrl, torch.float64, act=act)[1] if f32 else do
         rng = np.random.RandomState(7)
         variants = [do]
         for _ in range(NPERT):
             pq, pv = _perturbed(qpos, qvel, eps, rng)
-            variants.append(util.run_oracle(mj, pq, pv, ctrl, dtype)[1])
+            variants.append(util.run_oracle(mj, pq, pv, ctrl, dtype, act=act)[1])
     finally:
         oforward.CONTACT_HOOK = None
 

@@ -70,7 +70,32 @@ def stack_state(mj, B, seed=5):
     return qpos, qvel, rng.uniform(-1, 1, size=(B, mj.nu))
 
 
-def run_oracle(mj, qpos, qvel, ctrl, dtype=torch.float64, nsteps=1, warm=None):
+def sink_state(mj, B, seed=9):
+    """assets/xml/sink.xml: joints pushed past their limits in about half of the envs, free bodies pressed into the floor,
+    non-zero actuator activations."""
+    rng = np.random.RandomState(seed)
+    qpos = np.tile(np.asarray(mj.qpos0), (B, 1))
+    for j in range(mj.njnt):
+        t, a = int(mj.jnt_type[j]), int(mj.jnt_qposadr[j])
+        if t == 0:      # free: sink a little, random tilt
+            qpos[:, a:a + 2] += rng.uniform(-0.02, 0.02, size=(B, 2))
+            qpos[:, a + 2] -= rng.uniform(0.0, 0.03, size=B)
+            q = np.array([1.0, 0, 0, 0]) + 0.3 * rng.randn(B, 4)
+            qpos[:, a + 3:a + 7] = q / np.linalg.norm(q, axis=1, keepdims=True)
+        elif t == 1:    # ball: rotation angle up to ~1 rad about a random axis (limit 0.6)
+            ang = rng.uniform(0.0, 1.0, size=B)
+            ax = rng.randn(B, 3)
+            ax /= np.linalg.norm(ax, axis=1, keepdims=True)
+            qpos[:, a] = np.cos(ang / 2)
+            qpos[:, a + 1:a + 4] = ax * np.sin(ang / 2)[:, None]
+        else:           # slide / hinge: up to 1.3 x the range
+            lo, hi = mj.jnt_range[j]
+            qpos[:, a] = rng.uniform(1.3 * lo, 1.3 * hi, size=B)
+    qvel = 0.5 * rng.randn(B, mj.nv)
+    return qpos, qvel, rng.uniform(-1.5, 1.5, size=(B, mj.nu)), rng.uniform(-0.6, 0.6, size=(B, mj.na))
+
+
+def run_oracle(mj, qpos, qvel, ctrl, dtype=torch.float64, nsteps=1, warm=None, act=None):
     from oracle import forward as of
     from oracle import model as om
 
@@ -79,12 +104,14 @@ def run_oracle(mj, qpos, qvel, ctrl, dtype=torch.float64, nsteps=1, warm=None):
     d.qpos, d.qvel, d.ctrl = (torch.as_tensor(x).to(dtype) for x in (qpos, qvel, ctrl))
     if warm is not None:
         d.qacc_warmstart = torch.as_tensor(warm).to(dtype)
+    if act is not None:
+        d.act = torch.as_tensor(act).to(dtype)
     for _ in range(nsteps):
         d = of.step(m, d)
     return m, d
 
 
-def run_cuda(mj, qpos, qvel, ctrl, dtype=torch.float64, nsteps=1, warm=None, device="cuda:0"):
+def run_cuda(mj, qpos, qvel, ctrl, dtype=torch.float64, nsteps=1, warm=None, device="cuda:0", act=None):
     import mujoco_torch_b200 as mt
 
     mx = mt.device_put(mj, dtype=dtype).to(device)
@@ -93,6 +120,8 @@ def run_cuda(mj, qpos, qvel, ctrl, dtype=torch.float64, nsteps=1, warm=None, dev
               ctrl=torch.as_tensor(ctrl, device=device).to(dtype))
     if warm is not None:
         kw["qacc_warmstart"] = torch.as_tensor(warm, device=device).to(dtype)
+    if act is not None:
+        kw["act"] = torch.as_tensor(act, device=device).to(dtype)
     d = d.replace(**kw)
     for _ in range(nsteps):
         d = mt.step(mx, d)
