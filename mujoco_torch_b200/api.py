@@ -93,11 +93,20 @@ def _run(m: Model, d: Data, mode: int) -> Data:
     if flat:
         out = out.reshape(*lead, out.shape[-1])
     new = dict(d._fields)
-    sl = lambda name: out[..., m.field_off[name]: m.field_off[name] + int(np.prod(m.field_shape[name]) if m.field_shape[name] else 1)]
+    # one split call makes every field's view (host overhead matters at small batch sizes); fields are laid out back to
+    # back in L.D_FIELDS order
+    plan = m.__dict__.get("_field_plan")
+    if plan is None:
+        names = [n for n, _ in L.D_FIELDS]
+        sizes = [int(np.prod(m.field_shape[n])) if m.field_shape[n] else 1 for n in names]
+        plan = m.__dict__["_field_plan"] = (names, sizes, sum(sizes))
+    names, sizes, total = plan
+    parts = dict(zip(names, torch.split(out[..., :total], sizes, dim=-1)))
+    sl = parts.__getitem__
     for name in _OUT_FIELDS:
         shp = m.field_shape[name]
-        v = sl(name)
-        new[name] = v.reshape(tuple(lead) + tuple(shp))
+        v = parts[name]
+        new[name] = v if len(shp) == 1 else v.reshape(tuple(lead) + tuple(shp))
     # model-constant contact fields (reference collision_driver._compute_static_contact_dict :691-793); efc_address is
     # re-derived cone-aware every step by the reference (constraint.py:636-646), so it always comes from the model
     key = (lead, str(out.device))

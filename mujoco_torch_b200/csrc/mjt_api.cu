@@ -59,6 +59,7 @@ struct mjtModel {
   int max_smem;
   int solve_envs;  // envs (warps) per CTA in k_solve
   size_t solve_smem;
+  size_t solve_blob_bytes, solve_region_bytes;  // smem = blob + envs * region
   int hv(int k) const { return h[k]; }
 };
 
@@ -125,6 +126,8 @@ extern "C" int mjt_model_create(const void* blob_host, size_t nbytes, int device
   }
   m->solve_envs = best_e;
   m->solve_smem = sblob_b + region * best_e;
+  m->solve_blob_bytes = sblob_b;
+  m->solve_region_bytes = region;
   if (blob_b + 64 > (size_t)m->max_smem) {
     delete m;
     return fail("mjt_model_create: model blob exceeds shared memory");
@@ -174,9 +177,17 @@ static int set_smem(const void* fn, size_t bytes) {
 }
 
 // one forward pass (optionally followed by the in-kernel integrator) into `out`
+// Threads per CTA of the thread-per-env kernels: full-size CTAs once the batch fills the GPU twice over, otherwise
+// smaller CTAs so that a small batch still spreads over all SMs.
+static int env_threads(const mjtModel* m, int B) {
+  int t = MJT_ENV_THREADS;
+  while (t > 32 && (B + t - 1) / t < 2 * m->sm_count) t >>= 1;
+  return t;
+}
+
 template <typename T>
 static int run_forward(const mjtModel* m, const MjtIn& in, T* out, int B, int mode, cudaStream_t st, int* launches) {
-  const int threads = MJT_ENV_THREADS;
+  const int threads = env_threads(m, B);
   const int gx = (B + threads - 1) / threads;
   const size_t blob_b = ((size_t)m->blob_words + 3) / 4 * 16;
   const int nsens = m->hv(H_nsensordata);
@@ -203,13 +214,14 @@ static int run_forward(const mjtModel* m, const MjtIn& in, T* out, int B, int mo
   }
   {
     const int E = m->solve_envs;
+    const size_t smem = m->solve_blob_bytes + m->solve_region_bytes * E;
     const int gs = (B + E - 1) / E;
     if (m->hv(H_nv) <= 32) {
       if (set_smem<T>((const void*)k_solve<T, 1>, m->solve_smem)) return 1;
-      LAUNCH("k_solve", st, k_solve<T, 1><<<gs, 32 * E, m->solve_smem, st>>>(m->d_blob, m->d_blob + m->blob_words, m->solve_words, in, out, B, mode));
+      LAUNCH("k_solve", st, k_solve<T, 1><<<gs, 32 * E, smem, st>>>(m->d_blob, m->d_blob + m->blob_words, m->solve_words, in, out, B, mode));
     } else if (m->hv(H_nv) <= 64) {
       if (set_smem<T>((const void*)k_solve<T, 2>, m->solve_smem)) return 1;
-      LAUNCH("k_solve", st, k_solve<T, 2><<<gs, 32 * E, m->solve_smem, st>>>(m->d_blob, m->d_blob + m->blob_words, m->solve_words, in, out, B, mode));
+      LAUNCH("k_solve", st, k_solve<T, 2><<<gs, 32 * E, smem, st>>>(m->d_blob, m->d_blob + m->blob_words, m->solve_words, in, out, B, mode));
     } else {
       return fail("mjt: nv > 64 not supported by the dense solver kernel");
     }
@@ -235,7 +247,7 @@ static int run_step(const mjtModel* m, const MjtIn& in, T* out, T* scratch, int 
     return 0;
   }
   if (!scratch) return fail("mjt_step: RK4 needs a scratch buffer (mjt_model_scratch_words)");
-  const int threads = MJT_ENV_THREADS, gx = (B + threads - 1) / threads;
+  const int threads = env_threads(m, B), gx = (B + threads - 1) / threads;
   const size_t blob_b = ((size_t)m->blob_words + 3) / 4 * 16;
   const int nq = m->hv(H_nq), nv = m->hv(H_nv), na = m->hv(H_na);
   T* stage_buf = scratch;
