@@ -269,16 +269,18 @@ def main():
         nb_in, nb_out = pipe.h2d_bytes, pipe.d2h_bytes
 
         def e2e_step():
-            pipe.step()
+            pipe.step(synchronize=False)   # per-chunk streams keep their own H2D -> step -> D2H order across steps
 
         for _ in range(3):
             e2e_step()
+        pipe.synchronize()
         barrier()
         n_e2e = max(5, min(args.steps, 30))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(n_e2e):
             e2e_step()
+        pipe.synchronize()
         e1.record()
         barrier()
         el = sharding.max_over_ranks(e0.elapsed_time(e1), dev) * 1e-3

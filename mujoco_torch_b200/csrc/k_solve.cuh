@@ -443,10 +443,17 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
       for (int k = 0; k < DPL; ++k) grad.v[k] = Ma.v[k] - qfrc_smooth.v[k] - qfrc_con.v[k];
     };
     // reference _update_gradient :359-376 (the M^-1 / H^-1 application)
+    bool lm_is_m = true;   // Lm holds chol(M) (from the factor_m prologue) until a Hessian is factorised over it
     auto compute_mgrad = [&]() {
       if (newton) {
-        c.hessian(D);
-        c.cholesky(Lm);
+        unsigned any = 0;
+        for (int ch = 0; ch < Lo.nchunk; ++ch) any |= c.amask()[ch];
+        // no active row: H = M exactly, and chol(M) is already in Lm -- skip the assembly and the factorisation
+        if (any || !lm_is_m) {
+          c.hessian(D);
+          c.cholesky(Lm);
+          lm_is_m = !any;
+        }
       }
       Mgrad = c.cho_solve(Lm, grad);  // CG: Lm still holds chol(M)
     };

@@ -47,13 +47,19 @@ class HostPipeline:
                 v = getattr(d, k)[s]
                 bufs[k] = v.reshape(v.shape[0], -1).t().contiguous().cpu().pin_memory()   # (n, B_c)
             self.host.append(bufs)
+        self._primed = False
         self.h2d_bytes = sum(b[k].numel() * b[k].element_size() for b in self.host for k in self.in_fields)
         self.d2h_bytes = sum(b[k].numel() * b[k].element_size() for b in self.host for k in self.out_fields)
 
     def step(self, synchronize: bool = True):
-        cur = torch.cuda.current_stream()
-        for st in self.streams:
-            st.wait_stream(cur)
+        """One timestep for every chunk.  With ``synchronize=False`` the call only enqueues: each chunk's stream carries
+        its own ``H2D -> step -> D2H`` chain in order, so chunk A's next step starts as soon as its own results are back
+        on the host, while chunk B is still computing (call :meth:`synchronize` before reading ``host``)."""
+        if not self._primed:
+            cur = torch.cuda.current_stream()
+            for st in self.streams:
+                st.wait_stream(cur)
+            self._primed = True
         for c, st in enumerate(self.streams):
             with torch.cuda.stream(st):
                 dev = {k: self.host[c][k].to(self.base[c].qpos.device, non_blocking=True).t() for k in self.in_fields}
@@ -62,8 +68,11 @@ class HostPipeline:
                     v = getattr(out, k)
                     self.host[c][k].copy_(v.reshape(v.shape[0], -1).t(), non_blocking=True)
         if synchronize:
-            for st in self.streams:
-                st.synchronize()
+            self.synchronize()
+
+    def synchronize(self):
+        for st in self.streams:
+            st.synchronize()
 
     def gather(self, name: str) -> torch.Tensor:
         """Host state field as one ``(B, n)`` tensor (a copy)."""

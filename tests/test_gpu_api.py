@@ -100,6 +100,13 @@ def test_host_pipeline_equals_direct_step():
         ref = mt.step(mx, ref.replace(ctrl=d.ctrl))
         for k in ("qpos", "qvel", "qacc_warmstart"):
             assert torch.equal(pipe.gather(k), getattr(ref, k).cpu()), k
+    # free-running form: enqueue two more steps without waiting, then drain
+    pipe.step(synchronize=False)
+    pipe.step(synchronize=False)
+    pipe.synchronize()
+    for _ in range(2):
+        ref = mt.step(mx, ref.replace(ctrl=d.ctrl))
+    assert torch.equal(pipe.gather("qpos"), ref.qpos.cpu())
     assert pipe.h2d_bytes == 48 * (mj.nq + 2 * mj.nv + mj.nu) * 8 and pipe.d2h_bytes == 48 * (mj.nq + 2 * mj.nv) * 8
 
 
