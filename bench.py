@@ -301,13 +301,17 @@ def main():
 
     pub = PUBLISHED.get((args.model, args.dtype, B)) if int(mj.opt.integrator) == 0 and args.solver is None else None
     launches = ops.lib().mjt_step_launches(ops.model_handle(mx)) * args.steps
+    import ctypes
+
+    _e, _s = ctypes.c_int(), ctypes.c_int()
+    ops.lib().mjt_solve_config(ops.model_handle(mx), ctypes.byref(_e), ctypes.byref(_s))
     line = {
         "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": (value / pub) if pub else None, "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": workload_name(args, mj), "batch_per_gpu": B, "parallelism": f"dp{world} (envs sharded, no collective)",
                    "l2": f"per-step working set {mx.data_words * B * tsize / 1e6:.0f} MB > 126 MB L2 (inputs larger than L2)",
-                   "nv": mj.nv, "ncon": mx.ncon, "nefc": mx.nefc},
+                   "nv": mj.nv, "ncon": mx.ncon, "nefc": mx.nefc, "solve_envs_per_cta": _e.value, "solve_smem_bytes": _s.value},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "finite": finite,
         "published_baseline": {"value": pub, "hardware": "H200 f64 torch.compile(vmap) tuned, reference README.md:190"} if pub else None,
     }

@@ -26,10 +26,10 @@
 #include "k_smooth.cuh"
 
 struct SolveLayout {
-  int nP, oJ, oM, oL, oDinv, oXs, oYs, oD, oAref, oFloss, oJaref, oJv, oForce, oMask, nchunk, words;
+  int nP, oJ, oM, oL, oDinv, oXs, oYs, oD, oAref, oFloss, oJaref, oJv, oForce, oMask, oLive, nchunk, words;
 };
 
-__host__ __device__ inline SolveLayout solve_layout(int nv, int nefc, int jc_words, int nf) {
+__host__ __device__ inline SolveLayout solve_layout(int nv, int nefc, int jc_words, int nf, int nsrc, int tsize, bool compact) {
   SolveLayout s;
   s.nP = nv * (nv + 1) / 2;
   s.nchunk = (nefc + 31) / 32;
@@ -46,7 +46,9 @@ __host__ __device__ inline SolveLayout solve_layout(int nv, int nefc, int jc_wor
   s.oJaref = o; o += nefc;
   s.oJv = o; o += nefc;
   s.oForce = o; o += nefc;
-  s.oMask = o; o += 2 * s.nchunk;  // active-row and nonzero-force bitmasks (uint32 each, stored in T-sized slots)
+  s.oMask = o; o += s.nchunk;  // active-row bitmask over the *live* rows (uint32 per 32 rows, stored in T-sized slots)
+  // live-row list (nefc ints) + compact position of every source (nsrc ints), packed as ints
+  s.oLive = o; o += compact ? ((nefc + nsrc) * 4 + tsize - 1) / tsize : 0;
   s.words = (o + 3) & ~3;
   return s;
 }
@@ -75,7 +77,7 @@ __device__ __forceinline__ T vec_bcast(const Vec<T, 2>& x, int i) {
 
 __device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
 
-template <typename T, int DPL>
+template <typename T, int DPL, bool COMPACT>
 struct SolveCtx {
   const ModelView<T>& m;
   T* s;  // this env's shared-memory region
@@ -91,6 +93,10 @@ struct SolveCtx {
   const int* tri_ab;
   const int* dof_sadr;
   const int* dof_sent;
+  // COMPACT: row loops walk the live list (host picks it for models with more than two 32-row chunks); otherwise every
+  // row is visited in place with no indirection
+  static constexpr bool compact = COMPACT;
+  __device__ __forceinline__ int row_at(int idx) const { return compact ? lrow()[idx] : idx; }
 
   __device__ __forceinline__ T* Jc() const { return s + L.oJ; }
   __device__ __forceinline__ T* Mp() const { return s + L.oM; }
@@ -99,8 +105,52 @@ struct SolveCtx {
   __device__ __forceinline__ T* xs() const { return s + L.oXs; }
   __device__ __forceinline__ T* ys() const { return s + L.oYs; }
   __device__ __forceinline__ unsigned* amask() const { return reinterpret_cast<unsigned*>(s + L.oMask); }
-  __device__ __forceinline__ unsigned* fmask() const { return reinterpret_cast<unsigned*>(s + L.oMask) + L.nchunk; }
-  __device__ __forceinline__ bool row_active(int r) const { return (amask()[r >> 5] >> (r & 31)) & 1u; }
+  __device__ __forceinline__ int* lrow() const { return reinterpret_cast<int*>(s + L.oLive); }          // live row ids, ascending
+  __device__ __forceinline__ int* spos() const { return reinterpret_cast<int*>(s + L.oLive) + nefc; }   // source -> first live slot, -1 = dead
+  __device__ __forceinline__ bool slot_active(int k) const { return (amask()[k >> 5] >> (k & 31)) & 1u; }
+
+  // A source whose Jacobian block and reference accelerations are all exactly zero (inactive contact, limit or
+  // equality: constraint.py zeroes those rows) can never carry force: J.x - aref stays 0.  Such rows are dropped from
+  // every row loop; they keep Jaref = jv = force = 0.
+  // Returns the number of live rows (warp-uniform).  The context itself stays immutable so that it lives in registers.
+  __device__ __forceinline__ int build_live(const T* aref) const {
+    if (!compact) return nefc;   // few rows: every row stays in place (slot = row), nothing to build
+    const int nsrc = m.h(H_nsrc);
+    int* lr = lrow();
+    int* sp = spos();
+    int base = 0;
+    for (int s0 = 0; s0 < nsrc; s0 += 32) {
+      const int sidx = s0 + lane;
+      int nr = 0, r0 = 0;
+      bool live = false;
+      if (sidx < nsrc) {
+        r0 = src_row[sidx];
+        nr = src_nrows[sidx];
+        const int nw = nr * src_nsup[sidx];
+        const T* jp = Jc() + row_jadr[r0];
+        int nz = 0;   // branch-free so that the loads pipeline
+#pragma unroll 4
+        for (int k = 0; k < nw; ++k) nz |= (jp[k] != T(0)) ? 1 : 0;
+        for (int e = 0; e < nr; ++e) nz |= (aref[r0 + e] != T(0)) ? 1 : 0;
+        live = nz != 0;
+      }
+      const int cnt = live ? nr : 0;
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const int start = base + incl - cnt;
+      if (sidx < nsrc) {
+        sp[sidx] = live ? start : -1;
+        for (int e = 0; e < cnt; ++e) lr[start + e] = r0 + e;
+      }
+      base += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    __syncwarp();
+    return base;
+  }
 
   __device__ __forceinline__ Vec<T, DPL> zero() const {
     Vec<T, DPL> r;
@@ -143,9 +193,10 @@ struct SolveCtx {
     return y;
   }
   // out[r] = J[r,:] . x (- sub[r])   over each row's compact support
-  __device__ __forceinline__ void jmul(const Vec<T, DPL>& x, T* out, const T* sub) const {
+  __device__ __forceinline__ void jmul(const Vec<T, DPL>& x, T* out, const T* sub, int nlive) const {
     to_smem(x, xs());
-    for (int r = lane; r < nefc; r += 32) {
+    for (int idx = lane; idx < nlive; idx += 32) {
+      const int r = row_at(idx);
       const int sidx = row_src[r];
       const int ns = src_nsup[sidx];
       const int* col = sup_col + src_cadr[sidx];
@@ -171,6 +222,7 @@ struct SolveCtx {
       if (i < nv) {
         for (int q = dof_sadr[i], qe = dof_sadr[i + 1]; q < qe; ++q) {
           const int ent = dof_sent[q], sidx = ent & 0xffff, pos = ent >> 16;
+          if (compact && spos()[sidx] < 0) continue;
           const int r0 = src_row[sidx], nr = src_nrows[sidx], ns = src_nsup[sidx];
           const T* jp = Jc() + row_jadr[r0] + pos;
           const T* fp = f + r0;
@@ -293,9 +345,11 @@ struct SolveCtx {
         const int sidx = dof_sent[q] & 0xffff;
         if (src_nsup[sidx] != 1) continue;
         const int r0 = src_row[sidx], nr = src_nrows[sidx];
+        const int cs = compact ? spos()[sidx] : r0;
+        if (cs < 0) continue;
         const T* jp = Jc() + row_jadr[r0];
         for (int e = 0; e < nr; ++e)
-          if (row_active(r0 + e)) acc += D[r0 + e] * jp[e] * jp[e];
+          if (slot_active(cs + e)) acc += D[r0 + e] * jp[e] * jp[e];
       }
       H[tri(i) + i] += acc;
     }
@@ -304,9 +358,11 @@ struct SolveCtx {
     for (int sidx = 0; sidx < nsrc; ++sidx) {
       if (src_nsup[sidx] == 1) continue;
       const int r0 = src_row[sidx], nr = src_nrows[sidx];
+      const int cs = compact ? spos()[sidx] : r0;
+      if (cs < 0) continue;
       unsigned act = 0;
-      if (nr <= 32) act = active_bits(r0, nr);
-      else for (int e = 0; e < nr; ++e) act |= row_active(r0 + e) ? 1u : 0u;
+      if (nr <= 32) act = active_bits(cs, nr);
+      else for (int e = 0; e < nr; ++e) act |= slot_active(cs + e) ? 1u : 0u;
       if (!act) continue;
       const int ns = src_nsup[sidx];
       const int* col = sup_col + src_cadr[sidx];
@@ -325,7 +381,7 @@ struct SolveCtx {
           }
         } else {
           for (int e = 0; e < nr; ++e) {
-            if (!row_active(r0 + e)) continue;
+            if (!slot_active(cs + e)) continue;
             const T* jr = j0 + e * ns;
             acc += D[r0 + e] * jr[a] * jr[b];
           }
@@ -337,9 +393,9 @@ struct SolveCtx {
   }
 };
 
-template <typename T, int DPL>
+template <typename T, int DPL, bool COMPACT>
 __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T>& d, size_t B, int env,
-                          SolveCtx<T, DPL>& c, const Vec<T, DPL>& qfrc_smooth, const Vec<T, DPL>& qacc_smooth, int mode) {
+                          const SolveCtx<T, DPL, COMPACT>& c, const Vec<T, DPL>& qfrc_smooth, const Vec<T, DPL>& qacc_smooth, int mode) {
   typedef Vec<T, DPL> V;
   const int lane = c.lane;
   const int nv = c.nv, nefc = c.nefc, flags = m.h(H_disableflags);
@@ -400,15 +456,19 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
 
     V Ma, grad, Mgrad, search;
     T gauss = 0, cost = t_inf<T>(), prev_cost = 0;
+    if (c.compact)   // dead rows are never visited again: give them their final zeros now
+      for (int r = lane; r < nefc; r += 32) { Jaref[r] = T(0); jv[r] = T(0); force[r] = T(0); }
+    const int nlive = c.build_live(aref);   // rows that can carry force this step; the rest are exactly-zero rows
 
     // reference _update_constraint :320-357 (cost only, or cost + forces + J^T f)
     auto update_constraint = [&](bool with_force) {
       T cpart = 0;
-      for (int ch = 0; ch < Lo.nchunk; ++ch) {
-        const int r = (ch << 5) + lane;
+      for (int ch = 0; (ch << 5) < nlive; ++ch) {
+        const int idx = (ch << 5) + lane;
         bool act = false;
         T fo = 0;
-        if (r < nefc) {
+        if (idx < nlive) {
+          const int r = c.row_at(idx);
           const T ja = Jaref[r], dr = D[r];
           act = (ja < T(0)) || (r < ne_nf);
           T ff = 0;
@@ -425,8 +485,8 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
           if (act) cpart += T(0.5) * dr * ja * ja;
           if (with_force) force[r] = fo;
         }
-        const unsigned am = __ballot_sync(0xffffffffu, act), fm = __ballot_sync(0xffffffffu, fo != T(0));
-        if (with_force && lane == 0) { c.amask()[ch] = am; c.fmask()[ch] = fm; }
+        const unsigned am = __ballot_sync(0xffffffffu, act);
+        if (with_force && lane == 0) c.amask()[ch] = am;
       }
       __syncwarp();
       if (with_force) qfrc_con = c.jtmul(force);
@@ -447,7 +507,7 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
     auto compute_mgrad = [&]() {
       if (newton) {
         unsigned any = 0;
-        for (int ch = 0; ch < Lo.nchunk; ++ch) any |= c.amask()[ch];
+        for (int ch = 0; (ch << 5) < nlive; ++ch) any |= c.amask()[ch];
         // no active row: H = M exactly, and chol(M) is already in Lm -- skip the assembly and the factorisation
         if (any || !lm_is_m) {
           c.hessian(D);
@@ -463,7 +523,7 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
       const T smag = t_sqrt(c.dotv(search, search)) * scale;
       const T gtol = tolerance * ls_tolerance * smag;
       const V mv = c.symv(Mm, search);
-      c.jmul(search, jv, nullptr);
+      c.jmul(search, jv, nullptr, nlive);
       T qg0 = gauss, qg1, qg2;
       {
         T a = 0, b = 0, e = 0;
@@ -478,7 +538,8 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
         T q[3][3];
 #pragma unroll
         for (int a = 0; a < 3; ++a) q[a][0] = q[a][1] = q[a][2] = T(0);
-        for (int r = lane; r < nefc; r += 32) {
+        for (int idx = lane; idx < nlive; idx += 32) {
+          const int r = c.row_at(idx);
           const T ja = Jaref[r], jr = jv[r], dr = D[r];
           const T c0 = T(0.5) * ja * ja * dr, c1 = jr * ja * dr, c2 = T(0.5) * jr * jr * dr;
           T fl = 0, rf = 0;
@@ -548,7 +609,7 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
       if (improved) {
         qacc = axpy(qacc, alpha, search);
         Ma = axpy(Ma, alpha, mv);
-        for (int r = lane; r < nefc; r += 32) Jaref[r] += jv[r] * alpha;
+        for (int idx = lane; idx < nlive; idx += 32) { const int r = c.row_at(idx); Jaref[r] += jv[r] * alpha; }
         __syncwarp();
       }
     };
@@ -562,7 +623,7 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
 #pragma unroll
       for (int k = 0; k < DPL; ++k) { const int i = lane + 32 * k; warm.v[k] = i < nv ? in_get<T>(in.qacc_warmstart, B, env, i) : T(0); }
       qacc = warm;
-      c.jmul(qacc, Jaref, aref);
+      c.jmul(qacc, Jaref, aref, nlive);
       Ma = c.symv(Mm, qacc);
       Ma_w = Ma;
       cost = t_inf<T>();
@@ -570,13 +631,14 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
       cost_w = cost;
     }
     qacc = qacc_smooth;
-    c.jmul(qacc, jv, aref);  // Jaref(smooth) parked in jv while the two costs are compared
+    c.jmul(qacc, jv, aref, nlive);  // Jaref(smooth) parked in jv while the two costs are compared
     Ma = c.symv(Mm, qacc);
     {
       T* keep = Jaref;
       // evaluate the smooth cost on the parked values
       T cpart = 0;
-      for (int r = lane; r < nefc; r += 32) {
+      for (int idx = lane; idx < nlive; idx += 32) {
+        const int r = c.row_at(idx);
         const T ja = jv[r], dr = D[r];
         bool act = (ja < T(0)) || (r < ne_nf);
         if (use_floss) {
@@ -752,7 +814,7 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
   if (lane == 0) d.set(m.D(D_time), d.get(m.D(D_time)) + dt);
 }
 
-template <typename T, int DPL>
+template <typename T, int DPL, bool COMPACT>
 __global__ void __launch_bounds__((sizeof(T) == 4 ? 512 : MJT_SOLVE_F64_THREADS), (sizeof(T) == 4 ? 2 : MJT_SOLVE_F64_MINB)) k_solve(const int* __restrict__ gfull, const int* __restrict__ gblob, int blob_words, MjtIn in,
                                                T* __restrict__ out, int B, int mode) {
   extern __shared__ __align__(16) int smem_blob[];
@@ -763,7 +825,7 @@ __global__ void __launch_bounds__((sizeof(T) == 4 ? 512 : MJT_SOLVE_F64_THREADS)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int env0 = blockIdx.x * E;
   const int nv = m.h(H_nv), nefc = m.h(H_nefc);
-  const SolveLayout Lo = solve_layout(nv, nefc, m.h(H_jc_words), m.h(H_nf));
+  const SolveLayout Lo = solve_layout(nv, nefc, m.h(H_jc_words), m.h(H_nf), m.h(H_nsrc), (int)sizeof(T), COMPACT);
   T* region = reinterpret_cast<T*>(smem_blob + ((blob_words + 3) & ~3));
   const size_t Bs = (size_t)B;
 
@@ -801,7 +863,7 @@ __global__ void __launch_bounds__((sizeof(T) == 4 ? 512 : MJT_SOLVE_F64_THREADS)
   const int env = env0 + warp;
   const bool valid = env < B;
   EnvBuf<T> d{out + (valid ? env : 0), Bs};
-  SolveCtx<T, DPL> c{m, region + (size_t)warp * Lo.words, Lo, nv, nefc, lane,
+  SolveCtx<T, DPL, COMPACT> c{m, region + (size_t)warp * Lo.words, Lo, nv, nefc, lane,
                      m.I(I_row_src), m.I(I_row_jadr), m.I(I_src_nsup), m.I(I_src_cadr), m.I(I_src_row), m.I(I_src_nrows), m.I(I_sup_col), m.I(I_tri_ab), m.I(I_dof_sadr), m.I(I_dof_sent)};
   Vec<T, DPL> qfrc_smooth = c.zero(), qacc_smooth = c.zero();
   if (valid) {
@@ -830,5 +892,5 @@ __global__ void __launch_bounds__((sizeof(T) == 4 ? 512 : MJT_SOLVE_F64_THREADS)
   }
   __syncthreads();
   if (!valid) return;
-  solve_env<T, DPL>(m, in, d, Bs, env, c, qfrc_smooth, qacc_smooth, mode);
+  solve_env<T, DPL, COMPACT>(m, in, d, Bs, env, c, qfrc_smooth, qacc_smooth, mode);
 }

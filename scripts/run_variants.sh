@@ -9,7 +9,7 @@ try:
     d = json.loads(open('/tmp/rv.json').read())
     c = d.get('clocks') or {}
     print(sys.argv[1], sys.argv[2], '::', round(d['value'] / 1e6, 2), 'M/s', round(d['ms_per_step'], 3), 'ms',
-          {k: round(v, 3) for k, v in d['roofline']['kernel_ms_per_step'].items()}, 'clk', c.get('sm_mhz'), c.get('reasons'))
+          {k: round(v, 3) for k, v in d['roofline']['kernel_ms_per_step'].items()}, 'clk', c.get('sm_mhz'), 'E', d['config'].get('solve_envs_per_cta'), 'smem', d['config'].get('solve_smem_bytes'))
 except Exception as e:
     print(sys.argv[1], 'failed:', open('/tmp/rv.json').read()[:300])
 PY
