@@ -7,7 +7,10 @@
 #include "k_smooth.cuh"
 
 enum { SENS_ACCELEROMETER = 1, SENS_VELOCIMETER = 2, SENS_GYRO = 3, SENS_MAGNETOMETER = 6, SENS_RANGEFINDER = 7, SENS_JOINTPOS = 9,
-       SENS_JOINTVEL = 10, SENS_ACTUATORPOS = 13, SENS_ACTUATORVEL = 14, SENS_ACTUATORFRC = 15, SENS_JOINTACTFRC = 16 };
+       SENS_JOINTVEL = 10, SENS_TENDONPOS = 11, SENS_TENDONVEL = 12, SENS_ACTUATORPOS = 13, SENS_ACTUATORVEL = 14, SENS_ACTUATORFRC = 15,
+       SENS_JOINTACTFRC = 16, SENS_BALLQUAT = 18, SENS_BALLANGVEL = 19, SENS_FRAMEPOS = 26, SENS_FRAMEQUAT = 27, SENS_FRAMEXAXIS = 28,
+       SENS_FRAMEYAXIS = 29, SENS_FRAMEZAXIS = 30, SENS_FRAMELINVEL = 31, SENS_FRAMEANGVEL = 32, SENS_SUBTREECOM = 35, SENS_CLOCK = 45 };
+enum { OBJ_UNKNOWN = 0, OBJ_BODY = 1, OBJ_XBODY = 2, OBJ_GEOM = 5, OBJ_SITE = 6, OBJ_CAMERA = 7 };   // mjtObj
 
 template <typename T> __device__ __forceinline__ T safe_div(T a, T b) { return a / (b + (b == T(0) ? T(MJT_MINVAL) : T(0))); }
 
@@ -77,6 +80,41 @@ template <typename T> __device__ __forceinline__ T cutoff(T x, T c, int datatype
   return x;
 }
 
+// world position / rotation of a sensor object by mjtObj type (reference sensor.py:63-74)
+template <typename T>
+__device__ __forceinline__ void sensor_frame(const ModelView<T>& m, const EnvBuf<T>& d, int otype, int id, V3<T>* pos, T* mat) {
+  int oP = -1, oR = -1;
+  if (otype == OBJ_BODY) { oP = m.D(D_xipos); oR = m.D(D_ximat); }
+  else if (otype == OBJ_XBODY) { oP = m.D(D_xpos); oR = m.D(D_xmat); }
+  else if (otype == OBJ_GEOM) { oP = m.D(D_geom_xpos); oR = m.D(D_geom_xmat); }
+  else if (otype == OBJ_SITE) { oP = m.D(D_site_xpos); oR = m.D(D_site_xmat); }
+  if (oP < 0 || id < 0) {
+    *pos = V3<T>(0, 0, 0);
+    for (int k = 0; k < 9; ++k) mat[k] = (k % 4 == 0) ? T(1) : T(0);
+    return;
+  }
+  ld3(d, oP + 3 * id, *pos);
+  for (int k = 0; k < 9; ++k) mat[k] = d.get(oR + 9 * id + k);
+}
+// body that carries a sensor object
+template <typename T>
+__device__ __forceinline__ int sensor_body(const ModelView<T>& m, int otype, int id) {
+  if (otype == OBJ_BODY || otype == OBJ_XBODY) return id;
+  if (otype == OBJ_GEOM) return m.I(I_geom_bodyid)[id];
+  if (otype == OBJ_SITE) return m.I(I_site_bodyid)[id];
+  return 0;
+}
+// world orientation of a sensor object as a quaternion (sensor.py:161-176)
+template <typename T>
+__device__ __forceinline__ Q4<T> sensor_quat(const ModelView<T>& m, const EnvBuf<T>& d, int otype, int id) {
+  if (otype == OBJ_UNKNOWN || id < 0) return Q4<T>(1, 0, 0, 0);
+  const int b = sensor_body(m, otype, id);
+  const Q4<T> bq(d.get(m.D(D_xquat) + 4 * b), d.get(m.D(D_xquat) + 4 * b + 1), d.get(m.D(D_xquat) + 4 * b + 2), d.get(m.D(D_xquat) + 4 * b + 3));
+  if (otype == OBJ_XBODY) return bq;
+  const T* lq = otype == OBJ_BODY ? m.F(F_body_iquat) + 4 * id : (otype == OBJ_GEOM ? m.F(F_geom_quat) + 4 * id : m.F(F_site_quat) + 4 * id);
+  return qmul(bq, f4(lq));
+}
+
 template <typename T>
 __device__ void sensor_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T>& d, size_t B, int env, int stage) {
   const int ns = m.h(H_nsensor), oS = m.D(D_sensordata);
@@ -89,9 +127,64 @@ __device__ void sensor_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<
     if (m.I(I_sens_stage)[s] != stage) continue;
     const int type = m.I(I_sens_type)[s], obj = m.I(I_sens_objid)[s], adr = m.I(I_sens_adr)[s], dtp = m.I(I_sens_datatype)[s];
     const T cut = m.F(F_sens_cutoff)[s];
-    T val[3];
+    T val[4];
     int dim = 0;
-    if (type == SENS_JOINTPOS) { val[0] = d.get(m.D(D_qpos) + m.I(I_jnt_qposadr)[obj]); dim = 1; }
+    const int otype = m.I(I_sens_objtype)[s], rtype = m.I(I_sens_reftype)[s], rid = m.I(I_sens_refid)[s];
+    auto mat_t = [](const T* R, const V3<T>& v) { return V3<T>(R[0] * v.x + R[3] * v.y + R[6] * v.z, R[1] * v.x + R[4] * v.y + R[7] * v.z,
+                                                            R[2] * v.x + R[5] * v.y + R[8] * v.z); };
+    if (type == SENS_TENDONPOS) { val[0] = d.get(m.D(D_ten_length) + obj); dim = 1; }
+    else if (type == SENS_TENDONVEL) { val[0] = d.get(m.D(D_ten_velocity) + obj); dim = 1; }
+    else if (type == SENS_CLOCK) { val[0] = d.get(m.D(D_time)); dim = 1; }
+    else if (type == SENS_SUBTREECOM) { for (int k = 0; k < 3; ++k) val[k] = d.get(m.D(D_subtree_com) + 3 * obj + k); dim = 3; }
+    else if (type == SENS_BALLANGVEL) { for (int k = 0; k < 3; ++k) val[k] = d.get(m.D(D_qvel) + m.I(I_jnt_dofadr)[obj] + k); dim = 3; }
+    else if (type == SENS_BALLQUAT) {
+      const int qa = m.I(I_jnt_qposadr)[obj];
+      const Q4<T> q = qnormalize(Q4<T>(d.get(m.D(D_qpos) + qa), d.get(m.D(D_qpos) + qa + 1), d.get(m.D(D_qpos) + qa + 2), d.get(m.D(D_qpos) + qa + 3)));
+      val[0] = q.w; val[1] = q.x; val[2] = q.y; val[3] = q.z;
+      dim = 4;
+    } else if (type == SENS_FRAMEQUAT) {
+      Q4<T> q = sensor_quat(m, d, otype, obj);
+      if (rid != -1) q = qmul(qconj(sensor_quat(m, d, rtype, rid)), q);   // math.quat_inv = conjugate (math.py:264-273)
+      val[0] = q.w; val[1] = q.x; val[2] = q.y; val[3] = q.z;
+      dim = 4;
+    } else if (type == SENS_FRAMEPOS || type == SENS_FRAMEXAXIS || type == SENS_FRAMEYAXIS || type == SENS_FRAMEZAXIS) {
+      V3<T> xp, rp;
+      T xm[9], rm[9];
+      sensor_frame(m, d, otype, obj, &xp, xm);
+      V3<T> v = xp;
+      if (type != SENS_FRAMEPOS) {
+        const int a = type - SENS_FRAMEXAXIS;
+        v = V3<T>(xm[a], xm[3 + a], xm[6 + a]);
+      }
+      if (rid != -1) {
+        sensor_frame(m, d, rtype, rid, &rp, rm);
+        v = mat_t(rm, type == SENS_FRAMEPOS ? xp - rp : v);
+      }
+      val[0] = v.x; val[1] = v.y; val[2] = v.z;
+      dim = 3;
+    } else if (type == SENS_FRAMELINVEL || type == SENS_FRAMEANGVEL) {   // sensor.py:265-325
+      V3<T> xp, rp, ang, lin, sc;
+      T xm[9], rm[9];
+      sensor_frame(m, d, otype, obj, &xp, xm);
+      const int ob = sensor_body(m, otype, obj);
+      ld3(d, m.D(D_cvel) + 6 * ob, ang);
+      ld3(d, m.D(D_cvel) + 6 * ob + 3, lin);
+      ld3(d, m.D(D_subtree_com) + 3 * body_root[ob], sc);
+      V3<T> v = type == SENS_FRAMEANGVEL ? ang : lin - cross(xp - sc, ang);
+      if (rid > -1) {
+        V3<T> angr, linr, scr;
+        sensor_frame(m, d, rtype, rid, &rp, rm);
+        const int rb = sensor_body(m, rtype, rid);
+        ld3(d, m.D(D_cvel) + 6 * rb, angr);
+        ld3(d, m.D(D_cvel) + 6 * rb + 3, linr);
+        ld3(d, m.D(D_subtree_com) + 3 * body_root[rb], scr);
+        if (type == SENS_FRAMEANGVEL) v = mat_t(rm, ang - angr);
+        else v = mat_t(rm, v - (linr - cross(rp - scr, angr)) + cross(xp - rp, angr));
+      }
+      val[0] = v.x; val[1] = v.y; val[2] = v.z;
+      dim = 3;
+    }
+    else if (type == SENS_JOINTPOS) { val[0] = d.get(m.D(D_qpos) + m.I(I_jnt_qposadr)[obj]); dim = 1; }
     else if (type == SENS_JOINTVEL) { val[0] = d.get(m.D(D_qvel) + m.I(I_jnt_dofadr)[obj]); dim = 1; }
     else if (type == SENS_ACTUATORPOS) { val[0] = d.get(m.D(D_actuator_length) + obj); dim = 1; }
     else if (type == SENS_ACTUATORVEL) { val[0] = d.get(m.D(D_actuator_velocity) + obj); dim = 1; }

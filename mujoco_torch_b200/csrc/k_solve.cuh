@@ -19,6 +19,9 @@
 #ifndef MJT_CHOL_ROWS
 #define MJT_CHOL_ROWS 1   // n <= 32: keep each lane's row of L in registers during the factorisation
 #endif
+#ifndef MJT_COMPACT_MIN_NEFC
+#define MJT_COMPACT_MIN_NEFC 64   // models with more constraint rows than this use the live-row (COMPACT) solver instantiation
+#endif
 #ifndef MJT_SOLVE_F64_MINB
 #define MJT_SOLVE_F64_MINB 1
 #endif

@@ -98,7 +98,7 @@ extern "C" int mjt_model_create(const void* blob_host, size_t nbytes, int device
   // k_solve shared-memory budget: blob + E per-env regions; pick the E in {8,4,2,1} that maximises resident warps per SM
   const int nv = w[H_nv], nefc = w[H_nefc];
   const size_t tsz = m->f64 ? 8 : 4;
-  const size_t region = (size_t)solve_layout(nv, nefc, w[H_jc_words], w[H_nf], w[H_nsrc], (int)tsz, nefc > 64).words * tsz;
+  const size_t region = (size_t)solve_layout(nv, nefc, w[H_jc_words], w[H_nf], w[H_nsrc], (int)tsz, nefc > MJT_COMPACT_MIN_NEFC).words * tsz;
   const size_t blob_b = ((size_t)m->blob_words + 3) / 4 * 16;
   const size_t sblob_b = ((size_t)m->solve_words + 3) / 4 * 16;
   const size_t sm_total = (size_t)prop.sharedMemPerMultiprocessor;
@@ -217,7 +217,7 @@ static int run_forward(const mjtModel* m, const MjtIn& in, T* out, int B, int mo
     const size_t smem = m->solve_blob_bytes + m->solve_region_bytes * E;
     const int gs = (B + E - 1) / E;
     // COMPACT instantiation (live-row list) for models with more than two 32-row chunks of constraint rows
-    const bool compact = m->hv(H_nefc) > 64;
+    const bool compact = m->hv(H_nefc) > MJT_COMPACT_MIN_NEFC;
 #define MJT_SOLVE_LAUNCH(DPLV, CV)                                                                                      \
   do {                                                                                                                  \
     if (set_smem<T>((const void*)k_solve<T, DPLV, CV>, m->solve_smem)) return 1;                                        \

@@ -39,7 +39,7 @@ pair_fn pair_g1 pair_g2 pair_slot
 con_body1 con_body2 con_dim con_efcadr con_geom1 con_geom2
 src_type src_id src_row src_cadr src_nsup src_nrows sup_col row_src row_jadr jc_src tri_src triu_src tri_ab dof_sadr dof_sent
 eq_type eq_obj1 eq_obj2
-sens_type sens_objid sens_adr sens_dim sens_datatype sens_stage
+sens_type sens_objid sens_adr sens_dim sens_datatype sens_stage sens_objtype sens_reftype sens_refid
 rf_geom
 body_geomadr body_geomnum body_geom body_siteadr body_sitenum body_site
 cvx_geom cvx_nvert cvx_nface cvx_nfv cvx_nedge cvx_vertadr cvx_faceadr cvx_edgeadr cvx_normadr geom_cvx cvx_face cvx_edge

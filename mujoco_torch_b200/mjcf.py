@@ -992,12 +992,40 @@ class Compiler:
                 "actuatorvel": (SensorType.ACTUATORVEL, 1, Stage.VEL, DataType.REAL),
                 "actuatorfrc": (SensorType.ACTUATORFRC, 1, Stage.ACC, DataType.REAL),
                 "jointactuatorfrc": (SensorType.JOINTACTFRC, 1, Stage.ACC, DataType.REAL),
+                "tendonpos": (SensorType.TENDONPOS, 1, Stage.POS, DataType.REAL),
+                "tendonvel": (SensorType.TENDONVEL, 1, Stage.VEL, DataType.REAL),
+                "ballquat": (SensorType.BALLQUAT, 4, Stage.POS, DataType.QUATERNION),
+                "ballangvel": (SensorType.BALLANGVEL, 3, Stage.VEL, DataType.REAL),
+                "framepos": (SensorType.FRAMEPOS, 3, Stage.POS, DataType.REAL),
+                "framequat": (SensorType.FRAMEQUAT, 4, Stage.POS, DataType.QUATERNION),
+                "framexaxis": (SensorType.FRAMEXAXIS, 3, Stage.POS, DataType.AXIS),
+                "frameyaxis": (SensorType.FRAMEYAXIS, 3, Stage.POS, DataType.AXIS),
+                "framezaxis": (SensorType.FRAMEZAXIS, 3, Stage.POS, DataType.AXIS),
+                "framelinvel": (SensorType.FRAMELINVEL, 3, Stage.VEL, DataType.REAL),
+                "frameangvel": (SensorType.FRAMEANGVEL, 3, Stage.VEL, DataType.REAL),
+                "subtreecom": (SensorType.SUBTREECOM, 3, Stage.POS, DataType.REAL),
+                "clock": (SensorType.CLOCK, 1, Stage.POS, DataType.REAL),
             }
+            objtypes = {"body": ObjType.BODY, "xbody": ObjType.XBODY, "geom": ObjType.GEOM, "site": ObjType.SITE, "camera": ObjType.CAMERA}
+            kind_of = {ObjType.BODY: "body", ObjType.XBODY: "body", ObjType.GEOM: "geom", ObjType.SITE: "site", ObjType.CAMERA: "camera"}
             for se in sn:
                 if se.tag not in spec:
                     raise NotImplementedError(f"sensor {se.tag}")
                 st, dim, stage, dt = spec[se.tag]
-                if "site" in se.attrib:
+                rt, rid = ObjType.UNKNOWN, -1
+                if se.tag.startswith("frame"):
+                    ot = objtypes[se.get("objtype")]
+                    oid = name2id[kind_of[ot]][se.get("objname")]
+                    if "refname" in se.attrib:
+                        rt = objtypes[se.get("reftype")]
+                        rid = name2id[kind_of[rt]][se.get("refname")]
+                elif se.tag == "clock":
+                    ot, oid = ObjType.UNKNOWN, -1
+                elif "tendon" in se.attrib:
+                    ot, oid = ObjType.TENDON, [x["name"] for x in tendons].index(se.get("tendon"))
+                elif "body" in se.attrib:
+                    ot, oid = ObjType.BODY, name2id["body"][se.get("body")]
+                elif "site" in se.attrib:
                     ot, oid = ObjType.SITE, name2id["site"][se.get("site")]
                 elif "joint" in se.attrib:
                     ot, oid = ObjType.JOINT, name2id["joint"][se.get("joint")]
@@ -1006,7 +1034,8 @@ class Compiler:
                 else:
                     raise NotImplementedError("sensor object")
                 sens.append(dict(name=se.get("name"), type=int(st), dim=dim, needstage=int(stage), datatype=int(dt),
-                                 objtype=int(ot), objid=oid, adr=nsensordata, cutoff=float(se.get("cutoff", 0))))
+                                 objtype=int(ot), objid=oid, reftype=int(rt), refid=rid, adr=nsensordata,
+                                 cutoff=float(se.get("cutoff", 0))))
                 nsensordata += dim
         nsensor = len(sens)
 
@@ -1157,8 +1186,8 @@ class Compiler:
         for key, dt in (("type", np.int32), ("datatype", np.int32), ("needstage", np.int32), ("objtype", np.int32),
                         ("objid", np.int32), ("dim", np.int32), ("adr", np.int32), ("cutoff", np.float64)):
             setattr(m, "sensor_" + key, arr([s[key] for s in sens], dtype=dt))
-        m.sensor_reftype = np.zeros(nsensor, np.int32)
-        m.sensor_refid = np.full(nsensor, -1, np.int32)
+        m.sensor_reftype = np.array([x["reftype"] for x in sens], np.int32).reshape(nsensor)
+        m.sensor_refid = np.array([x["refid"] for x in sens], np.int32).reshape(nsensor)
         m.sensor_intprm = np.zeros((nsensor, 3), np.int32)
         # numerics + names
         nadr, ndata, cur = [], [], 0

@@ -145,6 +145,8 @@ class ObjType(enum.IntEnum):
     SITE = 6
     CAMERA = 7
     LIGHT = 8
+    TENDON = 18
+    ACTUATOR = 19
 
 
 class DisableBit(enum.IntFlag):

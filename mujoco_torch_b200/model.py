@@ -26,7 +26,10 @@ _FN_TABLE = {
 }
 _SUPPORTED_SENSORS = {SensorType.TOUCH, SensorType.ACCELEROMETER, SensorType.VELOCIMETER, SensorType.GYRO, SensorType.MAGNETOMETER,
                       SensorType.RANGEFINDER, SensorType.JOINTPOS, SensorType.JOINTVEL, SensorType.ACTUATORPOS,
-                      SensorType.ACTUATORVEL, SensorType.ACTUATORFRC, SensorType.JOINTACTFRC}
+                      SensorType.ACTUATORVEL, SensorType.ACTUATORFRC, SensorType.JOINTACTFRC, SensorType.TENDONPOS,
+                      SensorType.TENDONVEL, SensorType.BALLQUAT, SensorType.BALLANGVEL, SensorType.FRAMEPOS, SensorType.FRAMEQUAT,
+                      SensorType.FRAMEXAXIS, SensorType.FRAMEYAXIS, SensorType.FRAMEZAXIS, SensorType.FRAMELINVEL,
+                      SensorType.FRAMEANGVEL, SensorType.SUBTREECOM, SensorType.CLOCK}
 
 
 class Option:
@@ -442,6 +445,9 @@ class Model:
         I["eq_type"], I["eq_obj1"], I["eq_obj2"] = i32(mj.eq_type), i32(mj.eq_obj1id), i32(mj.eq_obj2id)
         I["sens_type"], I["sens_objid"], I["sens_adr"] = i32(mj.sensor_type), i32(mj.sensor_objid), i32(mj.sensor_adr)
         I["sens_dim"], I["sens_datatype"], I["sens_stage"] = i32(mj.sensor_dim), i32(mj.sensor_datatype), i32(mj.sensor_needstage)
+        I["sens_objtype"] = i32(mj.sensor_objtype)
+        I["sens_reftype"] = i32(getattr(mj, "sensor_reftype", np.zeros(self.nsensor)))
+        I["sens_refid"] = i32(getattr(mj, "sensor_refid", np.full(self.nsensor, -1)))
         # rangefinder candidate geoms: reference ray.precompute_ray_data :292-324 iterates geom types in this order
         rf = []
         for gt in (GeomType.PLANE, GeomType.SPHERE, GeomType.CAPSULE, GeomType.ELLIPSOID, GeomType.CYLINDER, GeomType.BOX):

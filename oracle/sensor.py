@@ -16,7 +16,55 @@ from .model import BOX, CAPSULE, DSBL_SENSOR, PLANE, SPHERE, mjMINVAL
 # mjtSensor values (mujoco_torch_b200.mjmodel.SensorType)
 S_ACCELEROMETER, S_VELOCIMETER, S_GYRO, S_MAGNETOMETER, S_RANGEFINDER = 1, 2, 3, 6, 7
 S_JOINTPOS, S_JOINTVEL, S_ACTUATORPOS, S_ACTUATORVEL, S_ACTUATORFRC, S_JOINTACTFRC = 9, 10, 13, 14, 15, 16
+S_TENDONPOS, S_TENDONVEL, S_BALLQUAT, S_BALLANGVEL = 11, 12, 18, 19
+S_FRAMEPOS, S_FRAMEQUAT, S_FRAMEXAXIS, S_FRAMEYAXIS, S_FRAMEZAXIS, S_FRAMELINVEL, S_FRAMEANGVEL = 26, 27, 28, 29, 30, 31, 32
+S_SUBTREECOM, S_CLOCK = 35, 45
+O_UNKNOWN, O_BODY, O_XBODY, O_GEOM, O_SITE, O_CAMERA = 0, 1, 2, 5, 6, 7
 STAGE_POS, STAGE_VEL, STAGE_ACC = 1, 2, 3
+
+
+def _frame(m, d, otype, oid):
+    """World position / rotation of a sensor object (sensor.py:63-74 objtype_data)."""
+    B = d.qpos.shape[0]
+    if otype == O_BODY:
+        return d.xipos[:, oid], d.ximat[:, oid]
+    if otype == O_XBODY:
+        return d.xpos[:, oid], d.xmat[:, oid]
+    if otype == O_GEOM:
+        return d.geom_xpos[:, oid], d.geom_xmat[:, oid]
+    if otype == O_SITE:
+        return d.site_xpos[:, oid], d.site_xmat[:, oid]
+    if otype == O_UNKNOWN:
+        return torch.zeros(B, 3, dtype=d.qpos.dtype), torch.eye(3, dtype=d.qpos.dtype).expand(B, 3, 3)
+    raise NotImplementedError(f"sensor object type {otype}")
+
+
+def _frame_quat(m, d, otype, oid):
+    """sensor.py:161-176."""
+    mj = m.mj
+    B = d.qpos.shape[0]
+    t = lambda a: torch.as_tensor(np.asarray(a), dtype=d.qpos.dtype).expand(B, 4)
+    if otype == O_XBODY:
+        return d.xquat[:, oid]
+    if otype == O_BODY:
+        return M.quat_mul(d.xquat[:, oid], t(mj.body_iquat[oid]))
+    if otype == O_GEOM:
+        return M.quat_mul(d.xquat[:, int(mj.geom_bodyid[oid])], t(mj.geom_quat[oid]))
+    if otype == O_SITE:
+        return M.quat_mul(d.xquat[:, int(mj.site_bodyid[oid])], t(mj.site_quat[oid]))
+    if otype == O_UNKNOWN:
+        return t([1.0, 0, 0, 0])
+    raise NotImplementedError(f"sensor object type {otype}")
+
+
+def _obj_body(mj, otype, oid):
+    if otype in (O_BODY, O_XBODY):
+        return oid
+    if otype == O_GEOM:
+        return int(mj.geom_bodyid[oid])
+    if otype == O_SITE:
+        return int(mj.site_bodyid[oid])
+    return 0
 INF = float("inf")
 
 
@@ -163,6 +211,41 @@ def sensor_pos(m, d):
         elif t == S_ACTUATORPOS:
             v = d.actuator_length[:, torch.as_tensor(objid, dtype=torch.long)]
             _write(d, adr, 1, _cutoff(v, cutoff, dtp)[:, :, None])
+        elif t == S_TENDONPOS:
+            v = d.ten_length[:, torch.as_tensor(objid, dtype=torch.long)]
+            _write(d, adr, 1, _cutoff(v, cutoff, dtp)[:, :, None])
+        elif t == S_BALLQUAT:
+            vals = []
+            for o in objid:
+                a = int(mj.jnt_qposadr[o])
+                vals.append(M.normalize(d.qpos[:, a : a + 4]))
+            _write(d, adr, 4, _cutoff(torch.stack(vals, 1), cutoff, dtp))
+        elif t == S_SUBTREECOM:
+            v = torch.stack([d.subtree_com[:, o] for o in objid], 1)
+            _write(d, adr, 3, _cutoff(v, cutoff, dtp))
+        elif t == S_CLOCK:
+            v = d.time[:, None].expand(-1, len(idx))
+            _write(d, adr, 1, _cutoff(v, cutoff, dtp)[:, :, None])
+        elif t in (S_FRAMEPOS, S_FRAMEXAXIS, S_FRAMEYAXIS, S_FRAMEZAXIS, S_FRAMEQUAT):
+            vals = []
+            for k, o in zip(idx, objid):
+                ot, rt, rid = int(mj.sensor_objtype[k]), int(mj.sensor_reftype[k]), int(mj.sensor_refid[k])
+                if t == S_FRAMEQUAT:
+                    q = _frame_quat(m, d, ot, int(o))
+                    if rid != -1:
+                        r = _frame_quat(m, d, rt, rid)
+                        q = M.quat_mul(M.quat_inv(r), q)
+                    vals.append(q)
+                    continue
+                xpos, xmat = _frame(m, d, ot, int(o))
+                rpos, rmat = _frame(m, d, rt, rid) if rid != -1 else (None, None)
+                if t == S_FRAMEPOS:
+                    v = xpos if rid == -1 else (rmat.transpose(-1, -2) * (xpos - rpos)[:, None, :]).sum(-1)
+                else:
+                    axis = xmat[:, :, {S_FRAMEXAXIS: 0, S_FRAMEYAXIS: 1, S_FRAMEZAXIS: 2}[t]]
+                    v = axis if rid == -1 else (rmat.transpose(-1, -2) * axis[:, None, :]).sum(-1)
+                vals.append(v)
+            _write(d, adr, 4 if t == S_FRAMEQUAT else 3, _cutoff(torch.stack(vals, 1), cutoff, dtp))
     return d
 
 
@@ -190,6 +273,37 @@ def sensor_vel(m, d):
         elif t == S_ACTUATORVEL:
             v = d.actuator_velocity[:, torch.as_tensor(objid, dtype=torch.long)]
             _write(d, adr, 1, _cutoff(v, cutoff, dtp)[:, :, None])
+        elif t == S_TENDONVEL:
+            v = d.ten_velocity[:, torch.as_tensor(objid, dtype=torch.long)]
+            _write(d, adr, 1, _cutoff(v, cutoff, dtp)[:, :, None])
+        elif t == S_BALLANGVEL:
+            vals = []
+            for o in objid:
+                a = int(mj.jnt_dofadr[o])
+                vals.append(d.qvel[:, a : a + 3])
+            _write(d, adr, 3, _cutoff(torch.stack(vals, 1), cutoff, dtp))
+        elif t in (S_FRAMELINVEL, S_FRAMEANGVEL):   # sensor.py:265-325
+            vals = []
+            for k, o in zip(idx, objid):
+                ot, rt, rid = int(mj.sensor_objtype[k]), int(mj.sensor_reftype[k]), int(mj.sensor_refid[k])
+                xpos_o, _ = _frame(m, d, ot, int(o))
+                # refid == -1 indexes the *last* element in the reference (python negative index); it is masked out afterwards
+                rr = rid if rid != -1 else {O_BODY: mj.nbody, O_XBODY: mj.nbody, O_GEOM: mj.ngeom, O_SITE: mj.nsite, O_UNKNOWN: 1}[rt] - 1
+                xpos_r, xmat_r = _frame(m, d, rt, rr)
+                ob, rb = _obj_body(mj, ot, int(o)), _obj_body(mj, rt, rr)
+                cvel_o, cvel_r = d.cvel[:, ob], d.cvel[:, rb]
+                off_o = xpos_o - d.subtree_com[:, int(mj.body_rootid[ob])]
+                off_r = xpos_r - d.subtree_com[:, int(mj.body_rootid[rb])]
+                ang, angr = cvel_o[:, :3], cvel_r[:, :3]
+                rot = lambda v: (xmat_r.transpose(-1, -2) * v[:, None, :]).sum(-1)
+                if t == S_FRAMELINVEL:
+                    lin = cvel_o[:, 3:] - M.cross(off_o, ang)
+                    linr = cvel_r[:, 3:] - M.cross(off_r, angr)
+                    rel = lin - linr + M.cross(xpos_o - xpos_r, angr)
+                    vals.append(rot(rel) if rid > -1 else lin)
+                else:
+                    vals.append(rot(ang - angr) if rid > -1 else ang)
+            _write(d, adr, 3, _cutoff(torch.stack(vals, 1), cutoff, dtp))
     return d
 
 
