@@ -32,10 +32,10 @@ struct SolveLayout {
   int nP, oJ, oM, oL, oDinv, oXs, oYs, oD, oAref, oFloss, oJaref, oJv, oForce, oMask, oLive, nchunk, words;
 };
 
-__host__ __device__ inline SolveLayout solve_layout(int nv, int nefc, int jc_words, int nf, int nsrc, int tsize, bool compact) {
+__host__ __device__ inline SolveLayout solve_layout(int nv, int nefc, int jc_words, int nf, int nsrc, int tsize, bool compact, int G) {
   SolveLayout s;
   s.nP = nv * (nv + 1) / 2;
-  s.nchunk = (nefc + 31) / 32;
+  s.nchunk = (nefc + G - 1) / G;   // one mask word per G rows (G = lanes per env)
   int o = 0;
   s.oJ = o; o += jc_words;
   s.oM = o; o += s.nP;
@@ -70,17 +70,27 @@ struct Vec {
   T v[DPL];
 };
 
-template <typename T>
-__device__ __forceinline__ T vec_bcast(const Vec<T, 1>& x, int i) { return __shfl_sync(0xffffffffu, x.v[0], i & 31); }
-template <typename T>
-__device__ __forceinline__ T vec_bcast(const Vec<T, 2>& x, int i) {
-  const T a = __shfl_sync(0xffffffffu, x.v[0], i & 31), b = __shfl_sync(0xffffffffu, x.v[1], i & 31);
-  return (i >> 5) ? b : a;
+// lanes of one env: a full warp (G = 32) or a half warp (G = 16, two envs per warp for models with nv <= 16)
+template <int G> __device__ __forceinline__ unsigned group_mask() {
+  return G == 32 ? 0xffffffffu : (0xffffu << ((threadIdx.x & 16)));
+}
+template <typename T, int G>
+__device__ __forceinline__ T group_sum(T v, unsigned gm) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gm, v, o, G);
+  return v;
+}
+template <typename T, int G>
+__device__ __forceinline__ T vec_bcast(const Vec<T, 1>& x, int i, unsigned gm) { return __shfl_sync(gm, x.v[0], i & (G - 1), G); }
+template <typename T, int G>
+__device__ __forceinline__ T vec_bcast(const Vec<T, 2>& x, int i, unsigned gm) {
+  const T a = __shfl_sync(gm, x.v[0], i & (G - 1), G), b = __shfl_sync(gm, x.v[1], i & (G - 1), G);
+  return (i >= G) ? b : a;
 }
 
 __device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
 
-template <typename T, int DPL, bool COMPACT>
+template <typename T, int DPL, bool COMPACT, int G>
 struct SolveCtx {
   const ModelView<T>& m;
   T* s;  // this env's shared-memory region
@@ -96,6 +106,7 @@ struct SolveCtx {
   const int* tri_ab;
   const int* dof_sadr;
   const int* dof_sent;
+  unsigned gm;   // shuffle / barrier mask of this env's G lanes
   // COMPACT: row loops walk the live list (host picks it for models with more than two 32-row chunks); otherwise every
   // row is visited in place with no indirection
   static constexpr bool compact = COMPACT;
@@ -110,7 +121,7 @@ struct SolveCtx {
   __device__ __forceinline__ unsigned* amask() const { return reinterpret_cast<unsigned*>(s + L.oMask); }
   __device__ __forceinline__ int* lrow() const { return reinterpret_cast<int*>(s + L.oLive); }          // live row ids, ascending
   __device__ __forceinline__ int* spos() const { return reinterpret_cast<int*>(s + L.oLive) + nefc; }   // source -> first live slot, -1 = dead
-  __device__ __forceinline__ bool slot_active(int k) const { return (amask()[k >> 5] >> (k & 31)) & 1u; }
+  __device__ __forceinline__ bool slot_active(int k) const { return (amask()[k / G] >> (k % G)) & 1u; }
 
   // A source whose Jacobian block and reference accelerations are all exactly zero (inactive contact, limit or
   // equality: constraint.py zeroes those rows) can never carry force: J.x - aref stays 0.  Such rows are dropped from
@@ -122,7 +133,7 @@ struct SolveCtx {
     int* lr = lrow();
     int* sp = spos();
     int base = 0;
-    for (int s0 = 0; s0 < nsrc; s0 += 32) {
+    for (int s0 = 0; s0 < nsrc; s0 += G) {
       const int sidx = s0 + lane;
       int nr = 0, r0 = 0;
       bool live = false;
@@ -140,8 +151,8 @@ struct SolveCtx {
       const int cnt = live ? nr : 0;
       int incl = cnt;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      for (int o = 1; o < G; o <<= 1) {
+        const int v = __shfl_up_sync(gm, incl, o, G);
         if (lane >= o) incl += v;
       }
       const int start = base + incl - cnt;
@@ -149,9 +160,9 @@ struct SolveCtx {
         sp[sidx] = live ? start : -1;
         for (int e = 0; e < cnt; ++e) lr[start + e] = r0 + e;
       }
-      base += __shfl_sync(0xffffffffu, incl, 31);
+      base += __shfl_sync(gm, incl, G - 1, G);
     }
-    __syncwarp();
+    __syncwarp(gm);
     return base;
   }
 
@@ -165,16 +176,16 @@ struct SolveCtx {
     T p = 0;
 #pragma unroll
     for (int k = 0; k < DPL; ++k) p += a.v[k] * b.v[k];
-    return warp_sum(p);
+    return group_sum<T, G>(p, gm);
   }
   __device__ __forceinline__ void to_smem(const Vec<T, DPL>& a, T* dst) const {
-    __syncwarp();
+    __syncwarp(gm);
 #pragma unroll
     for (int k = 0; k < DPL; ++k) {
-      const int i = lane + 32 * k;
+      const int i = lane + G * k;
       if (i < nv) dst[i] = a.v[k];
     }
-    __syncwarp();
+    __syncwarp(gm);
   }
   // y = A x for a symmetric matrix stored as a packed lower triangle
   __device__ __forceinline__ Vec<T, DPL> symv(const T* A, const Vec<T, DPL>& x) const {
@@ -182,7 +193,7 @@ struct SolveCtx {
     Vec<T, DPL> y = zero();
 #pragma unroll
     for (int k = 0; k < DPL; ++k) {
-      const int i = lane + 32 * k;
+      const int i = lane + G * k;
       if (i < nv) {
         const T* row = A + tri(i);
         const T* x = xs();
@@ -198,7 +209,7 @@ struct SolveCtx {
   // out[r] = J[r,:] . x (- sub[r])   over each row's compact support
   __device__ __forceinline__ void jmul(const Vec<T, DPL>& x, T* out, const T* sub, int nlive) const {
     to_smem(x, xs());
-    for (int idx = lane; idx < nlive; idx += 32) {
+    for (int idx = lane; idx < nlive; idx += G) {
       const int r = row_at(idx);
       const int sidx = row_src[r];
       const int ns = src_nsup[sidx];
@@ -212,7 +223,7 @@ struct SolveCtx {
       acc += acc2;
       out[r] = sub ? acc - sub[r] : acc;
     }
-    __syncwarp();
+    __syncwarp(gm);
   }
   // y = J^T f as a per-dof gather: lane i walks the (source, support position) pairs of dof i; rows of a source are
   // stored back to back (ns entries each).  f must be exactly zero on rows that carry no force.
@@ -220,7 +231,7 @@ struct SolveCtx {
     Vec<T, DPL> out;
 #pragma unroll
     for (int k = 0; k < DPL; ++k) {
-      const int i = lane + 32 * k;
+      const int i = lane + G * k;
       T acc = T(0);
       if (i < nv) {
         for (int q = dof_sadr[i], qe = dof_sadr[i + 1]; q < qe; ++q) {
@@ -242,11 +253,11 @@ struct SolveCtx {
     const int n = nv;
     const bool big = n > 16;
     T* di = dinv();
-    T r[32];
+    T r[G];
     const bool mine = lane < n;
     T* rowi = A + tri(mine ? lane : 0);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
+    for (int j = 0; j < G; ++j) {
       if (j < n) {
         const T* rowj = A + tri(j);
         T acc = (mine && lane >= j) ? rowi[j] : T(0), acc2 = T(0);
@@ -257,14 +268,14 @@ struct SolveCtx {
         }
         if (j & 1) acc -= r[j - 1] * rowj[j - 1];
         acc += acc2;
-        T sdiag = __shfl_sync(0xffffffffu, acc, j);
+        T sdiag = __shfl_sync(gm, acc, j, G);
         if (big) sdiag += T(1e-10); else sdiag = t_max(sdiag, T(1e-12));
         const T inv = t_rsqrt(sdiag);
         const T lij = (lane == j) ? sdiag * inv : acc * inv;
         r[j] = lane >= j ? lij : T(0);
         if (mine && lane >= j) rowi[j] = lij;   // column j of other rows is not read during this step: no hazard
         if (lane == 0) di[j] = inv;
-        __syncwarp();
+        __syncwarp(gm);
       }
     }
   }
@@ -278,7 +289,7 @@ struct SolveCtx {
       T t[DPL];
 #pragma unroll
       for (int p = 0; p < DPL; ++p) {
-        const int i = j + lane + 32 * p;
+        const int i = j + lane + G * p;
         t[p] = T(0);
         if (i < n) {
           const T* rowi = A + tri(i);
@@ -288,18 +299,18 @@ struct SolveCtx {
           t[p] = acc;
         }
       }
-      T sdiag = __shfl_sync(0xffffffffu, t[0], 0);
+      T sdiag = __shfl_sync(gm, t[0], 0, G);
       if (big) sdiag += T(1e-10); else sdiag = t_max(sdiag, T(1e-12));
       const T inv = t_rsqrt(sdiag);
       const T ljj = sdiag * inv;
-      __syncwarp();
+      __syncwarp(gm);
 #pragma unroll
       for (int p = 0; p < DPL; ++p) {
-        const int i = j + lane + 32 * p;
+        const int i = j + lane + G * p;
         if (i < n) A[tri(i) + j] = (i == j) ? ljj : t[p] * inv;
       }
       if (lane == 0) di[j] = inv;
-      __syncwarp();
+      __syncwarp(gm);
     }
   }
   // x <- (L L^T)^-1 x with x distributed one element per lane (reference small_cholesky_solve :132-168)
@@ -307,42 +318,47 @@ struct SolveCtx {
     const int n = nv;
     const T* di = dinv();
     for (int i = 0; i < n; ++i) {
-      const T xi = vec_bcast(x, i) * di[i];
+      const T xi = vec_bcast<T, G>(x, i, gm) * di[i];
 #pragma unroll
       for (int k = 0; k < DPL; ++k) {
-        const int j = lane + 32 * k;
+        const int j = lane + G * k;
         if (j == i) x.v[k] = xi;
         else if (j > i && j < n) x.v[k] -= Lm[tri(j) + i] * xi;
       }
     }
     for (int i = n - 1; i >= 0; --i) {
-      const T xi = vec_bcast(x, i) * di[i];
+      const T xi = vec_bcast<T, G>(x, i, gm) * di[i];
       const T* rowi = Lm + tri(i);
 #pragma unroll
       for (int k = 0; k < DPL; ++k) {
-        const int j = lane + 32 * k;
+        const int j = lane + G * k;
         if (j == i) x.v[k] = xi;
         else if (j < i) x.v[k] -= rowi[j] * xi;
       }
     }
     return x;
   }
-  // bits r0 .. r0+nr-1 (nr <= 32) of the active-row mask
-  __device__ __forceinline__ unsigned active_bits(int r0, int nr) const {
-    const unsigned* am = amask();
-    const int w = r0 >> 5, sh = r0 & 31;
-    const unsigned lo = am[w], hi = (sh && w + 1 < L.nchunk) ? am[w + 1] : 0u;
-    const unsigned v = __funnelshift_r(lo, hi, sh);
-    return nr >= 32 ? v : (v & ((1u << nr) - 1u));
+  // bits k0 .. k0+nr-1 (nr <= 32) of the active-slot mask (one mask word per G slots)
+  __device__ __forceinline__ unsigned active_bits(int k0, int nr) const {
+    if (G == 32) {
+      const unsigned* am = amask();
+      const int w = k0 >> 5, sh = k0 & 31;
+      const unsigned lo = am[w], hi = (sh && w + 1 < L.nchunk) ? am[w + 1] : 0u;
+      const unsigned v = __funnelshift_r(lo, hi, sh);
+      return nr >= 32 ? v : (v & ((1u << nr) - 1u));
+    }
+    unsigned v = 0;
+    for (int e = 0; e < nr; ++e) v |= (slot_active(k0 + e) ? 1u : 0u) << e;
+    return v;
   }
   // Lp <- Mp + sum over active rows r of D_r J_r^T J_r, source by source over the packed support pairs
   __device__ __forceinline__ void hessian(const T* D) const {
     T* H = Lp();
     const T* M0 = Mp();
-    for (int p = lane; p < L.nP; p += 32) H[p] = M0[p];
-    __syncwarp();
+    for (int p = lane; p < L.nP; p += G) H[p] = M0[p];
+    __syncwarp(gm);
     // sources that touch a single dof (joint limits, dof friction): one lane per dof adds their diagonal terms
-    for (int i = lane; i < nv; i += 32) {
+    for (int i = lane; i < nv; i += G) {
       T acc = T(0);
       for (int q = dof_sadr[i], qe = dof_sadr[i + 1]; q < qe; ++q) {
         const int sidx = dof_sent[q] & 0xffff;
@@ -356,7 +372,7 @@ struct SolveCtx {
       }
       H[tri(i) + i] += acc;
     }
-    __syncwarp();
+    __syncwarp(gm);
     const int nsrc = m.h(H_nsrc);
     for (int sidx = 0; sidx < nsrc; ++sidx) {
       if (src_nsup[sidx] == 1) continue;
@@ -371,7 +387,7 @@ struct SolveCtx {
       const int* col = sup_col + src_cadr[sidx];
       const int npair = (ns * (ns + 1)) >> 1;
       const T* j0 = Jc() + row_jadr[r0];   // rows of one source are stored back to back, ns entries each
-      for (int p = lane; p < npair; p += 32) {
+      for (int p = lane; p < npair; p += G) {
         const int ab = tri_ab[p], a = ab & 0xffff, b = ab >> 16;
         T acc = 0;
         if (nr <= 32) {
@@ -391,16 +407,17 @@ struct SolveCtx {
         }
         H[tri(col[a]) + col[b]] += acc;  // support columns are sorted ascending: col[a] >= col[b]
       }
-      __syncwarp();
+      __syncwarp(gm);
     }
   }
 };
 
-template <typename T, int DPL, bool COMPACT>
+template <typename T, int DPL, bool COMPACT, int G>
 __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T>& d, size_t B, int env,
-                          const SolveCtx<T, DPL, COMPACT>& c, const Vec<T, DPL>& qfrc_smooth, const Vec<T, DPL>& qacc_smooth, int mode) {
+                          const SolveCtx<T, DPL, COMPACT, G>& c, const Vec<T, DPL>& qfrc_smooth, const Vec<T, DPL>& qacc_smooth, int mode) {
   typedef Vec<T, DPL> V;
   const int lane = c.lane;
+  const unsigned gm = c.gm;
   const int nv = c.nv, nefc = c.nefc, flags = m.h(H_disableflags);
   const SolveLayout& Lo = c.L;
   T* const sm = c.s;
@@ -416,12 +433,12 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
   auto loadv = [&](int off) {
     V r;
 #pragma unroll
-    for (int k = 0; k < DPL; ++k) { const int i = lane + 32 * k; r.v[k] = i < nv ? d.get(off + i) : T(0); }
+    for (int k = 0; k < DPL; ++k) { const int i = lane + G * k; r.v[k] = i < nv ? d.get(off + i) : T(0); }
     return r;
   };
   auto storev = [&](int off, const V& x) {
 #pragma unroll
-    for (int k = 0; k < DPL; ++k) { const int i = lane + 32 * k; if (i < nv) d.set(off + i, x.v[k]); }
+    for (int k = 0; k < DPL; ++k) { const int i = lane + G * k; if (i < nv) d.set(off + i, x.v[k]); }
   };
   auto axpy = [&](const V& a, T s, const V& b) {
     V r;
@@ -443,7 +460,7 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
     // forward.py:390-396: solve() never runs; qfrc_constraint and qacc_warmstart keep the caller's values
 #pragma unroll
     for (int k = 0; k < DPL; ++k) {
-      const int i = lane + 32 * k;
+      const int i = lane + G * k;
       if (i < nv) {
         qfrc_con.v[k] = in_get<T>(in.qfrc_constraint, B, env, i);
         d.set(m.D(D_qacc_warmstart) + i, in_get<T>(in.qacc_warmstart, B, env, i));
@@ -460,14 +477,14 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
     V Ma, grad, Mgrad, search;
     T gauss = 0, cost = t_inf<T>(), prev_cost = 0;
     if (c.compact)   // dead rows are never visited again: give them their final zeros now
-      for (int r = lane; r < nefc; r += 32) { Jaref[r] = T(0); jv[r] = T(0); force[r] = T(0); }
+      for (int r = lane; r < nefc; r += G) { Jaref[r] = T(0); jv[r] = T(0); force[r] = T(0); }
     const int nlive = c.build_live(aref);   // rows that can carry force this step; the rest are exactly-zero rows
 
     // reference _update_constraint :320-357 (cost only, or cost + forces + J^T f)
     auto update_constraint = [&](bool with_force) {
       T cpart = 0;
-      for (int ch = 0; (ch << 5) < nlive; ++ch) {
-        const int idx = (ch << 5) + lane;
+      for (int ch = 0; (ch * G) < nlive; ++ch) {
+        const int idx = (ch * G) + lane;
         bool act = false;
         T fo = 0;
         if (idx < nlive) {
@@ -488,17 +505,17 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
           if (act) cpart += T(0.5) * dr * ja * ja;
           if (with_force) force[r] = fo;
         }
-        const unsigned am = __ballot_sync(0xffffffffu, act);
+        const unsigned am = (__ballot_sync(gm, act) >> (threadIdx.x & 31 & ~(G - 1))) & (G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u));
         if (with_force && lane == 0) c.amask()[ch] = am;
       }
-      __syncwarp();
+      __syncwarp(gm);
       if (with_force) qfrc_con = c.jtmul(force);
       T g = 0;
 #pragma unroll
       for (int k = 0; k < DPL; ++k) g += (Ma.v[k] - qfrc_smooth.v[k]) * (qacc.v[k] - qacc_smooth.v[k]);
-      gauss = T(0.5) * warp_sum(g);
+      gauss = T(0.5) * group_sum<T, G>(g, gm);
       prev_cost = cost;
-      cost = warp_sum(cpart) + gauss;
+      cost = group_sum<T, G>(cpart, gm) + gauss;
     };
 
     auto compute_grad = [&]() {
@@ -510,7 +527,7 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
     auto compute_mgrad = [&]() {
       if (newton) {
         unsigned any = 0;
-        for (int ch = 0; (ch << 5) < nlive; ++ch) any |= c.amask()[ch];
+        for (int ch = 0; (ch * G) < nlive; ++ch) any |= c.amask()[ch];
         // no active row: H = M exactly, and chol(M) is already in Lm -- skip the assembly and the factorisation
         if (any || !lm_is_m) {
           c.hessian(D);
@@ -532,8 +549,8 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
         T a = 0, b = 0, e = 0;
 #pragma unroll
         for (int k = 0; k < DPL; ++k) { a += search.v[k] * Ma.v[k]; b += search.v[k] * qfrc_smooth.v[k]; e += search.v[k] * mv.v[k]; }
-        qg1 = warp_sum(a) - warp_sum(b);
-        qg2 = T(0.5) * warp_sum(e);
+        qg1 = group_sum<T, G>(a, gm) - group_sum<T, G>(b, gm);
+        qg2 = T(0.5) * group_sum<T, G>(e, gm);
       }
       struct Pt { T alpha, cost, d0, d1; };
       // evaluates NA step sizes in one pass over the constraint rows
@@ -541,7 +558,7 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
         T q[3][3];
 #pragma unroll
         for (int a = 0; a < 3; ++a) q[a][0] = q[a][1] = q[a][2] = T(0);
-        for (int idx = lane; idx < nlive; idx += 32) {
+        for (int idx = lane; idx < nlive; idx += G) {
           const int r = c.row_at(idx);
           const T ja = Jaref[r], jr = jv[r], dr = D[r];
           const T c0 = T(0.5) * ja * ja * dr, c1 = jr * ja * dr, c2 = T(0.5) * jr * jr * dr;
@@ -564,7 +581,7 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
           if (a < NA) {
-            const T t0 = qg0 + warp_sum(q[a][0]), t1 = qg1 + warp_sum(q[a][1]), t2 = qg2 + warp_sum(q[a][2]);
+            const T t0 = qg0 + group_sum<T, G>(q[a][0], gm), t1 = qg1 + group_sum<T, G>(q[a][1], gm), t2 = qg2 + group_sum<T, G>(q[a][2], gm);
             out[a].alpha = al[a];
             out[a].cost = al[a] * al[a] * t2 + al[a] * t1 + t0;
             out[a].d0 = T(2) * al[a] * t2 + t1;
@@ -612,8 +629,8 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
       if (improved) {
         qacc = axpy(qacc, alpha, search);
         Ma = axpy(Ma, alpha, mv);
-        for (int idx = lane; idx < nlive; idx += 32) { const int r = c.row_at(idx); Jaref[r] += jv[r] * alpha; }
-        __syncwarp();
+        for (int idx = lane; idx < nlive; idx += G) { const int r = c.row_at(idx); Jaref[r] += jv[r] * alpha; }
+        __syncwarp(gm);
       }
     };
 
@@ -624,7 +641,7 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
     T cost_w = t_inf<T>();
     if (!(flags & DSBL_WARMSTART)) {
 #pragma unroll
-      for (int k = 0; k < DPL; ++k) { const int i = lane + 32 * k; warm.v[k] = i < nv ? in_get<T>(in.qacc_warmstart, B, env, i) : T(0); }
+      for (int k = 0; k < DPL; ++k) { const int i = lane + G * k; warm.v[k] = i < nv ? in_get<T>(in.qacc_warmstart, B, env, i) : T(0); }
       qacc = warm;
       c.jmul(qacc, Jaref, aref, nlive);
       Ma = c.symv(Mm, qacc);
@@ -640,7 +657,7 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
       T* keep = Jaref;
       // evaluate the smooth cost on the parked values
       T cpart = 0;
-      for (int idx = lane; idx < nlive; idx += 32) {
+      for (int idx = lane; idx < nlive; idx += G) {
         const int r = c.row_at(idx);
         const T ja = jv[r], dr = D[r];
         bool act = (ja < T(0)) || (r < ne_nf);
@@ -654,15 +671,15 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
         }
         if (act) cpart += T(0.5) * dr * ja * ja;
       }
-      const T cost_s = warp_sum(cpart);  // gauss term is exactly zero at qacc_smooth
+      const T cost_s = group_sum<T, G>(cpart, gm);  // gauss term is exactly zero at qacc_smooth
       take_warm = cost_w < cost_s;
       if (take_warm) {
         qacc = warm;
         Ma = Ma_w;
       } else {
-        for (int r = lane; r < nefc; r += 32) keep[r] = jv[r];
+        for (int r = lane; r < nefc; r += G) keep[r] = jv[r];
       }
-      __syncwarp();
+      __syncwarp(gm);
     }
     cost = t_inf<T>();
     prev_cost = 0;
@@ -704,7 +721,7 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
       }
     }
     storev(m.D(D_qacc_warmstart), qacc);
-    for (int r = lane; r < nefc; r += 32) d.set(m.D(D_efc_force) + r, force[r]);
+    for (int r = lane; r < nefc; r += G) d.set(m.D(D_efc_force) + r, force[r]);
   }
   storev(m.D(D_qacc), qacc);
   storev(m.D(D_qfrc_constraint), qfrc_con);
@@ -718,20 +735,20 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
   V qacc_int = qacc;
   bool refactor = false;
   if (integrator == INT_EULER && !(flags & DSBL_EULERDAMP)) {
-    for (int p = lane; p < Lo.nP; p += 32) Lm[p] = Mm[p];
-    __syncwarp();
-    for (int i = lane; i < nv; i += 32) Lm[tri(i) + i] += dt * m.F(F_dof_damping)[i];
+    for (int p = lane; p < Lo.nP; p += G) Lm[p] = Mm[p];
+    __syncwarp(gm);
+    for (int i = lane; i < nv; i += G) Lm[tri(i) + i] += dt * m.F(F_dof_damping)[i];
     refactor = true;
   } else if (integrator == INT_IMPLICITFAST) {
     // qderiv = moment^T diag(biasprm2*[affine] + gainprm2*[affine]*ctrl) moment - diag(damping)  (derivative.py:22-68)
     const int nu = m.h(H_nu);
     const bool actuation = !(flags & DSBL_ACTUATION), damper = !(flags & DSBL_DAMPER);
     if (actuation || damper || m.h(H_ntendon)) {
-      for (int p = lane; p < Lo.nP; p += 32) Lm[p] = Mm[p];
-      __syncwarp();
+      for (int p = lane; p < Lo.nP; p += G) Lm[p] = Mm[p];
+      __syncwarp(gm);
       if (damper)
-        for (int i = lane; i < nv; i += 32) Lm[tri(i) + i] += dt * m.F(F_dof_damping)[i];
-      __syncwarp();
+        for (int i = lane; i < nv; i += G) Lm[tri(i) + i] += dt * m.F(F_dof_damping)[i];
+      __syncwarp(gm);
       if (actuation)
         for (int u = 0; u < nu; ++u) {
           T vel = 0;
@@ -741,32 +758,32 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
             vel += m.F(F_act_gainprm)[10 * u + 2] * cu;
           }
           if (vel == T(0)) continue;
-          for (int p = lane; p < Lo.nP; p += 32) {
+          for (int p = lane; p < Lo.nP; p += G) {
             int i = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
             while (tri(i + 1) <= p) ++i;
             while (tri(i) > p) --i;
             const int j = p - tri(i);
             Lm[p] -= dt * d.get(m.D(D_actuator_moment) + u * nv + i) * vel * d.get(m.D(D_actuator_moment) + u * nv + j);
           }
-          __syncwarp();
+          __syncwarp(gm);
         }
       for (int t = 0; t < m.h(H_ntendon); ++t) {
         const T td = m.F(F_ten_damping)[t];
         if (td == T(0)) continue;
-        for (int p = lane; p < Lo.nP; p += 32) {
+        for (int p = lane; p < Lo.nP; p += G) {
           int i = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
           while (tri(i + 1) <= p) ++i;
           while (tri(i) > p) --i;
           const int j = p - tri(i);
           Lm[p] += dt * d.get(m.D(D_ten_J) + t * nv + i) * td * d.get(m.D(D_ten_J) + t * nv + j);
         }
-        __syncwarp();
+        __syncwarp(gm);
       }
       refactor = true;
     }
   }
   if (refactor) {
-    __syncwarp();
+    __syncwarp(gm);
     c.cholesky(Lm);
     V rhs;
 #pragma unroll
@@ -776,7 +793,7 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
 
   // ---- _advance (forward.py:255-310)
   const int nu = m.h(H_nu);
-  for (int u = lane; u < nu; u += 32) {
+  for (int u = lane; u < nu; u += G) {
     const int adr = m.I(I_act_actadr)[u];
     if (adr < 0) continue;
     for (int a = adr; a < adr + m.I(I_act_actnum)[u]; ++a) {
@@ -798,7 +815,7 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
   c.to_smem(qvel, c.xs());
   const T* nvel = c.xs();
   const int oQ = m.D(D_qpos);
-  for (int j = lane; j < m.h(H_njnt); j += 32) {
+  for (int j = lane; j < m.h(H_njnt); j += G) {
     const int jt = m.I(I_jnt_type)[j], qa = m.I(I_jnt_qposadr)[j], da = m.I(I_jnt_dofadr)[j];
     if (jt == JNT_FREE || jt == JNT_BALL) {
       int qq = qa, dd = da;
@@ -817,18 +834,19 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
   if (lane == 0) d.set(m.D(D_time), d.get(m.D(D_time)) + dt);
 }
 
-template <typename T, int DPL, bool COMPACT>
+template <typename T, int DPL, bool COMPACT, int G>
 __global__ void __launch_bounds__((sizeof(T) == 4 ? 512 : MJT_SOLVE_F64_THREADS), (sizeof(T) == 4 ? 2 : MJT_SOLVE_F64_MINB)) k_solve(const int* __restrict__ gfull, const int* __restrict__ gblob, int blob_words, MjtIn in,
                                                T* __restrict__ out, int B, int mode) {
   extern __shared__ __align__(16) int smem_blob[];
   __shared__ uint64_t bar;
   stage_blob(smem_blob, &bar, gblob, blob_words);
   const ModelView<T> m = make_view<T>(smem_blob);
-  const int E = blockDim.x >> 5;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int E = blockDim.x / G;                                   // envs per CTA, G lanes each
+  const int warp = threadIdx.x / G, lane = threadIdx.x & (G - 1);   // "warp" = env slot inside the CTA
+  const unsigned gm = group_mask<G>();
   const int env0 = blockIdx.x * E;
   const int nv = m.h(H_nv), nefc = m.h(H_nefc);
-  const SolveLayout Lo = solve_layout(nv, nefc, m.h(H_jc_words), m.h(H_nf), m.h(H_nsrc), (int)sizeof(T), COMPACT);
+  const SolveLayout Lo = solve_layout(nv, nefc, m.h(H_jc_words), m.h(H_nf), m.h(H_nsrc), (int)sizeof(T), COMPACT, G);
   T* region = reinterpret_cast<T*>(smem_blob + ((blob_words + 3) & ~3));
   const size_t Bs = (size_t)B;
 
@@ -866,21 +884,21 @@ __global__ void __launch_bounds__((sizeof(T) == 4 ? 512 : MJT_SOLVE_F64_THREADS)
   const int env = env0 + warp;
   const bool valid = env < B;
   EnvBuf<T> d{out + (valid ? env : 0), Bs};
-  SolveCtx<T, DPL, COMPACT> c{m, region + (size_t)warp * Lo.words, Lo, nv, nefc, lane,
-                     m.I(I_row_src), m.I(I_row_jadr), m.I(I_src_nsup), m.I(I_src_cadr), m.I(I_src_row), m.I(I_src_nrows), m.I(I_sup_col), m.I(I_tri_ab), m.I(I_dof_sadr), m.I(I_dof_sent)};
+  SolveCtx<T, DPL, COMPACT, G> c{m, region + (size_t)warp * Lo.words, Lo, nv, nefc, lane,
+                     m.I(I_row_src), m.I(I_row_jadr), m.I(I_src_nsup), m.I(I_src_cadr), m.I(I_src_row), m.I(I_src_nrows), m.I(I_sup_col), m.I(I_tri_ab), m.I(I_dof_sadr), m.I(I_dof_sent), group_mask<G>()};
   Vec<T, DPL> qfrc_smooth = c.zero(), qacc_smooth = c.zero();
   if (valid) {
     // ---- factor_m + qacc_smooth
     T* Lm = c.Lp();
     const T* Mm = c.Mp();
-    for (int p = lane; p < Lo.nP; p += 32) Lm[p] = Mm[p];
-    __syncwarp();
+    for (int p = lane; p < Lo.nP; p += G) Lm[p] = Mm[p];
+    __syncwarp(gm);
     c.cholesky(Lm);
 #pragma unroll
-    for (int k = 0; k < DPL; ++k) { const int i = lane + 32 * k; qfrc_smooth.v[k] = i < nv ? d.get(m.D(D_qfrc_smooth) + i) : T(0); }
+    for (int k = 0; k < DPL; ++k) { const int i = lane + G * k; qfrc_smooth.v[k] = i < nv ? d.get(m.D(D_qfrc_smooth) + i) : T(0); }
     qacc_smooth = c.cho_solve(Lm, qfrc_smooth);
 #pragma unroll
-    for (int k = 0; k < DPL; ++k) { const int i = lane + 32 * k; if (i < nv) d.set(m.D(D_qacc_smooth) + i, qacc_smooth.v[k]); }
+    for (int k = 0; k < DPL; ++k) { const int i = lane + G * k; if (i < nv) d.set(m.D(D_qacc_smooth) + i, qacc_smooth.v[k]); }
   }
   __syncthreads();
   {  // cooperative store of qLD = chol(M) (dense lower, zeros above the diagonal)
@@ -895,5 +913,5 @@ __global__ void __launch_bounds__((sizeof(T) == 4 ? 512 : MJT_SOLVE_F64_THREADS)
   }
   __syncthreads();
   if (!valid) return;
-  solve_env<T, DPL, COMPACT>(m, in, d, Bs, env, c, qfrc_smooth, qacc_smooth, mode);
+  solve_env<T, DPL, COMPACT, G>(m, in, d, Bs, env, c, qfrc_smooth, qacc_smooth, mode);
 }

@@ -60,6 +60,7 @@ struct mjtModel {
   int solve_envs;  // envs (warps) per CTA in k_solve
   size_t solve_smem;
   size_t solve_blob_bytes, solve_region_bytes;  // smem = blob + envs * region
+  int solve_lanes;                              // lanes per env in k_solve (32, or 16 for nv <= 16)
   int hv(int k) const { return h[k]; }
 };
 
@@ -95,30 +96,34 @@ extern "C" int mjt_model_create(const void* blob_host, size_t nbytes, int device
   m->max_smem = (int)prop.sharedMemPerBlockOptin;
   CUDA_OK(cudaMalloc(&m->d_blob, nbytes));
   CUDA_OK(cudaMemcpy(m->d_blob, blob_host, nbytes, cudaMemcpyHostToDevice));
-  // k_solve shared-memory budget: blob + E per-env regions; pick the E in {8,4,2,1} that maximises resident warps per SM
+  // k_solve launch shape.  G lanes per env: a half warp for models with nv <= 16 (two envs per warp), else a full warp.
+  // Pick the envs per CTA that maximise resident envs per SM under the shared-memory and register budgets.
   const int nv = w[H_nv], nefc = w[H_nefc];
   const size_t tsz = m->f64 ? 8 : 4;
-  const size_t region = (size_t)solve_layout(nv, nefc, w[H_jc_words], w[H_nf], w[H_nsrc], (int)tsz, nefc > MJT_COMPACT_MIN_NEFC).words * tsz;
+  const int G = nv <= 16 ? 16 : 32;
+  m->solve_lanes = G;
+  const size_t region = (size_t)solve_layout(nv, nefc, w[H_jc_words], w[H_nf], w[H_nsrc], (int)tsz, nefc > MJT_COMPACT_MIN_NEFC, G).words * tsz;
   const size_t blob_b = ((size_t)m->blob_words + 3) / 4 * 16;
   const size_t sblob_b = ((size_t)m->solve_words + 3) / 4 * 16;
   const size_t sm_total = (size_t)prop.sharedMemPerMultiprocessor;
   int best_e = 0;
-  size_t best_warps = 0;
+  size_t best_envs = 0;
   // f64 kernel: MJT_SOLVE_F64_THREADS x MJT_SOLVE_F64_MINB threads fit the register file; f32 kernel: 2 x 512
-  const int emax = m->f64 ? MJT_SOLVE_F64_THREADS / 32 : 16;
-  const size_t wcap = m->f64 ? (size_t)(MJT_SOLVE_F64_THREADS / 32) * MJT_SOLVE_F64_MINB : 32;
-  for (int e = emax; e >= 1; --e) {   // most resident warps per SM wins; ties go to the larger CTA
+  const int tmax = m->f64 ? MJT_SOLVE_F64_THREADS : 512;
+  const size_t tcap = (size_t)tmax * (m->f64 ? MJT_SOLVE_F64_MINB : 2);   // resident threads per SM
+  const int estep = 32 / G, emax = tmax / G;
+  for (int e = emax; e >= estep; e -= estep) {   // most resident envs per SM wins; ties go to the larger CTA
     const size_t need = sblob_b + region * e + 1024;
     if (need > (size_t)m->max_smem) continue;
     size_t ctas = sm_total / need;
     if (ctas > 32) ctas = 32;
-    size_t warps = ctas * e;
-    if (warps > wcap) warps = wcap;
-    if (warps > best_warps) { best_warps = warps; best_e = e; }
+    size_t envs = ctas * e;
+    if (envs * G > tcap) envs = tcap / G;
+    if (envs > best_envs) { best_envs = envs; best_e = e; }
   }
   if (const char* force = getenv("MJT_SOLVE_E")) {   // tuning knob: force envs per CTA
     const int e = atoi(force);
-    if (e >= 1 && e <= emax && sblob_b + region * e + 1024 <= (size_t)m->max_smem) best_e = e;
+    if (e >= estep && e <= emax && e % estep == 0 && sblob_b + region * e + 1024 <= (size_t)m->max_smem) best_e = e;
   }
   if (best_e == 0) {
     delete m;
@@ -218,16 +223,18 @@ static int run_forward(const mjtModel* m, const MjtIn& in, T* out, int B, int mo
     const int gs = (B + E - 1) / E;
     // COMPACT instantiation (live-row list) for models with more than two 32-row chunks of constraint rows
     const bool compact = m->hv(H_nefc) > MJT_COMPACT_MIN_NEFC;
-#define MJT_SOLVE_LAUNCH(DPLV, CV)                                                                                      \
+#define MJT_SOLVE_LAUNCH(DPLV, CV, GV)                                                                                  \
   do {                                                                                                                  \
-    if (set_smem<T>((const void*)k_solve<T, DPLV, CV>, m->solve_smem)) return 1;                                        \
-    LAUNCH("k_solve", st, k_solve<T, DPLV, CV><<<gs, 32 * E, smem, st>>>(m->d_blob, m->d_blob + m->blob_words,        \
-                                                                         m->solve_words, in, out, B, mode));          \
+    if (set_smem<T>((const void*)k_solve<T, DPLV, CV, GV>, m->solve_smem)) return 1;                                    \
+    LAUNCH("k_solve", st, k_solve<T, DPLV, CV, GV><<<gs, GV * E, smem, st>>>(m->d_blob, m->d_blob + m->blob_words,    \
+                                                                             m->solve_words, in, out, B, mode));      \
   } while (0)
-    if (m->hv(H_nv) <= 32) {
-      if (compact) MJT_SOLVE_LAUNCH(1, true); else MJT_SOLVE_LAUNCH(1, false);
+    if (m->solve_lanes == 16) {
+      if (compact) MJT_SOLVE_LAUNCH(1, true, 16); else MJT_SOLVE_LAUNCH(1, false, 16);
+    } else if (m->hv(H_nv) <= 32) {
+      if (compact) MJT_SOLVE_LAUNCH(1, true, 32); else MJT_SOLVE_LAUNCH(1, false, 32);
     } else if (m->hv(H_nv) <= 64) {
-      if (compact) MJT_SOLVE_LAUNCH(2, true); else MJT_SOLVE_LAUNCH(2, false);
+      if (compact) MJT_SOLVE_LAUNCH(2, true, 32); else MJT_SOLVE_LAUNCH(2, false, 32);
     } else {
       return fail("mjt: nv > 64 not supported by the dense solver kernel");
     }
