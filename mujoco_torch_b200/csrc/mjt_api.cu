@@ -15,6 +15,9 @@
 #include "k_solve.cuh"
 #include "mjt_common.cuh"
 
+#ifndef MJT_CONSTRAINT_SPLIT
+#define MJT_CONSTRAINT_SPLIT 1024   // CTAs per env block in k_constraint (capped by the number of row sources)
+#endif
 static thread_local std::string g_err;
 
 // Optional per-kernel timing (bench.py's roofline leg): when enabled every launch is bracketed by CUDA events on the
@@ -100,7 +103,10 @@ extern "C" int mjt_model_create(const void* blob_host, size_t nbytes, int device
   // Pick the envs per CTA that maximise resident envs per SM under the shared-memory and register budgets.
   const int nv = w[H_nv], nefc = w[H_nefc];
   const size_t tsz = m->f64 ? 8 : 4;
-  const int G = nv <= 16 ? 16 : 32;
+  int G = nv <= 16 ? 16 : 32;
+  if (const char* fg = getenv("MJT_SOLVE_G")) {   // experiment knob: half warps with two dofs per lane for 16 < nv <= 32
+    if (atoi(fg) == 16 && nv <= 32) G = 16;
+  }
   m->solve_lanes = G;
   const size_t region = (size_t)solve_layout(nv, nefc, w[H_jc_words], w[H_nf], w[H_nsrc], (int)tsz, nefc > MJT_COMPACT_MIN_NEFC, G).words * tsz;
   const size_t blob_b = ((size_t)m->blob_words + 3) / 4 * 16;
@@ -208,7 +214,11 @@ static int run_forward(const mjtModel* m, const MjtIn& in, T* out, int B, int mo
   }
   if (m->hv(H_nsrc) > 0) {
     if (set_smem<T>((const void*)k_constraint<T>, blob_b)) return 1;
-    dim3 grid(m->hv(H_nsrc), gx < 65535 ? gx : 65535);
+    // grid.x CTAs share one env block and split its row sources; each CTA stages the model blob once, so a few sources
+    // per CTA amortise the staging while still spreading an env block's rows over several SMs
+    int sx = m->hv(H_nsrc) < MJT_CONSTRAINT_SPLIT ? m->hv(H_nsrc) : MJT_CONSTRAINT_SPLIT;
+    if (const char* fs = getenv("MJT_CONSTRAINT_SPLIT")) { const int v = atoi(fs); if (v >= 1) sx = v < m->hv(H_nsrc) ? v : m->hv(H_nsrc); }
+    dim3 grid(sx, gx < 65535 ? gx : 65535);
     LAUNCH("k_constraint", st, k_constraint<T><<<grid, threads, blob_b, st>>>(m->d_blob, m->blob_words, in, out, B));
     ++n;
   }
@@ -229,8 +239,10 @@ static int run_forward(const mjtModel* m, const MjtIn& in, T* out, int B, int mo
     LAUNCH("k_solve", st, k_solve<T, DPLV, CV, GV><<<gs, GV * E, smem, st>>>(m->d_blob, m->d_blob + m->blob_words,    \
                                                                              m->solve_words, in, out, B, mode));      \
   } while (0)
-    if (m->solve_lanes == 16) {
+    if (m->solve_lanes == 16 && m->hv(H_nv) <= 16) {
       if (compact) MJT_SOLVE_LAUNCH(1, true, 16); else MJT_SOLVE_LAUNCH(1, false, 16);
+    } else if (m->solve_lanes == 16) {
+      if (compact) MJT_SOLVE_LAUNCH(2, true, 16); else MJT_SOLVE_LAUNCH(2, false, 16);
     } else if (m->hv(H_nv) <= 32) {
       if (compact) MJT_SOLVE_LAUNCH(1, true, 32); else MJT_SOLVE_LAUNCH(1, false, 32);
     } else if (m->hv(H_nv) <= 64) {

@@ -13,7 +13,7 @@ run --model humanoid --batch 65536 --integrator implicitfast --dtype f32
 run --model humanoid --batch 131072
 run --model humanoid --batch 4096
 for b in 1024 16384 65536; do run --model stack --batch $b; done   # config 5 (RK4)
-run --model walker2d --batch 32768 --integrator rk4
+run --model walker2d --batch 32768
 run --model hopper --batch 131072
 python - <<'PY'
 import json
