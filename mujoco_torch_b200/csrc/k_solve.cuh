@@ -90,6 +90,48 @@ __device__ __forceinline__ T vec_bcast(const Vec<T, 2>& x, int i, unsigned gm) {
 
 __device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
 
+// In-place Cholesky of a packed lower triangle for n <= G (one row per lane): lane i keeps row i of L in registers, so
+// the inner product reads only row j from shared memory (a broadcast) instead of two strided rows.  A free function of
+// scalars and pointers only: MJT_CHOL_CALL = 1 compiles it once per kernel (__noinline__; the unrolled body is ~1.5 k
+// instructions and has three call sites) without forcing the solver context out of registers.
+#ifndef MJT_CHOL_CALL
+#define MJT_CHOL_CALL 0
+#endif
+#if MJT_CHOL_CALL
+#define MJT_CHOL_INLINE __noinline__
+#else
+#define MJT_CHOL_INLINE __forceinline__
+#endif
+template <typename T, int G>
+__device__ MJT_CHOL_INLINE void cholesky_rows_fn(T* A, T* di, int n, int lane, unsigned gm) {
+  const bool big = n > 16;
+  T r[G];
+  const bool mine = lane < n;
+  T* rowi = A + tri(mine ? lane : 0);
+#pragma unroll
+  for (int j = 0; j < G; ++j) {
+    if (j < n) {
+      const T* rowj = A + tri(j);
+      T acc = (mine && lane >= j) ? rowi[j] : T(0), acc2 = T(0);
+#pragma unroll
+      for (int k = 0; k + 1 < j; k += 2) {
+        acc -= r[k] * rowj[k];
+        acc2 -= r[k + 1] * rowj[k + 1];
+      }
+      if (j & 1) acc -= r[j - 1] * rowj[j - 1];
+      acc += acc2;
+      T sdiag = __shfl_sync(gm, acc, j, G);
+      if (big) sdiag += T(1e-10); else sdiag = t_max(sdiag, T(1e-12));
+      const T inv = t_rsqrt(sdiag);
+      const T lij = (lane == j) ? sdiag * inv : acc * inv;
+      r[j] = lane >= j ? lij : T(0);
+      if (mine && lane >= j) rowi[j] = lij;   // column j of other rows is not read during this step: no hazard
+      if (lane == 0) di[j] = inv;
+      __syncwarp(gm);
+    }
+  }
+}
+
 template <typename T, int DPL, bool COMPACT, int G>
 struct SolveCtx {
   const ModelView<T>& m;
@@ -247,38 +289,7 @@ struct SolveCtx {
     }
     return out;
   }
-  // n <= 32 (one row per lane): lane i keeps row i of L in registers, so the inner product reads only row j from
-  // shared memory (a broadcast) instead of two strided rows
-  __device__ __forceinline__ void cholesky_rows(T* A) const {
-    const int n = nv;
-    const bool big = n > 16;
-    T* di = dinv();
-    T r[G];
-    const bool mine = lane < n;
-    T* rowi = A + tri(mine ? lane : 0);
-#pragma unroll
-    for (int j = 0; j < G; ++j) {
-      if (j < n) {
-        const T* rowj = A + tri(j);
-        T acc = (mine && lane >= j) ? rowi[j] : T(0), acc2 = T(0);
-#pragma unroll
-        for (int k = 0; k + 1 < j; k += 2) {
-          acc -= r[k] * rowj[k];
-          acc2 -= r[k + 1] * rowj[k + 1];
-        }
-        if (j & 1) acc -= r[j - 1] * rowj[j - 1];
-        acc += acc2;
-        T sdiag = __shfl_sync(gm, acc, j, G);
-        if (big) sdiag += T(1e-10); else sdiag = t_max(sdiag, T(1e-12));
-        const T inv = t_rsqrt(sdiag);
-        const T lij = (lane == j) ? sdiag * inv : acc * inv;
-        r[j] = lane >= j ? lij : T(0);
-        if (mine && lane >= j) rowi[j] = lij;   // column j of other rows is not read during this step: no hazard
-        if (lane == 0) di[j] = inv;
-        __syncwarp(gm);
-      }
-    }
-  }
+  __device__ __forceinline__ void cholesky_rows(T* A) const { cholesky_rows_fn<T, G>(A, dinv(), nv, lane, gm); }
   __device__ __forceinline__ void cholesky(T* A) const {
     if (DPL == 1 && MJT_CHOL_ROWS) { cholesky_rows(A); return; }
     const int n = nv;
