@@ -366,6 +366,7 @@ struct SolveCtx {
   __device__ __forceinline__ void hessian(const T* D) const {
     T* H = Lp();
     const T* M0 = Mp();
+    __syncwarp(gm);   // the previous factor may still be read by lagging lanes
     for (int p = lane; p < L.nP; p += G) H[p] = M0[p];
     __syncwarp(gm);
     // sources that touch a single dof (joint limits, dof friction): one lane per dof adds their diagonal terms
@@ -745,6 +746,7 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
   const T dt = m.opt(OPT_timestep);
   V qacc_int = qacc;
   bool refactor = false;
+  __syncwarp(gm);   // every lane is done reading the solver's factor before Lm is rebuilt below (racecheck-clean)
   if (integrator == INT_EULER && !(flags & DSBL_EULERDAMP)) {
     for (int p = lane; p < Lo.nP; p += G) Lm[p] = Mm[p];
     __syncwarp(gm);

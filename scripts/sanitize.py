@@ -1,0 +1,25 @@
+"""Small steps of every kernel family for compute-sanitizer (memcheck / racecheck / synccheck): odd batch sizes, f64 and f32,
+full-warp, half-warp, compact and two-dof-per-lane solver instantiations, convex narrowphase, RK4, sensors."""
+import os, sys
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import util
+import mujoco_torch_b200 as mt
+
+CASES = [("humanoid", {}, 0.4, 33), ("halfcheetah", {}, 0.6, 37), ("ant", {}, 0.0, 5), ("ant_zoo", {"cone": 1, "solver": 1}, 0.5, 19),
+         ("stack", {}, -2.0, 7), ("sink", {}, -3.0, 9), ("sink", {"integrator": 3}, -3.0, 3), ("equality_bodies", {}, 0.0, 4),
+         ("convex", {}, -1.0, 3), ("cartpole", {}, 0.0, 1)]
+for name, opt, drop, B in CASES:
+    mj = util.load_model(name, **opt)
+    act = None
+    if drop >= 0:
+        qpos, qvel, ctrl = util.seeded_state(mj, B, drop=drop)
+    elif drop < -2.5:
+        qpos, qvel, ctrl, act = util.sink_state(mj, B)
+    else:
+        qpos, qvel, ctrl = util.pile_state(mj, B) if drop > -1.5 else util.stack_state(mj, B)
+    for dtype in (torch.float64, torch.float32):
+        mx, d = util.run_cuda(mj, qpos, qvel, ctrl, dtype, nsteps=2, act=act)
+        assert torch.isfinite(d.qpos).all(), (name, dtype)
+    print("ok", name, opt, B, flush=True)
