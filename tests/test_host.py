@@ -122,3 +122,24 @@ def test_unsupported_features_raise():
     mj.opt.solver = 0  # PGS
     with pytest.raises(NotImplementedError):
         mt.device_put(mj)
+
+
+def test_out_of_scope_models_raise_at_device_put():
+    """sparse-M models (nv >= 60), collisions the reference has no function for, and unsupported sensors fail
+    loudly at device_put -- never at step time, never silently."""
+    from mujoco_torch_b200 import mjcf
+
+    links = "".join(f'<body pos="0 0 -0.1"><joint type="hinge" axis="0 1 0"/><geom type="capsule" size="0.02" fromto="0 0 0 0 0 -0.1"/>'
+                    for _ in range(60)) + "</body>" * 60
+    big = mjcf.from_xml_string(f"<mujoco><worldbody>{links}</worldbody></mujoco>")
+    assert big.nv == 60
+    with pytest.raises(NotImplementedError, match="sparse"):
+        mt.device_put(big)
+    cyl = mjcf.from_xml_string('<mujoco><worldbody><geom type="plane" size="1 1 .1"/><body pos="0 0 1"><freejoint/>'
+                               '<geom type="cylinder" size="0.1 0.2"/></body></worldbody></mujoco>')
+    with pytest.raises(NotImplementedError, match="collisions not implemented"):
+        mt.device_put(cyl)
+    frc = mjcf.from_xml_string('<mujoco><worldbody><body pos="0 0 1"><joint type="hinge"/><geom type="sphere" size="0.1"/>'
+                               '<site name="s"/></body></worldbody><sensor><force site="s"/></sensor></mujoco>')
+    with pytest.raises(NotImplementedError, match="sensor"):
+        mt.device_put(frc)
