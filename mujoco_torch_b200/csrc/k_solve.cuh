@@ -12,49 +12,9 @@
 // every data-dependent branch (active rows, line-search bracketing, early exit) is warp-uniform: inactive rows and
 // converged envs cost nothing -- the per-env early exit the reference's masked while_loop emulates.
 #pragma once
-// f64 launch shape of k_solve: threads per CTA (= 32 x envs per CTA) and minimum CTAs per SM (caps registers/thread)
-#ifndef MJT_SOLVE_F64_THREADS
-#define MJT_SOLVE_F64_THREADS 512
-#endif
-#ifndef MJT_CHOL_ROWS
-#define MJT_CHOL_ROWS 1   // n <= 32: keep each lane's row of L in registers during the factorisation
-#endif
-#ifndef MJT_COMPACT_MIN_NEFC
-#define MJT_COMPACT_MIN_NEFC 64   // models with more constraint rows than this use the live-row (COMPACT) solver instantiation
-#endif
-#ifndef MJT_SOLVE_F64_MINB
-#define MJT_SOLVE_F64_MINB 1
-#endif
+#include "mjt_solve_layout.h"
 #include "mjt_common.cuh"
 #include "k_smooth.cuh"
-
-struct SolveLayout {
-  int nP, oJ, oM, oL, oDinv, oXs, oYs, oD, oAref, oFloss, oJaref, oJv, oForce, oMask, oLive, nchunk, words;
-};
-
-__host__ __device__ inline SolveLayout solve_layout(int nv, int nefc, int jc_words, int nf, int nsrc, int tsize, bool compact, int G) {
-  SolveLayout s;
-  s.nP = nv * (nv + 1) / 2;
-  s.nchunk = (nefc + G - 1) / G;   // one mask word per G rows (G = lanes per env)
-  int o = 0;
-  s.oJ = o; o += jc_words;
-  s.oM = o; o += s.nP;
-  s.oL = o; o += s.nP;
-  s.oDinv = o; o += nv;
-  s.oXs = o; o += nv;
-  s.oYs = o; o += nv;
-  s.oD = o; o += nefc;
-  s.oAref = o; o += nefc;
-  s.oFloss = o; o += nf > 0 ? nefc : 0;
-  s.oJaref = o; o += nefc;
-  s.oJv = o; o += nefc;
-  s.oForce = o; o += nefc;
-  s.oMask = o; o += s.nchunk;  // active-row bitmask over the *live* rows (uint32 per 32 rows, stored in T-sized slots)
-  // live-row list (nefc ints) + compact position of every source (nsrc ints), packed as ints
-  s.oLive = o; o += compact ? ((nefc + nsrc) * 4 + tsize - 1) / tsize : 0;
-  s.words = (o + 3) & ~3;
-  return s;
-}
 
 // 4/8-byte asynchronous global->shared copy (LDGSTS): no staging register, so a thread keeps all its copies in flight
 template <typename T>

@@ -12,7 +12,7 @@
 #include "k_convex.cuh"
 #include "k_sensor.cuh"
 #include "k_smooth.cuh"
-#include "k_solve.cuh"
+#include "mjt_solve_layout.h"
 #include "mjt_common.cuh"
 
 #ifndef MJT_CONSTRAINT_SPLIT
@@ -178,6 +178,15 @@ static MjtIn to_in(const mjtStateIn* s) {
   return in;
 }
 
+static cudaError_t launch_solve(int lanes, int dpl, bool compact, int grid, int threads, size_t smem, size_t smem_attr, cudaStream_t st,
+                                const int* blob, const int* sblob, int solve_words, const MjtIn& in, float* out, int B, int mode) {
+  return mjt_launch_solve_f32(lanes, dpl, compact, grid, threads, smem, smem_attr, st, blob, sblob, solve_words, in, out, B, mode);
+}
+static cudaError_t launch_solve(int lanes, int dpl, bool compact, int grid, int threads, size_t smem, size_t smem_attr, cudaStream_t st,
+                                const int* blob, const int* sblob, int solve_words, const MjtIn& in, double* out, int B, int mode) {
+  return mjt_launch_solve_f64(lanes, dpl, compact, grid, threads, smem, smem_attr, st, blob, sblob, solve_words, in, out, B, mode);
+}
+
 template <typename T>
 static int set_smem(const void* fn, size_t bytes) {
   if (bytes > 48 * 1024) {
@@ -233,23 +242,16 @@ static int run_forward(const mjtModel* m, const MjtIn& in, T* out, int B, int mo
     const int gs = (B + E - 1) / E;
     // COMPACT instantiation (live-row list) for models with more than two 32-row chunks of constraint rows
     const bool compact = m->hv(H_nefc) > MJT_COMPACT_MIN_NEFC;
-#define MJT_SOLVE_LAUNCH(DPLV, CV, GV)                                                                                  \
-  do {                                                                                                                  \
-    if (set_smem<T>((const void*)k_solve<T, DPLV, CV, GV>, m->solve_smem)) return 1;                                    \
-    LAUNCH("k_solve", st, k_solve<T, DPLV, CV, GV><<<gs, GV * E, smem, st>>>(m->d_blob, m->d_blob + m->blob_words,    \
-                                                                             m->solve_words, in, out, B, mode));      \
-  } while (0)
-    if (m->solve_lanes == 16 && m->hv(H_nv) <= 16) {
-      if (compact) MJT_SOLVE_LAUNCH(1, true, 16); else MJT_SOLVE_LAUNCH(1, false, 16);
-    } else if (m->solve_lanes == 16) {
-      if (compact) MJT_SOLVE_LAUNCH(2, true, 16); else MJT_SOLVE_LAUNCH(2, false, 16);
-    } else if (m->hv(H_nv) <= 32) {
-      if (compact) MJT_SOLVE_LAUNCH(1, true, 32); else MJT_SOLVE_LAUNCH(1, false, 32);
-    } else if (m->hv(H_nv) <= 64) {
-      if (compact) MJT_SOLVE_LAUNCH(2, true, 32); else MJT_SOLVE_LAUNCH(2, false, 32);
-    } else {
-      return fail("mjt: nv > 64 not supported by the dense solver kernel");
+    const int lanes = m->solve_lanes;
+    if (m->hv(H_nv) > 2 * lanes) return fail("mjt: nv > 64 not supported by the dense solver kernel");
+    const int dpl = m->hv(H_nv) <= lanes ? 1 : 2;
+    cudaError_t se;
+    {
+      ProfScope prof__("k_solve", st);
+      se = launch_solve(lanes, dpl, compact, gs, lanes * E, smem, m->solve_smem, st, m->d_blob, m->d_blob + m->blob_words, m->solve_words,
+                        in, out, B, mode);
     }
+    if (se != cudaSuccess) return fail(std::string("k_solve launch: ") + cudaGetErrorString(se));
     ++n;
   }
   // acc-stage sensors run only when the solver ran (reference forward.py:390-401 returns early when nefc == 0)
