@@ -203,7 +203,18 @@ def main():
     if dist:
         import torch.distributed as td
 
-        td.init_process_group("nccl", device_id=dev)
+        # NCCL may log its banner to stdout when NCCL_DEBUG is set in the environment: keep stdout for the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            td.init_process_group("nccl", device_id=dev)
+            td.barrier()   # creates the communicator now, while stdout is parked on stderr
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     dtype = torch.float64 if args.dtype == "f64" else torch.float32
     tsize = 8 if args.dtype == "f64" else 4
