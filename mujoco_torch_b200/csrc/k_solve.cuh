@@ -722,32 +722,56 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
       if (damper)
         for (int i = lane; i < nv; i += G) Lm[tri(i) + i] += dt * m.F(F_dof_damping)[i];
       __syncwarp(gm);
-      if (actuation)
-        for (int u = 0; u < nu; ++u) {
+      if (actuation) {
+        // d(force_u)/d(velocity) of actuator u (derivative.py:40-55)
+        auto act_vel = [&](int u) {
           T vel = 0;
           if (m.I(I_act_biastype)[u] == BIAS_AFFINE) vel += m.F(F_act_biasprm)[10 * u + 2];
           if (m.I(I_act_gaintype)[u] == GAIN_AFFINE) {
             const T cu = m.I(I_act_dyntype)[u] != DYN_NONE ? d.get(m.D(D_act) + m.I(I_act_actadr)[u]) : in_get<T>(in.ctrl, B, env, u);
             vel += m.F(F_act_gainprm)[10 * u + 2] * cu;
           }
+          return vel;
+        };
+        // a hinge / slide joint transmission has the single moment entry gear[0] at its dof: a diagonal update
+        auto simple_dof = [&](int u) {
+          const int trn = m.I(I_act_trntype)[u];
+          if (trn != TRN_JOINT && trn != TRN_JOINTINPARENT) return -1;
+          const int j = m.I(I_act_trnid)[u], jt = m.I(I_jnt_type)[j];
+          return (jt == JNT_HINGE || jt == JNT_SLIDE) ? m.I(I_jnt_dofadr)[j] : -1;
+        };
+        for (int u0 = 0; u0 < nu; u0 += G) {   // lane u evaluates actuator u; the updates are applied one by one
+          const int u = u0 + lane;
+          int dof = -1;
+          T val = 0;
+          if (u < nu) {
+            dof = simple_dof(u);
+            if (dof >= 0) { const T g = m.F(F_act_gear)[6 * u]; val = dt * g * act_vel(u) * g; }
+          }
+          const int cnt = (nu - u0) < G ? (nu - u0) : G;
+          for (int k = 0; k < cnt; ++k) {
+            const int dk = __shfl_sync(gm, dof, k, G);
+            const T vk = __shfl_sync(gm, val, k, G);
+            if (lane == 0 && dk >= 0 && vk != T(0)) Lm[tri(dk) + dk] -= vk;
+          }
+        }
+        __syncwarp(gm);
+        for (int u = 0; u < nu; ++u) {   // ball / free / tendon transmissions: dense rank-one update from the stored moment row
+          if (simple_dof(u) >= 0) continue;
+          const T vel = act_vel(u);
           if (vel == T(0)) continue;
           for (int p = lane; p < Lo.nP; p += G) {
-            int i = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
-            while (tri(i + 1) <= p) ++i;
-            while (tri(i) > p) --i;
-            const int j = p - tri(i);
+            const int ab = c.tri_ab[p], i = ab & 0xffff, j = ab >> 16;
             Lm[p] -= dt * d.get(m.D(D_actuator_moment) + u * nv + i) * vel * d.get(m.D(D_actuator_moment) + u * nv + j);
           }
           __syncwarp(gm);
         }
+      }
       for (int t = 0; t < m.h(H_ntendon); ++t) {
         const T td = m.F(F_ten_damping)[t];
         if (td == T(0)) continue;
         for (int p = lane; p < Lo.nP; p += G) {
-          int i = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
-          while (tri(i + 1) <= p) ++i;
-          while (tri(i) > p) --i;
-          const int j = p - tri(i);
+          const int ab = c.tri_ab[p], i = ab & 0xffff, j = ab >> 16;
           Lm[p] += dt * d.get(m.D(D_ten_J) + t * nv + i) * td * d.get(m.D(D_ten_J) + t * nv + j);
         }
         __syncwarp(gm);

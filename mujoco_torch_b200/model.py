@@ -571,7 +571,7 @@ class Model:
             return out
 
         # the solver kernel stages a reduced blob (only the tables it reads) so that more envs fit in shared memory
-        solve_keep = set("jnt_type jnt_qposadr jnt_dofadr act_dyntype act_gaintype act_biastype act_actadr act_actnum act_actlimited "
+        solve_keep = set("jnt_type jnt_qposadr jnt_dofadr act_trntype act_trnid act_gear act_dyntype act_gaintype act_biastype act_actadr act_actnum act_actlimited "
                          "src_row src_nrows src_nsup src_cadr sup_col row_src row_jadr tri_ab dof_sadr dof_sent jc_src "
                          "opt dof_damping act_actrange act_gainprm act_biasprm act_dynprm ten_damping".split())
         solve_blob = assemble(solve_keep)
