@@ -79,6 +79,7 @@ __device__ void constraint_source(const ModelView<T>& m, const MjtIn& in, const 
   const int* body_root = m.I(I_body_rootid);
   const T* dof_iw = m.F(F_dof_invweight0);
 
+  bool live = true;   // false when every row of this source is exactly zero this step (J, aref) -- see k_solve's live tile
   switch (type) {
     case SRC_LIM_SH: {  // constraint.py:338-372
       const int qa = m.I(I_jnt_qposadr)[id], da = m.I(I_jnt_dofadr)[id];
@@ -87,6 +88,7 @@ __device__ void constraint_source(const ModelView<T>& m, const MjtIn& in, const 
       const T val = dist_min < dist_max ? T(1) : T(-1);
       T pos = t_min(dist_min, dist_max) - m.F(F_jnt_margin)[id];
       const T act = pos < T(0) ? T(1) : T(0);
+      live = act != T(0);
       pos *= act;
       out.zero(row0, 1);
       out.J(row0, da, val * act);
@@ -100,6 +102,7 @@ __device__ void constraint_source(const ModelView<T>& m, const MjtIn& in, const 
       q2axisangle(q, &axis, &angle);
       T pos = t_max(m.F(F_jnt_range)[2 * id], m.F(F_jnt_range)[2 * id + 1]) - angle - m.F(F_jnt_margin)[id];
       const T act = pos < T(0) ? T(1) : T(0);
+      live = act != T(0);
       pos *= act;
       out.zero(row0, 1);
       const T j3[3] = {-axis.x * act, -axis.y * act, -axis.z * act};
@@ -112,6 +115,7 @@ __device__ void constraint_source(const ModelView<T>& m, const MjtIn& in, const 
       const T dist_min = len - m.F(F_ten_range)[2 * id], dist_max = m.F(F_ten_range)[2 * id + 1] - len;
       T pos = t_min(dist_min, dist_max) - m.F(F_ten_margin)[id];
       const T act = pos < T(0) ? T(1) : T(0);
+      live = act != T(0);
       const T sign = (dist_min < dist_max ? T(1) : T(-1)) * act;
       pos *= act;
       T jv = 0;
@@ -143,6 +147,7 @@ __device__ void constraint_source(const ModelView<T>& m, const MjtIn& in, const 
       const T has2 = j2raw > -1 ? T(1) : T(0);
       const T* data = m.F(F_eq_data) + 11 * id;
       const T active = in.eq_active ? T(in.eq_active[(size_t)id * B + env]) : T(1);
+      live = active != T(0);
       const int qa1 = m.I(I_jnt_qposadr)[j1], da1 = m.I(I_jnt_dofadr)[j1], qa2 = m.I(I_jnt_qposadr)[j2], da2 = m.I(I_jnt_dofadr)[j2];
       const T pos1 = d.get(oQpos + qa1), pos2 = d.get(oQpos + qa2) * has2;
       const T ref1 = m.F(F_qpos0)[qa1], ref2 = m.F(F_qpos0)[qa2] * has2;
@@ -167,6 +172,7 @@ __device__ void constraint_source(const ModelView<T>& m, const MjtIn& in, const 
       const int b1 = m.I(I_eq_obj1)[id], b2 = m.I(I_eq_obj2)[id];
       const T* data = m.F(F_eq_data) + 11 * id;
       const T active = in.eq_active ? T(in.eq_active[(size_t)id * B + env]) : T(1);
+      live = active != T(0);
       const V3<T> anchor1(data[0], data[1], data[2]), anchor2(data[3], data[4], data[5]);
       V3<T> x1, x2;
       T R1[9], R2[9];
@@ -237,6 +243,7 @@ __device__ void constraint_source(const ModelView<T>& m, const MjtIn& in, const 
       const int nrows = condim == 1 ? 1 : (elliptic ? condim : 2 * (condim - 1));
       const T dist = d.get(m.D(D_contact_dist) + c) - m.F(F_con_includemargin)[c];
       const bool active = dist < T(0);
+      live = active;
       const T* fri = m.F(F_con_friction) + 5 * c;
       const T t = m.F(F_body_invweight0)[2 * b1] + m.F(F_body_invweight0)[2 * b2];
       T jv[MJT_MAXROWS];
@@ -304,6 +311,7 @@ __device__ void constraint_source(const ModelView<T>& m, const MjtIn& in, const 
     } break;
     default: break;
   }
+  d.set(m.D(D_scr_live) + s, live ? T(1) : T(0));
 }
 
 template <typename T>

@@ -92,7 +92,7 @@ __device__ MJT_CHOL_INLINE void cholesky_rows_fn(T* A, T* di, int n, int lane, u
   }
 }
 
-template <typename T, int DPL, bool COMPACT, int G>
+template <typename T, int DPL, bool COMPACT, int G, bool TILE>
 struct SolveCtx {
   const ModelView<T>& m;
   T* s;  // this env's shared-memory region
@@ -112,6 +112,13 @@ struct SolveCtx {
   // COMPACT: row loops walk the live list (host picks it for models with more than two 32-row chunks); otherwise every
   // row is visited in place with no indirection
   static constexpr bool compact = COMPACT;
+  // TILE (live tile, implies COMPACT): the row vectors are indexed by live slot and the J tile holds only the live sources,
+  // at dynamic offsets jpos[source]; otherwise vectors are indexed by row and J sits at its static compact offsets
+  static constexpr bool tile = TILE;
+  __device__ __forceinline__ int vi(int idx, int r) const { return TILE ? idx : r; }                 // index into D / aref / Jaref / jv / force
+  __device__ __forceinline__ int* jpos() const { return spos() + m.h(H_nsrc); }
+  __device__ __forceinline__ const T* jsrc(int sidx, int r0) const { return Jc() + (TILE ? jpos()[sidx] : row_jadr[r0]); }   // J block of a source
+  __device__ __forceinline__ int nrowcap() const { return TILE ? m.h(H_live_rcap) : nefc; }
   __device__ __forceinline__ int row_at(int idx) const { return compact ? lrow()[idx] : idx; }
 
   __device__ __forceinline__ T* Jc() const { return s + L.oJ; }
@@ -122,12 +129,67 @@ struct SolveCtx {
   __device__ __forceinline__ T* ys() const { return s + L.oYs; }
   __device__ __forceinline__ unsigned* amask() const { return reinterpret_cast<unsigned*>(s + L.oMask); }
   __device__ __forceinline__ int* lrow() const { return reinterpret_cast<int*>(s + L.oLive); }          // live row ids, ascending
-  __device__ __forceinline__ int* spos() const { return reinterpret_cast<int*>(s + L.oLive) + nefc; }   // source -> first live slot, -1 = dead
+  __device__ __forceinline__ int* spos() const { return reinterpret_cast<int*>(s + L.oLive) + (TILE ? m.h(H_live_rcap) : nefc); }   // source -> first live slot, -1 = dead
   __device__ __forceinline__ bool slot_active(int k) const { return (amask()[k / G] >> (k % G)) & 1u; }
 
   // A source whose Jacobian block and reference accelerations are all exactly zero (inactive contact, limit or
   // equality: constraint.py zeroes those rows) can never carry force: J.x - aref stays 0.  Such rows are dropped from
   // every row loop; they keep Jaref = jv = force = 0.
+  // Live tile: slots and J offsets of the sources the constraint kernel flagged live (hidden field scr_live), then their
+  // D / aref / frictionloss rows and Jacobian blocks gathered from the dense Data fields.  Returns the number of live rows,
+  // or -1 when they do not fit the tile (the env is then left to the full-tile launch).
+  __device__ __forceinline__ int build_tile(const EnvBuf<T>& d, T* Dv, T* arefv, T* flossv) const {
+    const int nsrc = m.h(H_nsrc), rcap = m.h(H_live_rcap), jcap = m.h(H_live_jcap);
+    int* lr = lrow();
+    int* sp = spos();
+    int* jp = jpos();
+    int base = 0, jbase = 0;
+    for (int s0 = 0; s0 < nsrc; s0 += G) {
+      const int sidx = s0 + lane;
+      int nr = 0, r0 = 0, nw = 0;
+      bool live = false;
+      if (sidx < nsrc) {
+        r0 = src_row[sidx];
+        nr = src_nrows[sidx];
+        nw = nr * src_nsup[sidx];
+        live = d.get(m.D(D_scr_live) + sidx) != T(0);
+      }
+      const int cnt = live ? nr : 0, jw = live ? nw : 0;
+      int incl = cnt, jincl = jw;
+#pragma unroll
+      for (int o = 1; o < G; o <<= 1) {
+        const int v = __shfl_up_sync(gm, incl, o, G), w = __shfl_up_sync(gm, jincl, o, G);
+        if (lane >= o) { incl += v; jincl += w; }
+      }
+      const int start = base + incl - cnt, jstart = jbase + jincl - jw;
+      if (sidx < nsrc) {
+        sp[sidx] = live ? start : -1;
+        jp[sidx] = jstart;
+        if (start + cnt <= rcap)
+          for (int e = 0; e < cnt; ++e) lr[start + e] = r0 + e;
+      }
+      base += __shfl_sync(gm, incl, G - 1, G);
+      jbase += __shfl_sync(gm, jincl, G - 1, G);
+    }
+    __syncwarp(gm);
+    if (base > rcap || jbase > jcap) return -1;
+    const int oD = m.D(D_efc_D), oA = m.D(D_efc_aref), oF = m.D(D_efc_frictionloss), oJ = m.D(D_efc_J);
+    for (int idx = lane; idx < base; idx += G) {
+      const int r = lr[idx];
+      Dv[idx] = d.get(oD + r);
+      arefv[idx] = d.get(oA + r);
+      if (flossv) flossv[idx] = d.get(oF + r);
+    }
+    T* J = Jc();
+    for (int idx = 0; idx < base; ++idx) {   // one live row at a time, lanes over its support columns
+      const int r = lr[idx], sidx = row_src[r], ns = src_nsup[sidx];
+      const int* col = sup_col + src_cadr[sidx];
+      T* dst = J + jp[sidx] + (r - src_row[sidx]) * ns;
+      for (int k = lane; k < ns; k += G) dst[k] = d.get(oJ + r * nv + col[k]);
+    }
+    __syncwarp(gm);
+    return base;
+  }
   // Returns the number of live rows (warp-uniform).  The context itself stays immutable so that it lives in registers.
   __device__ __forceinline__ int build_live(const T* aref) const {
     if (!compact) return nefc;   // few rows: every row stays in place (slot = row), nothing to build
@@ -143,7 +205,7 @@ struct SolveCtx {
         r0 = src_row[sidx];
         nr = src_nrows[sidx];
         const int nw = nr * src_nsup[sidx];
-        const T* jp = Jc() + row_jadr[r0];
+        const T* jp = jsrc(sidx, r0);
         int nz = 0;   // branch-free so that the loads pipeline
 #pragma unroll 4
         for (int k = 0; k < nw; ++k) nz |= (jp[k] != T(0)) ? 1 : 0;
@@ -216,14 +278,14 @@ struct SolveCtx {
       const int sidx = row_src[r];
       const int ns = src_nsup[sidx];
       const int* col = sup_col + src_cadr[sidx];
-      const T* jr = Jc() + row_jadr[r];
+      const T* jr = TILE ? jsrc(sidx, 0) + (r - src_row[sidx]) * ns : Jc() + row_jadr[r];
       const T* x = xs();
       T acc = 0, acc2 = 0;
       int k = 0;
       for (; k + 1 < ns; k += 2) { acc += jr[k] * x[col[k]]; acc2 += jr[k + 1] * x[col[k + 1]]; }
       if (k < ns) acc += jr[k] * x[col[k]];
       acc += acc2;
-      out[r] = sub ? acc - sub[r] : acc;
+      out[vi(idx, r)] = sub ? acc - sub[vi(idx, r)] : acc;
     }
     __syncwarp(gm);
   }
@@ -238,10 +300,11 @@ struct SolveCtx {
       if (i < nv) {
         for (int q = dof_sadr[i], qe = dof_sadr[i + 1]; q < qe; ++q) {
           const int ent = dof_sent[q], sidx = ent & 0xffff, pos = ent >> 16;
-          if (compact && spos()[sidx] < 0) continue;
+          const int cs = compact ? spos()[sidx] : 0;
+          if (cs < 0) continue;
           const int r0 = src_row[sidx], nr = src_nrows[sidx], ns = src_nsup[sidx];
-          const T* jp = Jc() + row_jadr[r0] + pos;
-          const T* fp = f + r0;
+          const T* jp = jsrc(sidx, r0) + pos;
+          const T* fp = f + (TILE ? cs : r0);
           for (int e = 0; e < nr; ++e) acc += jp[e * ns] * fp[e];
         }
       }
@@ -338,9 +401,10 @@ struct SolveCtx {
         const int r0 = src_row[sidx], nr = src_nrows[sidx];
         const int cs = compact ? spos()[sidx] : r0;
         if (cs < 0) continue;
-        const T* jp = Jc() + row_jadr[r0];
+        const T* jp = jsrc(sidx, r0);
+        const T* Ds = D + (TILE ? cs : r0);
         for (int e = 0; e < nr; ++e)
-          if (slot_active(cs + e)) acc += D[r0 + e] * jp[e] * jp[e];
+          if (slot_active(cs + e)) acc += Ds[e] * jp[e] * jp[e];
       }
       H[tri(i) + i] += acc;
     }
@@ -358,7 +422,8 @@ struct SolveCtx {
       const int ns = src_nsup[sidx];
       const int* col = sup_col + src_cadr[sidx];
       const int npair = (ns * (ns + 1)) >> 1;
-      const T* j0 = Jc() + row_jadr[r0];   // rows of one source are stored back to back, ns entries each
+      const T* j0 = jsrc(sidx, r0);   // rows of one source are stored back to back, ns entries each
+      const T* Ds = D + (TILE ? cs : r0);
       for (int p = lane; p < npair; p += G) {
         const int ab = tri_ab[p], a = ab & 0xffff, b = ab >> 16;
         T acc = 0;
@@ -368,13 +433,13 @@ struct SolveCtx {
             const int e = __ffs(mk) - 1;
             mk &= mk - 1;
             const T* jr = j0 + e * ns;
-            acc += D[r0 + e] * jr[a] * jr[b];
+            acc += Ds[e] * jr[a] * jr[b];
           }
         } else {
           for (int e = 0; e < nr; ++e) {
             if (!slot_active(cs + e)) continue;
             const T* jr = j0 + e * ns;
-            acc += D[r0 + e] * jr[a] * jr[b];
+            acc += Ds[e] * jr[a] * jr[b];
           }
         }
         H[tri(col[a]) + col[b]] += acc;  // support columns are sorted ascending: col[a] >= col[b]
@@ -384,9 +449,9 @@ struct SolveCtx {
   }
 };
 
-template <typename T, int DPL, bool COMPACT, int G>
+template <typename T, int DPL, bool COMPACT, int G, bool TILE>
 __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T>& d, size_t B, int env,
-                          const SolveCtx<T, DPL, COMPACT, G>& c, const Vec<T, DPL>& qfrc_smooth, const Vec<T, DPL>& qacc_smooth, int mode) {
+                          const SolveCtx<T, DPL, COMPACT, G, TILE>& c, const Vec<T, DPL>& qfrc_smooth, const Vec<T, DPL>& qacc_smooth, int mode) {
   typedef Vec<T, DPL> V;
   const int lane = c.lane;
   const unsigned gm = c.gm;
@@ -448,9 +513,14 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
 
     V Ma, grad, Mgrad, search;
     T gauss = 0, cost = t_inf<T>(), prev_cost = 0;
-    if (c.compact)   // dead rows are never visited again: give them their final zeros now
+    if (c.compact && !TILE)   // dead rows are never visited again: give them their final zeros now
       for (int r = lane; r < nefc; r += G) { Jaref[r] = T(0); jv[r] = T(0); force[r] = T(0); }
-    const int nlive = c.build_live(aref);   // rows that can carry force this step; the rest are exactly-zero rows
+    // rows that can carry force this step; the rest are exactly-zero rows
+    const int nlive = TILE ? c.build_tile(d, D, aref, m.h(H_nf) > 0 ? floss : nullptr) : c.build_live(aref);
+    if (TILE) {
+      if (lane == 0) d.set(m.D(D_scr_ovf), nlive < 0 ? T(1) : T(0));
+      if (nlive < 0) return;   // does not fit the live tile: the full-tile launch that follows solves this env
+    }
 
     // reference _update_constraint :320-357 (cost only, or cost + forces + J^T f)
     auto update_constraint = [&](bool with_force) {
@@ -460,12 +530,12 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
         bool act = false;
         T fo = 0;
         if (idx < nlive) {
-          const int r = c.row_at(idx);
-          const T ja = Jaref[r], dr = D[r];
+          const int r = c.row_at(idx), q = c.vi(idx, r);
+          const T ja = Jaref[q], dr = D[q];
           act = (ja < T(0)) || (r < ne_nf);
           T ff = 0;
           if (use_floss) {
-            const T fl = floss[r];
+            const T fl = floss[q];
             if (fl > T(0)) {
               const T rr = T(1) / (dr + (dr == T(0) ? T(MJT_MINVAL) : T(0)));
               const bool lin_neg = ja <= -rr * fl, lin_pos = ja >= rr * fl;
@@ -475,7 +545,7 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
           }
           fo = (act ? dr * -ja : T(0)) + ff;
           if (act) cpart += T(0.5) * dr * ja * ja;
-          if (with_force) force[r] = fo;
+          if (with_force) force[q] = fo;
         }
         const unsigned am = (__ballot_sync(gm, act) >> (threadIdx.x & 31 & ~(G - 1))) & (G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u));
         if (with_force && lane == 0) c.amask()[ch] = am;
@@ -531,11 +601,11 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
 #pragma unroll
         for (int a = 0; a < 3; ++a) q[a][0] = q[a][1] = q[a][2] = T(0);
         for (int idx = lane; idx < nlive; idx += G) {
-          const int r = c.row_at(idx);
-          const T ja = Jaref[r], jr = jv[r], dr = D[r];
+          const int r = c.row_at(idx), vq = c.vi(idx, r);
+          const T ja = Jaref[vq], jr = jv[vq], dr = D[vq];
           const T c0 = T(0.5) * ja * ja * dr, c1 = jr * ja * dr, c2 = T(0.5) * jr * jr * dr;
           T fl = 0, rf = 0;
-          const bool hasf = use_floss && (fl = floss[r]) > T(0);
+          const bool hasf = use_floss && (fl = floss[vq]) > T(0);
           if (hasf) rf = fl / (dr + (dr == T(0) ? T(MJT_MINVAL) : T(0)));
 #pragma unroll
           for (int a = 0; a < 3; ++a) {
@@ -601,7 +671,7 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
       if (improved) {
         qacc = axpy(qacc, alpha, search);
         Ma = axpy(Ma, alpha, mv);
-        for (int idx = lane; idx < nlive; idx += G) { const int r = c.row_at(idx); Jaref[r] += jv[r] * alpha; }
+        for (int idx = lane; idx < nlive; idx += G) { const int q = c.vi(idx, c.row_at(idx)); Jaref[q] += jv[q] * alpha; }
         __syncwarp(gm);
       }
     };
@@ -630,11 +700,11 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
       // evaluate the smooth cost on the parked values
       T cpart = 0;
       for (int idx = lane; idx < nlive; idx += G) {
-        const int r = c.row_at(idx);
-        const T ja = jv[r], dr = D[r];
+        const int r = c.row_at(idx), q = c.vi(idx, r);
+        const T ja = jv[q], dr = D[q];
         bool act = (ja < T(0)) || (r < ne_nf);
         if (use_floss) {
-          const T fl = floss[r];
+          const T fl = floss[q];
           if (fl > T(0)) {
             const T rr = T(1) / (dr + (dr == T(0) ? T(MJT_MINVAL) : T(0)));
             if (ja <= -rr * fl) { act = false; cpart += -T(0.5) * rr * fl * fl - fl * ja; }
@@ -649,7 +719,8 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
         qacc = warm;
         Ma = Ma_w;
       } else {
-        for (int r = lane; r < nefc; r += G) keep[r] = jv[r];
+        if (TILE) { for (int idx = lane; idx < nlive; idx += G) keep[idx] = jv[idx]; }
+        else { for (int r = lane; r < nefc; r += G) keep[r] = jv[r]; }
       }
       __syncwarp(gm);
     }
@@ -693,7 +764,13 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
       }
     }
     storev(m.D(D_qacc_warmstart), qacc);
-    for (int r = lane; r < nefc; r += G) d.set(m.D(D_efc_force) + r, force[r]);
+    if (TILE) {   // dead rows carry no force; live rows scatter from their slots
+      for (int r = lane; r < nefc; r += G) d.set(m.D(D_efc_force) + r, T(0));
+      __syncwarp(gm);
+      for (int idx = lane; idx < nlive; idx += G) d.set(m.D(D_efc_force) + c.lrow()[idx], force[idx]);
+    } else {
+      for (int r = lane; r < nefc; r += G) d.set(m.D(D_efc_force) + r, force[r]);
+    }
   }
   storev(m.D(D_qacc), qacc);
   storev(m.D(D_qfrc_constraint), qfrc_con);
@@ -831,11 +908,21 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
   if (lane == 0) d.set(m.D(D_time), d.get(m.D(D_time)) + dt);
 }
 
-template <typename T, int DPL, bool COMPACT, int G>
+template <typename T, int DPL, bool COMPACT, int G, bool TILE>
 __global__ void __launch_bounds__((sizeof(T) == 4 ? 512 : MJT_SOLVE_F64_THREADS), (sizeof(T) == 4 ? 2 : MJT_SOLVE_F64_MINB)) k_solve(const int* __restrict__ gfull, const int* __restrict__ gblob, int blob_words, MjtIn in,
-                                               T* __restrict__ out, int B, int mode) {
+                                               T* __restrict__ out, int B, int mode, int only_flagged) {
   extern __shared__ __align__(16) int smem_blob[];
   __shared__ uint64_t bar;
+  if (only_flagged) {
+    // second pass after a live-tile launch: only envs whose tile overflowed (scr_ovf != 0) are solved here; a CTA without
+    // any leaves before it stages anything
+    const int e_cta = blockDim.x / G, e0 = blockIdx.x * e_cta;
+    const int o_ovf = gblob[MJT_OFF_D + D_scr_ovf];
+    bool mine = false;
+    for (int e = threadIdx.x; e < e_cta; e += blockDim.x)
+      if (e0 + e < B) mine = mine || (out[(size_t)o_ovf * (size_t)B + e0 + e] != T(0));
+    if (!__syncthreads_or(mine ? 1 : 0)) return;
+  }
   stage_blob(smem_blob, &bar, gblob, blob_words);
   const ModelView<T> m = make_view<T>(smem_blob);
   const int E = blockDim.x / G;                                   // envs per CTA, G lanes each
@@ -843,13 +930,14 @@ __global__ void __launch_bounds__((sizeof(T) == 4 ? 512 : MJT_SOLVE_F64_THREADS)
   const unsigned gm = group_mask<G>();
   const int env0 = blockIdx.x * E;
   const int nv = m.h(H_nv), nefc = m.h(H_nefc);
-  const SolveLayout Lo = solve_layout(nv, nefc, m.h(H_jc_words), m.h(H_nf), m.h(H_nsrc), (int)sizeof(T), COMPACT, G);
+  const SolveLayout Lo = solve_layout(nv, nefc, m.h(H_jc_words), m.h(H_nf), m.h(H_nsrc), (int)sizeof(T), COMPACT, G,
+                                      TILE ? m.h(H_live_rcap) : 0, TILE ? m.h(H_live_jcap) : 0);
   T* region = reinterpret_cast<T*>(smem_blob + ((blob_words + 3) & ~3));
   const size_t Bs = (size_t)B;
 
   // ---- cooperative, env-contiguous loads: thread t serves env t % E, so E consecutive envs share every word's cache line
   const int ce = threadIdx.x % E, ck0 = threadIdx.x / E, cks = blockDim.x / E;
-  const bool cvalid = env0 + ce < B;
+  const bool cvalid = env0 + ce < B && (!only_flagged || out[(size_t)m.D(D_scr_ovf) * Bs + env0 + ce] != T(0));
   T* const crg = region + (size_t)ce * Lo.words;
   T* const cout = out + env0 + ce;
   const int* tri_ab = m.I(I_tri_ab);   // packed lower index p -> (a, b): dense word a*nv+b, mirrored word b*nv+a
@@ -860,7 +948,7 @@ __global__ void __launch_bounds__((sizeof(T) == 4 ? 512 : MJT_SOLVE_F64_THREADS)
         const int ab = tri_ab[p];
         cp_async_word(crg + Lo.oM + p, cout + (size_t)(oM + (ab & 0xffff) * nv + (ab >> 16)) * Bs);
       }
-    if (nefc) {
+    if (nefc && !TILE) {   // the live tile gathers its rows per env once it knows which sources are live
       const int oJ = m.D(D_efc_J), jcw = m.h(H_jc_words);
       const int* jsrc = m.I(I_jc_src);   // compact J entry -> dense word row*nv+col
       if (cvalid)
@@ -879,9 +967,9 @@ __global__ void __launch_bounds__((sizeof(T) == 4 ? 512 : MJT_SOLVE_F64_THREADS)
   __syncthreads();
 
   const int env = env0 + warp;
-  const bool valid = env < B;
+  const bool valid = env < B && (!only_flagged || out[(size_t)m.D(D_scr_ovf) * Bs + (env < B ? env : 0)] != T(0));
   EnvBuf<T> d{out + (valid ? env : 0), Bs};
-  SolveCtx<T, DPL, COMPACT, G> c{m, region + (size_t)warp * Lo.words, Lo, nv, nefc, lane,
+  SolveCtx<T, DPL, COMPACT, G, TILE> c{m, region + (size_t)warp * Lo.words, Lo, nv, nefc, lane,
                      m.I(I_row_src), m.I(I_row_jadr), m.I(I_src_nsup), m.I(I_src_cadr), m.I(I_src_row), m.I(I_src_nrows), m.I(I_sup_col), m.I(I_tri_ab), m.I(I_dof_sadr), m.I(I_dof_sent), group_mask<G>()};
   Vec<T, DPL> qfrc_smooth = c.zero(), qacc_smooth = c.zero();
   if (valid) {
@@ -910,5 +998,5 @@ __global__ void __launch_bounds__((sizeof(T) == 4 ? 512 : MJT_SOLVE_F64_THREADS)
   }
   __syncthreads();
   if (!valid) return;
-  solve_env<T, DPL, COMPACT, G>(m, in, d, Bs, env, c, qfrc_smooth, qacc_smooth, mode);
+  solve_env<T, DPL, COMPACT, G, TILE>(m, in, d, Bs, env, c, qfrc_smooth, qacc_smooth, mode);
 }

@@ -64,6 +64,11 @@ struct mjtModel {
   size_t solve_smem;
   size_t solve_blob_bytes, solve_region_bytes;  // smem = blob + envs * region
   int solve_lanes;                              // lanes per env in k_solve (32, or 16 for nv <= 16)
+  // live-tile launch (models with many, mostly inactive rows): a first k_solve pass whose tile only has room for rcap
+  // live rows / jcap J words per env; envs that overflow are flagged and solved by a second pass with the full tile
+  bool tile;
+  int tile_envs;
+  size_t tile_smem, tile_region_bytes;
   int hv(int k) const { return h[k]; }
 };
 
@@ -73,7 +78,7 @@ static const char* kFieldNames[] = {
     "geom_xpos", "geom_xmat", "site_xpos", "site_xmat", "subtree_com", "cinert", "crb", "cdof", "cdof_dot", "cvel", "qM", "qLD",
     "ten_length", "ten_J", "ten_velocity", "actuator_length", "actuator_moment", "actuator_velocity", "actuator_force", "qfrc_bias",
     "qfrc_passive", "qfrc_gravcomp", "qfrc_actuator", "qfrc_smooth", "qacc_smooth", "qfrc_constraint", "contact_dist", "contact_pos",
-    "contact_frame", "efc_J", "efc_D", "efc_aref", "efc_frictionloss", "efc_force", "sensordata", "scr_cacc", "scr_cfrc"
+    "contact_frame", "efc_J", "efc_D", "efc_aref", "efc_frictionloss", "efc_force", "sensordata", "scr_cacc", "scr_cfrc", "scr_live", "scr_ovf"
 
 };
 static_assert(sizeof(kFieldNames) / sizeof(kFieldNames[0]) == NUM_D, "field name table out of sync with mjt_layout.h");
@@ -108,29 +113,35 @@ extern "C" int mjt_model_create(const void* blob_host, size_t nbytes, int device
     if (atoi(fg) == 16 && nv <= 32) G = 16;
   }
   m->solve_lanes = G;
-  const size_t region = (size_t)solve_layout(nv, nefc, w[H_jc_words], w[H_nf], w[H_nsrc], (int)tsz, nefc > MJT_COMPACT_MIN_NEFC, G).words * tsz;
+  const bool compact = nefc > MJT_COMPACT_MIN_NEFC;
+  const size_t region = (size_t)solve_layout(nv, nefc, w[H_jc_words], w[H_nf], w[H_nsrc], (int)tsz, compact, G).words * tsz;
   const size_t blob_b = ((size_t)m->blob_words + 3) / 4 * 16;
   const size_t sblob_b = ((size_t)m->solve_words + 3) / 4 * 16;
   const size_t sm_total = (size_t)prop.sharedMemPerMultiprocessor;
-  int best_e = 0;
-  size_t best_envs = 0;
   // f64 kernel: MJT_SOLVE_F64_THREADS x MJT_SOLVE_F64_MINB threads fit the register file; f32 kernel: 2 x 512
   const int tmax = m->f64 ? MJT_SOLVE_F64_THREADS : 512;
   const size_t tcap = (size_t)tmax * (m->f64 ? MJT_SOLVE_F64_MINB : 2);   // resident threads per SM
   const int estep = 32 / G, emax = tmax / G;
-  for (int e = emax; e >= estep; e -= estep) {   // most resident envs per SM wins; ties go to the larger CTA
-    const size_t need = sblob_b + region * e + 1024;
-    if (need > (size_t)m->max_smem) continue;
-    size_t ctas = sm_total / need;
-    if (ctas > 32) ctas = 32;
-    size_t envs = ctas * e;
-    if (envs * G > tcap) envs = tcap / G;
-    if (envs > best_envs) { best_envs = envs; best_e = e; }
-  }
-  if (const char* force = getenv("MJT_SOLVE_E")) {   // tuning knob: force envs per CTA
-    const int e = atoi(force);
-    if (e >= estep && e <= emax && e % estep == 0 && sblob_b + region * e + 1024 <= (size_t)m->max_smem) best_e = e;
-  }
+  const size_t max_smem = (size_t)m->max_smem;
+  auto pick_envs = [&](size_t reg, const char* knob) {   // most resident envs per SM wins; ties go to the larger CTA
+    int best_e = 0;
+    size_t best_envs = 0;
+    for (int e = emax; e >= estep; e -= estep) {
+      const size_t need = sblob_b + reg * e + 1024;
+      if (need > max_smem) continue;
+      size_t ctas = sm_total / need;
+      if (ctas > 32) ctas = 32;
+      size_t envs = ctas * e;
+      if (envs * G > tcap) envs = tcap / G;
+      if (envs > best_envs) { best_envs = envs; best_e = e; }
+    }
+    if (const char* force = getenv(knob)) {   // tuning knob: force envs per CTA
+      const int e = atoi(force);
+      if (e >= estep && e <= emax && e % estep == 0 && sblob_b + reg * e + 1024 <= max_smem) best_e = e;
+    }
+    return best_e;
+  };
+  const int best_e = pick_envs(region, "MJT_SOLVE_E");
   if (best_e == 0) {
     delete m;
     return fail("mjt_model_create: model too large for the shared-memory solver tile (nv * nefc)");
@@ -139,6 +150,20 @@ extern "C" int mjt_model_create(const void* blob_host, size_t nbytes, int device
   m->solve_smem = sblob_b + region * best_e;
   m->solve_blob_bytes = sblob_b;
   m->solve_region_bytes = region;
+  m->tile = false;
+  m->tile_envs = 0;
+  m->tile_smem = m->tile_region_bytes = 0;
+  const char* tile_off = getenv("MJT_LIVE_TILE");   // A/B knob: MJT_LIVE_TILE=0 keeps the single full-tile launch
+  if (compact && w[H_live_rcap] > 0 && !(tile_off && atoi(tile_off) == 0)) {
+    const size_t treg = (size_t)solve_layout(nv, nefc, w[H_jc_words], w[H_nf], w[H_nsrc], (int)tsz, true, G, w[H_live_rcap], w[H_live_jcap]).words * tsz;
+    const int te = pick_envs(treg, "MJT_TILE_E");
+    if (te > 0 && treg < region) {
+      m->tile = true;
+      m->tile_envs = te;
+      m->tile_region_bytes = treg;
+      m->tile_smem = sblob_b + treg * te;
+    }
+  }
   if (blob_b + 64 > (size_t)m->max_smem) {
     delete m;
     return fail("mjt_model_create: model blob exceeds shared memory");
@@ -178,13 +203,13 @@ static MjtIn to_in(const mjtStateIn* s) {
   return in;
 }
 
-static cudaError_t launch_solve(int lanes, int dpl, bool compact, int grid, int threads, size_t smem, size_t smem_attr, cudaStream_t st,
-                                const int* blob, const int* sblob, int solve_words, const MjtIn& in, float* out, int B, int mode) {
-  return mjt_launch_solve_f32(lanes, dpl, compact, grid, threads, smem, smem_attr, st, blob, sblob, solve_words, in, out, B, mode);
+static cudaError_t launch_solve(int lanes, int dpl, int compact, int only_flagged, int grid, int threads, size_t smem, size_t smem_attr,
+                                cudaStream_t st, const int* blob, const int* sblob, int solve_words, const MjtIn& in, float* out, int B, int mode) {
+  return mjt_launch_solve_f32(lanes, dpl, compact, 0, 0, only_flagged, grid, threads, smem, smem_attr, st, blob, sblob, solve_words, in, out, B, mode);
 }
-static cudaError_t launch_solve(int lanes, int dpl, bool compact, int grid, int threads, size_t smem, size_t smem_attr, cudaStream_t st,
-                                const int* blob, const int* sblob, int solve_words, const MjtIn& in, double* out, int B, int mode) {
-  return mjt_launch_solve_f64(lanes, dpl, compact, grid, threads, smem, smem_attr, st, blob, sblob, solve_words, in, out, B, mode);
+static cudaError_t launch_solve(int lanes, int dpl, int compact, int only_flagged, int grid, int threads, size_t smem, size_t smem_attr,
+                                cudaStream_t st, const int* blob, const int* sblob, int solve_words, const MjtIn& in, double* out, int B, int mode) {
+  return mjt_launch_solve_f64(lanes, dpl, compact, 0, 0, only_flagged, grid, threads, smem, smem_attr, st, blob, sblob, solve_words, in, out, B, mode);
 }
 
 template <typename T>
@@ -241,14 +266,24 @@ static int run_forward(const mjtModel* m, const MjtIn& in, T* out, int B, int mo
     const size_t smem = m->solve_blob_bytes + m->solve_region_bytes * E;
     const int gs = (B + E - 1) / E;
     // COMPACT instantiation (live-row list) for models with more than two 32-row chunks of constraint rows
-    const bool compact = m->hv(H_nefc) > MJT_COMPACT_MIN_NEFC;
+    const int compact = m->hv(H_nefc) > MJT_COMPACT_MIN_NEFC ? 1 : 0;
     const int lanes = m->solve_lanes;
     if (m->hv(H_nv) > 2 * lanes) return fail("mjt: nv > 64 not supported by the dense solver kernel");
     const int dpl = m->hv(H_nv) <= lanes ? 1 : 2;
     cudaError_t se;
-    {
+    if (m->tile) {   // live-tile pass over every env, then the full tile for the envs it flagged
+      const int TE = m->tile_envs;
+      const size_t tsmem = m->solve_blob_bytes + m->tile_region_bytes * TE;
       ProfScope prof__("k_solve", st);
-      se = launch_solve(lanes, dpl, compact, gs, lanes * E, smem, m->solve_smem, st, m->d_blob, m->d_blob + m->blob_words, m->solve_words,
+      se = launch_solve(lanes, dpl, 2, 0, (B + TE - 1) / TE, lanes * TE, tsmem, m->tile_smem, st, m->d_blob, m->d_blob + m->blob_words,
+                        m->solve_words, in, out, B, mode);
+      ++n;
+      if (se == cudaSuccess)
+        se = launch_solve(lanes, dpl, 1, 1, gs, lanes * E, smem, m->solve_smem, st, m->d_blob, m->d_blob + m->blob_words, m->solve_words,
+                          in, out, B, mode);
+    } else {
+      ProfScope prof__("k_solve", st);
+      se = launch_solve(lanes, dpl, compact, 0, gs, lanes * E, smem, m->solve_smem, st, m->d_blob, m->d_blob + m->blob_words, m->solve_words,
                         in, out, B, mode);
     }
     if (se != cudaSuccess) return fail(std::string("k_solve launch: ") + cudaGetErrorString(se));
@@ -333,7 +368,7 @@ extern "C" int mjt_forward(const mjtModel* m, const mjtStateIn* in, void* out, i
 }
 
 extern "C" int mjt_step_launches(const mjtModel* m) {
-  int per_forward = 2;  // k_smooth + k_solve
+  int per_forward = m->tile ? 3 : 2;  // k_smooth + k_solve (live-tile models: two k_solve passes)
   if (m->hv(H_npair_cand) > 0) ++per_forward;
   if (m->hv(H_nsrc) > 0) ++per_forward;
   if (m->hv(H_nsensordata) > 0) ++per_forward;
@@ -373,7 +408,8 @@ extern "C" int mjt_profile_end(char* buf, size_t nbuf) {
 }
 
 extern "C" int mjt_solve_config(const mjtModel* m, int* envs_per_cta, int* smem_bytes) {
-  if (envs_per_cta) *envs_per_cta = m->solve_envs;
-  if (smem_bytes) *smem_bytes = (int)m->solve_smem;
+  // the launch that processes every env: the live-tile pass when the model has one
+  if (envs_per_cta) *envs_per_cta = m->tile ? m->tile_envs : m->solve_envs;
+  if (smem_bytes) *smem_bytes = (int)(m->tile ? m->tile_smem : m->solve_smem);
   return 0;
 }

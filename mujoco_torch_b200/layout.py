@@ -21,7 +21,7 @@ ncon nefc ne nf nl npair_cand nsrc
 disableflags solver cone integrator iterations ls_iterations
 data_words has_gravcomp has_fluid nv_pad nlim_sh nlim_ball nfric_dof nfric_ten nlim_ten
 ne_connect ne_weld ne_joint maskwords nsens_pos nsens_vel nsens_acc
-nconvex nrfgeom jc_words solve_blob_words
+nconvex nrfgeom jc_words solve_blob_words live_rcap live_jcap
 """.split()
 
 # ---- int arrays ---------------------------------------------------------------------------
@@ -90,6 +90,9 @@ D_FIELDS = [
     ("sensordata", "(nsensordata,)"),
     # scratch used between kernels (not exposed)
     ("scr_cacc", "(nbody,6)"), ("scr_cfrc", "(nbody,6)"),
+    # per row source: 1 when the constraint kernel instantiated non-zero rows for it this step; per env: 1 when the live
+    # tile of the solver overflowed and the env has to be solved by the full-tile kernel
+    ("scr_live", "(nsrc,)"), ("scr_ovf", "()"),
 ]
 
 # kernel dispatch "source" types for the constraint kernel
@@ -99,7 +102,7 @@ PAIR_FNS = "PLANE_SPHERE PLANE_CAPSULE SPHERE_SPHERE SPHERE_CAPSULE CAPSULE_CAPS
 PAIR_NCON = dict(PLANE_SPHERE=1, PLANE_CAPSULE=2, SPHERE_SPHERE=1, SPHERE_CAPSULE=1, CAPSULE_CAPSULE=1, PLANE_CONVEX=4,
                  SPHERE_CONVEX=1, CAPSULE_CONVEX=2, CONVEX_CONVEX=4)
 
-HIDDEN_FIELDS = {"scr_cacc", "scr_cfrc"}
+HIDDEN_FIELDS = {"scr_cacc", "scr_cfrc", "scr_live", "scr_ovf"}
 MAGIC = 0x4D4A5431  # "MJT1"
 
 

@@ -24,6 +24,11 @@ _FN_TABLE = {
     (_G.CAPSULE, _G.BOX): "CAPSULE_CONVEX", (_G.CAPSULE, _G.MESH): "CAPSULE_CONVEX", (_G.BOX, _G.BOX): "CONVEX_CONVEX",
     (_G.BOX, _G.MESH): "CONVEX_CONVEX", (_G.MESH, _G.MESH): "CONVEX_CONVEX",
 }
+# Solver live tile: room for LIVE_FRAC of the constraint rows, at least LIVE_MIN_ROWS.  Measured on the bench states the live
+# share is far below that (box stack: <= 60 of 336 rows, Ant: <= 36 of 284); envs that need more take the full-tile pass.
+LIVE_FRAC = 0.25
+LIVE_MIN_ROWS = 64
+
 _SUPPORTED_SENSORS = {SensorType.TOUCH, SensorType.ACCELEROMETER, SensorType.VELOCIMETER, SensorType.GYRO, SensorType.MAGNETOMETER,
                       SensorType.RANGEFINDER, SensorType.JOINTPOS, SensorType.JOINTVEL, SensorType.ACTUATORPOS,
                       SensorType.ACTUATORVEL, SensorType.ACTUATORFRC, SensorType.JOINTACTFRC, SensorType.TENDONPOS,
@@ -394,6 +399,16 @@ class Model:
         dof_sent = [e for x in per_dof for e in x]
         self.sup = dict(src_cadr=src_cadr, src_nsup=src_nsup, src_nrows=src_nrows, cols=cols, row_src=row_src, row_jadr=row_jadr,
                         jc_words=jadr, dof_sadr=dof_sadr, dof_sent=dof_sent)
+        # Live tile of the solver (models with many, mostly inactive rows): room for LIVE_FRAC of the rows and of the compact
+        # J, never less than 64 rows.  Envs that need more fall back to the full tile (csrc/k_solve.cuh).
+        nefc = len(row_src)
+        if nefc > 64:
+            rcap = min(nefc, max(LIVE_MIN_ROWS, -(-int(nefc * LIVE_FRAC) // 16) * 16))
+            maxsup = max(src_nsup) if src_nsup else 1
+            jcap = min(jadr, max(rcap * maxsup * 3 // 4, LIVE_MIN_ROWS))
+            self.live_caps = (rcap, jcap) if rcap * 4 <= nefc * 3 else (0, 0)
+        else:
+            self.live_caps = (0, 0)
 
     # ---- blob
     def _pack(self):
@@ -511,7 +526,8 @@ class Model:
 
         # Data field table
         sizes = dict(nq=self.nq, nv=self.nv, nu=self.nu, na=self.na, nbody=self.nbody, njnt=self.njnt, ngeom=self.ngeom,
-                     nsite=self.nsite, ntendon=self.ntendon, ncon=self.ncon, nefc=self.nefc, nsensordata=self.nsensordata)
+                     nsite=self.nsite, ntendon=self.ntendon, ncon=self.ncon, nefc=self.nefc, nsensordata=self.nsensordata,
+                     nsrc=len(self.src))
         self.field_shape, self.field_off, off = {}, {}, 0
         for name, expr in L.D_FIELDS:
             shp = tuple(int(s) for s in eval(expr, {}, sizes))
@@ -531,7 +547,8 @@ class Model:
                  has_fluid=int(self.opt.has_fluid_params), nv_pad=self.nv | 1, nlim_sh=cnt("LIM_SH"), nlim_ball=cnt("LIM_BALL"),
                  nfric_dof=cnt("FRIC_DOF"), nfric_ten=cnt("FRIC_TEN"), nlim_ten=cnt("LIM_TEN"), ne_connect=cnt("EQ_CONNECT"),
                  ne_weld=cnt("EQ_WELD"), ne_joint=cnt("EQ_JOINT"), maskwords=self.maskwords, nsens_pos=int((st == 1).sum()),
-                 nsens_vel=int((st == 2).sum()), nsens_acc=int((st == 3).sum()), nconvex=len(cv), nrfgeom=len(rf), jc_words=self.sup["jc_words"])
+                 nsens_vel=int((st == 2).sum()), nsens_acc=int((st == 3).sum()), nconvex=len(cv), nrfgeom=len(rf), jc_words=self.sup["jc_words"],
+                 live_rcap=self.live_caps[0], live_jcap=self.live_caps[1])
         nH, nI, nF, nD = len(L.H_SCALARS), len(L.I_ARRAYS), len(L.F_ARRAYS), len(L.D_FIELDS)
         def assemble(keep=None, extra=None):
             """One blob; with ``keep`` only the named arrays carry data (the others get length 0)."""

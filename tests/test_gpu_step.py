@@ -285,3 +285,34 @@ def test_stack_rk4_step():
         best = torch.minimum(best, e)
     frac = float((best < 1e-8).float().mean())
     assert frac >= 0.75, f"only {frac:.2f} of envs follow an oracle trajectory; worst {float(best.max()):.2e}"
+
+
+@pytest.mark.parametrize("name,state,opt", [("stack", "pile", {"integrator": 0}), ("stack", "stack", {}), ("ant", "seed", {}),
+                                            ("ant_zoo", "seed", {"cone": 1, "solver": 1})])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+def test_live_tile_matches_full_tile(name, state, opt, dtype, monkeypatch):
+    """Models with many, mostly inactive rows run k_solve on a live tile (room for a fraction of the rows) and hand envs that
+    overflow it to a second, full-tile pass.  Both passes walk the same live rows in the same order, so three launches must
+    agree to the last bit: default caps, caps so small that almost every env overflows, and the live tile switched off."""
+    import mujoco_torch_b200.model as model_mod
+
+    mj = util.load_model(name, **opt)
+    B = 96
+    qpos, qvel, ctrl = {"pile": util.pile_state, "stack": util.stack_state,
+                        "seed": lambda m, b: util.seeded_state(m, b, drop=0.5 if name == "ant_zoo" else 0.0)}[state](mj, B)
+    outs = {}
+    for tag in ("default", "tiny", "off"):
+        with monkeypatch.context() as mp:
+            if tag == "tiny":
+                mp.setattr(model_mod, "LIVE_FRAC", 0.01)
+                mp.setattr(model_mod, "LIVE_MIN_ROWS", 16)
+            if tag == "off":
+                mp.setenv("MJT_LIVE_TILE", "0")
+            mx, d = util.run_cuda(mj, qpos, qvel, ctrl, dtype, nsteps=3)
+        if tag == "default":
+            assert mx.live_caps[0] > 0, "model was expected to use the live tile"
+        outs[tag] = {k: getattr(d, k).cpu().clone() for k in ("qpos", "qvel", "qacc", "qacc_warmstart", "efc_force", "qfrc_constraint", "qLD")}
+    assert torch.isfinite(outs["off"]["qpos"]).all()
+    for tag in ("default", "tiny"):
+        for k, v in outs["off"].items():
+            assert torch.equal(outs[tag][k], v), f"{name} {tag}: {k} differs from the full-tile launch by {float((outs[tag][k] - v).abs().max()):.3e}"
