@@ -43,6 +43,28 @@ def algorithmic_bytes(mj, tsize):
     return (rd + wr) * tsize
 
 
+def algorithmic_flops(mj, mx):
+    """Algorithmic flops per env-step from the model dims, SURVEY.md 8(d) formulae (FMA = 2 flops; the symmetric count of
+    J^T D J, so that exploiting symmetry / sparsity is not rewarded twice).  Solver work is data dependent: the solver body
+    is counted ONCE (exact for Humanoid, iterations = 1; a lower bound for the models that iterate to convergence) and the
+    line search at its configured maximum of ls_iterations."""
+    nv, nbody, ncon, nefc = mj.nv, mj.nbody, mx.ncon, mx.nefc
+    integ, newton = int(mj.opt.integrator), int(mj.opt.solver) == 2
+    ls_it = int(mj.opt.ls_iterations)
+    chol, tri = nv ** 3 / 3.0, 2.0 * nv * nv
+    smooth = 700.0 * nbody + 6.0 * nv * nv + chol + tri            # kinematics..rne, make_m (tree-sparse half), factor_m, qacc_smooth
+    constraint = ncon * 2 * nv * 18 + 18 * nv * ncon + 4 * nefc * nv   # contact Jacobians, frame.Jdiff, rows + aref
+    solve = 0.0
+    if nefc:
+        ctx = 4 * nefc * nv + 2 * nv * nv                            # J.x, J^T f, M.x
+        grad = (nv * (nv + 1) * nefc + chol + tri) if newton else tri
+        linesearch = 2 * nefc * nv + 2 * nv * nv + (2 + 3 * ls_it) * 10 * nefc
+        solve = 3 * ctx + 2 * grad + linesearch + ctx               # warm/smooth contexts, 2 gradients, 1 line search, post-LS update
+    refactor = chol + tri if integ == 3 or (integ == 0 and not (int(mj.opt.disableflags) & (1 << 15)) and float(np.abs(mj.dof_damping).sum()) > 0) else 0.0
+    fwd = smooth + constraint + solve
+    return (4 * fwd if integ == 1 else fwd + refactor)
+
+
 def load_model(name, args):
     from mujoco_torch_b200.mjmodel import MjModelLite
 
@@ -249,6 +271,16 @@ def main():
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
     finite = bool(torch.isfinite(d.qpos).all())
+    # live-tile models: share of envs the last step handed to the full-tile pass (hidden per-env flag of the output buffer)
+    tile_overflow = None
+    if getattr(mx, "live_caps", (0, 0))[0] > 0 and os.environ.get("MJT_LIVE_TILE", "1") != "0":
+        try:
+            root = d.qpos._base if d.qpos._base is not None else d.qpos
+            off = mx.field_off["scr_ovf"]
+            flags = root[:, off] if (root.dim() == 2 and root.shape[0] == B and root.shape[1] == mx.data_words) else root.reshape(-1)[off * B:(off + 1) * B]
+            tile_overflow = float((flags != 0).double().mean())
+        except Exception:  # noqa: BLE001
+            tile_overflow = None
     from mujoco_torch_b200 import sharding
 
     ms_max = sharding.max_over_ranks(ms, dev)
@@ -275,6 +307,19 @@ def main():
                 "traffic": measured_traffic(top, args.model, args.dtype, B), "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
                 "algorithmic_bytes_per_env_step": algorithmic_bytes(mj, tsize),
                 "kernel_ms_per_step": per_step, "kernel_share": {k: v / sum(per_step.values()) for k, v in per_step.items()}}
+
+    # compute roofline (SURVEY.md 8(d) asks for both): algorithmic flops of the whole step over the measured FMA-pipe peak
+    try:
+        fma_peak = ops.fma_peak(args.dtype == "f64")
+        aflops = algorithmic_flops(mj, mx)
+        step_ms = ms_max / args.steps
+        roofline["fma"] = {"achieved": aflops * B / (step_ms * 1e-3) / 1e12, "peak": fma_peak, "unit": "TFLOP/s",
+                           "frac": aflops * B / (step_ms * 1e-3) / 1e12 / fma_peak if fma_peak else None,
+                           "algorithmic_flops_per_env_step": aflops, "pipe": "fp64" if args.dtype == "f64" else "fp32",
+                           "peak_source": "mjt_fma_peak (register-resident FMA chains, measured in this run)",
+                           "scope": "whole step; solver body counted once, line search at ls_iterations"}
+    except Exception as exc:  # noqa: BLE001
+        roofline["fma"] = {"error": str(exc)}
 
     # ---- end to end through the public API from pinned host buffers
     e2e = None
@@ -328,7 +373,9 @@ def main():
         "vs_baseline": (value / pub) if pub else None, "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": workload_name(args, mj), "batch_per_gpu": B, "parallelism": f"dp{world} (envs sharded, no collective)",
                    "l2": f"per-step working set {mx.data_words * B * tsize / 1e6:.0f} MB > 126 MB L2 (inputs larger than L2)",
-                   "nv": mj.nv, "ncon": mx.ncon, "nefc": mx.nefc, "solve_envs_per_cta": _e.value, "solve_smem_bytes": _s.value},
+                   "nv": mj.nv, "ncon": mx.ncon, "nefc": mx.nefc, "solve_envs_per_cta": _e.value, "solve_smem_bytes": _s.value,
+                   **({"solve_live_tile": {"rows": mx.live_caps[0], "j_words": mx.live_caps[1], "overflow_frac_last_step": tile_overflow}}
+                      if tile_overflow is not None else {})},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "finite": finite,
         "published_baseline": {"value": pub, "hardware": "H200 f64 torch.compile(vmap) tuned, reference README.md:178-247"} if pub else None,
     }

@@ -86,6 +86,11 @@ int mjt_profile_end(char* buf, size_t nbuf);
 /* Launch configuration of the solver kernel (environments = warps per CTA, dynamic shared memory bytes). */
 int mjt_solve_config(const mjtModel* m, int* envs_per_cta, int* smem_bytes);
 
+/* Measured FMA-pipe throughput of the current device in TFLOP/s (FMA = 2 flops), FP64 if is_f64 else FP32: register-resident
+ * independent FMA chains, best of 5 launches, timed with CUDA events on `stream`.  Denominator of bench.py's compute roofline
+ * (SURVEY.md 8(d)); the reference has no counterpart. */
+int mjt_fma_peak(int is_f64, double* tflops, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

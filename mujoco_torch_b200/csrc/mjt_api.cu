@@ -279,7 +279,7 @@ static int run_forward(const mjtModel* m, const MjtIn& in, T* out, int B, int mo
                         m->solve_words, in, out, B, mode);
       ++n;
       if (se == cudaSuccess)
-        se = launch_solve(lanes, dpl, 1, 1, gs, lanes * E, smem, m->solve_smem, st, m->d_blob, m->d_blob + m->blob_words, m->solve_words,
+        se = launch_solve(lanes, dpl, compact, 1, gs, lanes * E, smem, m->solve_smem, st, m->d_blob, m->d_blob + m->blob_words, m->solve_words,
                           in, out, B, mode);
     } else {
       ProfScope prof__("k_solve", st);

@@ -8,6 +8,8 @@ contiguous ModelBlob that every CTA stages into shared memory with a single TMA 
 
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -25,9 +27,11 @@ _FN_TABLE = {
     (_G.BOX, _G.MESH): "CONVEX_CONVEX", (_G.MESH, _G.MESH): "CONVEX_CONVEX",
 }
 # Solver live tile: room for LIVE_FRAC of the constraint rows, at least LIVE_MIN_ROWS.  Measured on the bench states the live
-# share is far below that (box stack: <= 60 of 336 rows, Ant: <= 36 of 284); envs that need more take the full-tile pass.
-LIVE_FRAC = 0.25
-LIVE_MIN_ROWS = 64
+# share is far below that (box stack: <= 112 of 336 rows for 99 % of the envs, Ant: <= 36 of 284); envs that need more take
+# the full-tile pass.  Models solved by half warps (nv <= 16) are occupancy-limited by the row vectors rather than by M / L, so
+# they get the tighter *_HALFWARP pair (profiles/README.md has the sweep).
+LIVE_FRAC, LIVE_MIN_ROWS = 0.33, 64
+LIVE_FRAC_HALFWARP, LIVE_MIN_ROWS_HALFWARP = 0.15, 48
 
 _SUPPORTED_SENSORS = {SensorType.TOUCH, SensorType.ACCELEROMETER, SensorType.VELOCIMETER, SensorType.GYRO, SensorType.MAGNETOMETER,
                       SensorType.RANGEFINDER, SensorType.JOINTPOS, SensorType.JOINTVEL, SensorType.ACTUATORPOS,
@@ -403,10 +407,13 @@ class Model:
         # J, never less than 64 rows.  Envs that need more fall back to the full tile (csrc/k_solve.cuh).
         nefc = len(row_src)
         if nefc > 64:
-            rcap = min(nefc, max(LIVE_MIN_ROWS, -(-int(nefc * LIVE_FRAC) // 16) * 16))
+            half = self.nv <= 16
+            min_rows = int(os.environ.get("MJT_LIVE_MIN_ROWS", LIVE_MIN_ROWS_HALFWARP if half else LIVE_MIN_ROWS))   # tuning knobs (A/B runs)
+            frac = float(os.environ.get("MJT_LIVE_FRAC", LIVE_FRAC_HALFWARP if half else LIVE_FRAC))
+            rcap = min(nefc, max(min_rows, -(-int(nefc * frac) // 16) * 16))
             maxsup = max(src_nsup) if src_nsup else 1
-            jcap = min(jadr, max(rcap * maxsup * 3 // 4, LIVE_MIN_ROWS))
-            self.live_caps = (rcap, jcap) if rcap * 4 <= nefc * 3 else (0, 0)
+            jcap = min(jadr, max(rcap * maxsup * 3 // 4, min_rows))
+            self.live_caps = (rcap, jcap) if rcap * 2 <= nefc else (0, 0)   # a tile that does not halve the rows costs more than it saves (HalfCheetah, measured)
         else:
             self.live_caps = (0, 0)
 

@@ -56,8 +56,17 @@ def lib():
     L.mjt_profile_end.restype = ctypes.c_int
     L.mjt_solve_config.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
     L.mjt_solve_config.restype = ctypes.c_int
+    L.mjt_fma_peak.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.c_void_p]
+    L.mjt_fma_peak.restype = ctypes.c_int
     _lib = L
     return L
+
+
+def fma_peak(f64: bool) -> float:
+    """Measured FMA-pipe throughput of the current CUDA device in TFLOP/s (csrc/mjt_peak.cu)."""
+    v = ctypes.c_double()
+    _check(lib().mjt_fma_peak(1 if f64 else 0, ctypes.byref(v), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return v.value
 
 
 def profile_begin():
@@ -78,7 +87,7 @@ def profile_end() -> dict:
 
 EXPORTS = ("mjt_version", "mjt_last_error", "mjt_model_create", "mjt_model_destroy", "mjt_model_data_words",
            "mjt_model_scratch_words", "mjt_model_dtype_size", "mjt_model_field", "mjt_step", "mjt_forward", "mjt_step_launches",
-           "mjt_profile_begin", "mjt_profile_end", "mjt_solve_config")
+           "mjt_profile_begin", "mjt_profile_end", "mjt_solve_config", "mjt_fma_peak")
 
 
 def _check(rc):

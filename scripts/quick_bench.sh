@@ -6,7 +6,7 @@ for a in "$@"; do
 import sys, json
 try:
     d = json.loads(open('/tmp/qb.json').read())
-    print(f"{sys.argv[1]:45s} {d['value']/1e6:8.3f} M/s {d['ms_per_step']:8.3f} ms", {k: round(v, 3) for k, v in d['roofline']['kernel_ms_per_step'].items()}, 'E', d['config'].get('solve_envs_per_cta'), 'smem', d['config'].get('solve_smem_bytes'))
+    print(f"{sys.argv[1]:45s} {d['value']/1e6:8.3f} M/s {d['ms_per_step']:8.3f} ms", {k: round(v, 3) for k, v in d['roofline']['kernel_ms_per_step'].items()}, 'E', d['config'].get('solve_envs_per_cta'), 'smem', d['config'].get('solve_smem_bytes'), d['config'].get('solve_live_tile', ''))
 except Exception as e:
     print(sys.argv[1], 'failed:', open('/tmp/qb.json').read()[-300:])
 PY

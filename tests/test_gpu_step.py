@@ -304,8 +304,10 @@ def test_live_tile_matches_full_tile(name, state, opt, dtype, monkeypatch):
     for tag in ("default", "tiny", "off"):
         with monkeypatch.context() as mp:
             if tag == "tiny":
-                mp.setattr(model_mod, "LIVE_FRAC", 0.01)
-                mp.setattr(model_mod, "LIVE_MIN_ROWS", 16)
+                for k in ("LIVE_FRAC", "LIVE_FRAC_HALFWARP"):
+                    mp.setattr(model_mod, k, 0.01)
+                for k in ("LIVE_MIN_ROWS", "LIVE_MIN_ROWS_HALFWARP"):
+                    mp.setattr(model_mod, k, 16)
             if tag == "off":
                 mp.setenv("MJT_LIVE_TILE", "0")
             mx, d = util.run_cuda(mj, qpos, qvel, ctrl, dtype, nsteps=3)
