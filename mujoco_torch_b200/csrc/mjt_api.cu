@@ -278,9 +278,14 @@ static int run_forward(const mjtModel* m, const MjtIn& in, T* out, int B, int mo
       se = launch_solve(lanes, dpl, 2, 0, (B + TE - 1) / TE, lanes * TE, tsmem, m->tile_smem, st, m->d_blob, m->d_blob + m->blob_words,
                         m->solve_words, in, out, B, mode);
       ++n;
-      if (se == cudaSuccess)
-        se = launch_solve(lanes, dpl, compact, 1, gs, lanes * E, smem, m->solve_smem, st, m->d_blob, m->d_blob + m->blob_words, m->solve_words,
-                          in, out, B, mode);
+      if (se == cudaSuccess) {
+        // one warp per CTA: CTAs without a flagged env leave at once, flagged envs pack the SMs regardless of where they sit
+        int E2 = 32 / lanes;
+        if (const char* fe = getenv("MJT_OVF_E")) { const int v = atoi(fe); if (v >= E2 && v <= E && v % E2 == 0) E2 = v; }
+        const size_t smem2 = m->solve_blob_bytes + m->solve_region_bytes * E2;
+        se = launch_solve(lanes, dpl, compact, 1, (B + E2 - 1) / E2, lanes * E2, smem2, m->solve_smem, st, m->d_blob, m->d_blob + m->blob_words,
+                          m->solve_words, in, out, B, mode);
+      }
     } else {
       ProfScope prof__("k_solve", st);
       se = launch_solve(lanes, dpl, compact, 0, gs, lanes * E, smem, m->solve_smem, st, m->d_blob, m->d_blob + m->blob_words, m->solve_words,
