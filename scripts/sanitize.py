@@ -9,8 +9,17 @@ import mujoco_torch_b200 as mt
 
 CASES = [("humanoid", {}, 0.4, 33), ("halfcheetah", {}, 0.6, 37), ("ant", {}, 0.0, 5), ("ant_zoo", {"cone": 1, "solver": 1}, 0.5, 19),
          ("stack", {}, -2.0, 7), ("sink", {}, -3.0, 9), ("sink", {"integrator": 3}, -3.0, 3), ("equality_bodies", {}, 0.0, 4),
-         ("convex", {}, -1.0, 3), ("cartpole", {}, 0.0, 1)]
-for name, opt, drop, B in CASES:
+         ("convex", {}, -1.0, 3), ("cartpole", {}, 0.0, 1),
+         # live-tile solver with caps so small that most envs overflow into the full-tile pass (5th entry: env overrides)
+         ("stack", {"integrator": 0}, -1.0, 7, {"MJT_LIVE_MIN_ROWS": "16", "MJT_LIVE_FRAC": "0.01"}),
+         ("ant_zoo", {"cone": 1, "solver": 1}, 0.5, 19, {"MJT_LIVE_MIN_ROWS": "16", "MJT_LIVE_FRAC": "0.01"})]
+ONLY = os.environ.get("MJT_SANITIZE_ONLY")   # comma-separated model names (time-boxed runs)
+for name, opt, drop, B, *rest in CASES:
+    if ONLY and name not in ONLY.split(","):
+        continue
+    for k in ("MJT_LIVE_MIN_ROWS", "MJT_LIVE_FRAC"):
+        os.environ.pop(k, None)
+    os.environ.update(rest[0] if rest else {})
     mj = util.load_model(name, **opt)
     act = None
     if drop >= 0:
@@ -22,4 +31,4 @@ for name, opt, drop, B in CASES:
     for dtype in (torch.float64, torch.float32):
         mx, d = util.run_cuda(mj, qpos, qvel, ctrl, dtype, nsteps=2, act=act)
         assert torch.isfinite(d.qpos).all(), (name, dtype)
-    print("ok", name, opt, B, flush=True)
+    print("ok", name, opt, B, rest[0] if rest else "", flush=True)
