@@ -143,3 +143,32 @@ def test_out_of_scope_models_raise_at_device_put():
                                '<site name="s"/></body></worldbody><sensor><force site="s"/></sensor></mujoco>')
     with pytest.raises(NotImplementedError, match="sensor"):
         mt.device_put(frc)
+
+
+def test_live_tile_caps_and_blob_header():
+    """Solver live tile: only models whose tile would at least halve the rows get one; the caps travel in the
+    blob header, and the two hidden flag fields are the last Data fields of the layout."""
+    caps = {n: mt.device_put(util.load_model(n)).live_caps for n in ("humanoid", "halfcheetah", "hopper", "ant", "ant_zoo", "stack")}
+    assert caps["humanoid"] == (0, 0) and caps["halfcheetah"] == (0, 0) and caps["hopper"] == (0, 0)
+    for n in ("ant", "ant_zoo", "stack"):
+        mx = mt.device_put(util.load_model(n))
+        rcap, jcap = mx.live_caps
+        assert 0 < 2 * rcap <= mx.nefc and rcap % 16 == 0 and 0 < jcap <= mx.sup["jc_words"]
+        hdr = np.asarray(mx.blob[: len(L.H_SCALARS)])
+        assert int(hdr[L.H_SCALARS.index("live_rcap")]) == rcap and int(hdr[L.H_SCALARS.index("live_jcap")]) == jcap
+        assert mx.field_shape["scr_live"] == (len(mx.src),) and mx.field_shape["scr_ovf"] == ()
+    assert [n for n, _ in L.D_FIELDS][-2:] == ["scr_live", "scr_ovf"] and {"scr_live", "scr_ovf"} <= L.HIDDEN_FIELDS
+
+
+def test_bench_algorithmic_counts_match_survey():
+    """bench.py's roofline numerators: SURVEY.md §8(d) gives 1 712 B (f64) of minimal state I/O and ~0.17 MFLOP per Humanoid
+    env-step; HalfCheetah 568 B."""
+    import bench
+
+    mj = util.load_model("humanoid")
+    assert bench.algorithmic_bytes(mj, 8) == 1712 and bench.algorithmic_bytes(mj, 4) == 856
+    assert bench.algorithmic_bytes(util.load_model("halfcheetah"), 8) == 568
+    fl = bench.algorithmic_flops(mj, mt.device_put(mj))
+    assert 1.6e5 < fl < 1.9e5
+    mj.opt.integrator = 1   # RK4: four forwards
+    assert bench.algorithmic_flops(mj, mt.device_put(mj)) == pytest.approx(4 * fl)
