@@ -168,3 +168,54 @@ def test_thousand_step_rollout_stays_finite_and_tracks_f64():
     drift = (outs[torch.float32] - outs[torch.float64]).abs()
     print(f"1000-step f32-vs-f64 drift: median {float(drift.median()):.3e} max {float(drift.max()):.3e}")
     assert float(outs[torch.float64][:, 1].abs().max()) < 5.0   # root z stays near the floor
+
+
+FULL_SIZE = [
+    # BASELINE.json configs at their full batch sizes (bench.py's own initial-state distribution)
+    ("halfcheetah", {}, 4096, torch.float64),                          # config 2
+    ("ant_zoo", {"cone": 1, "solver": 1}, 32768, torch.float32),       # config 3
+    ("humanoid", {}, 65536, torch.float64),                            # config 4 (Euler, the published setup)
+    ("humanoid", {"integrator": 3}, 65536, torch.float32),             # config 4 (ImplicitFast, f32)
+    ("stack", {}, 16384, torch.float32),                               # config 5 (RK4; live-tile solver)
+]
+
+
+@pytest.mark.parametrize("name,opt,B,dtype", FULL_SIZE, ids=[f"{c[0]}-{c[2]}-{str(c[3])[-7:]}" for c in FULL_SIZE])
+def test_full_size_batch_properties(name, opt, B, dtype):
+    """At BASELINE's full batch sizes the oracle is too slow to be the checker, so the step is held to size-independent
+    properties: (1) an env's result does not depend on the batch it is in -- 256 envs sampled from the full batch and stepped
+    as a small batch (the size the oracle parity tests run at) give bit-identical state; (2) permuting the envs permutes the
+    result; (3) every output is finite and free-joint quaternions stay unit.  Together with the small-batch oracle parity
+    this carries parity to the full size."""
+    import mujoco_torch_b200 as mt
+    from mujoco_torch_b200 import sharding
+
+    mj = util.load_model(name, **opt)
+    qpos, qvel, ctrl = sharding.initial_state(mj, name, 0, B, seed=42)
+    dev = "cuda:0"
+    mx = mt.device_put(mj, dtype=dtype).to(dev)
+    T = lambda a: torch.as_tensor(a, device=dev).to(dtype)
+    d0 = mt.make_data(mx).expand(B).clone().replace(qpos=T(qpos), qvel=T(qvel), ctrl=T(ctrl[0]))
+    keys = ("qpos", "qvel", "qacc", "qacc_warmstart", "efc_force", "qfrc_constraint", "sensordata")
+    full = d0
+    for _ in range(2):
+        full = mt.step(mx, full)
+    for k in keys:
+        assert torch.isfinite(getattr(full, k)).all(), k
+    for j in range(mj.njnt):
+        if int(mj.jnt_type[j]) == 0:
+            a = int(mj.jnt_qposadr[j])
+            assert float((full.qpos[:, a + 3:a + 7].norm(dim=1) - 1).abs().max()) < (1e-12 if dtype == torch.float64 else 1e-5)
+    g = torch.Generator().manual_seed(7)
+    pick = torch.randperm(B, generator=g)[:256].to(dev)
+    sub = d0[pick]
+    for _ in range(2):
+        sub = mt.step(mx, sub)
+    for k in keys:
+        assert torch.equal(getattr(sub, k), getattr(full, k)[pick]), f"{k}: env result depends on the batch it is stepped in"
+    perm = torch.randperm(B, generator=g).to(dev)
+    shuffled = mt.step(mx, d0[perm])
+    straight = mt.step(mx, d0)
+    for k in keys:
+        assert torch.equal(getattr(shuffled, k), getattr(straight, k)[perm]), f"{k}: step is not permutation equivariant"
+    assert torch.equal(shuffled.contact.dist, straight.contact.dist[perm])
