@@ -142,6 +142,28 @@ def _env_minor(t: torch.Tensor, batched: bool, dtype) -> torch.Tensor:
     return t.t().contiguous()
 
 
+# Inputs that usually stay the same tensor from step to step (user forces, mocap targets, equality switches): their env-minor
+# copy is kept per model and reused while the source is untouched (same storage, shape, strides and version counter), which
+# removes two strided-copy kernels from every Humanoid step.
+_CACHED_ARGS = ("qfrc_applied", "xfrc_applied", "mocap_pos", "mocap_quat", "eq_active")
+
+
+def _env_minor_cached(model, name, t: torch.Tensor, batched: bool, dtype) -> torch.Tensor:
+    if name not in _CACHED_ARGS or t.numel() == 0:
+        return _env_minor(t, batched, dtype)
+    try:
+        key = (t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()), t.dtype, str(t.device), batched)
+    except RuntimeError:   # inference tensors do not track versions: no reuse
+        return _env_minor(t, batched, dtype)
+    cache = model.__dict__.setdefault("_minor_cache", {})
+    hit = cache.get(name)
+    if hit is not None and hit[0] == key:
+        return hit[2]
+    e = _env_minor(t, batched, dtype)
+    cache[name] = (key, t, e) if e.data_ptr() != t.data_ptr() else (None, None, None)   # the source is kept alive with its copy
+    return e
+
+
 def _launch(model_id: int, mode: int, tensors) -> torch.Tensor:
     model = _MODELS.get(model_id)
     if model is None:
@@ -157,7 +179,7 @@ def _launch(model_id: int, mode: int, tensors) -> torch.Tensor:
     st = StateIn()
     for name, t in zip(_STATE_ARGS, tensors):
         want = torch.int32 if name == "eq_active" else model.dtype
-        e = _env_minor(t, batched, want)
+        e = _env_minor_cached(model, name, t, batched, want)
         keep.append(e)
         setattr(st, name, e.data_ptr() if e.numel() else None)
     st.qacc = None

@@ -219,3 +219,22 @@ def test_full_size_batch_properties(name, opt, B, dtype):
     for k in keys:
         assert torch.equal(getattr(shuffled, k), getattr(straight, k)[perm]), f"{k}: step is not permutation equivariant"
     assert torch.equal(shuffled.contact.dist, straight.contact.dist[perm])
+
+
+def test_cached_constant_inputs_follow_in_place_updates():
+    """ops.py keeps the env-minor copy of inputs that rarely change (xfrc_applied, qfrc_applied, mocap, eq_active) between
+    steps; an in-place update of the source tensor must invalidate it (version counter), and so must a replaced tensor."""
+    mt, mj, mx, d = _batch(B=16)
+    base = mt.step(mx, d)
+    again = mt.step(mx, d)                      # served from the cache
+    assert torch.equal(base.qacc, again.qacc)
+    d.xfrc_applied[:, 1, 2] = 500.0             # in place: same storage, new version
+    pushed = mt.step(mx, d)
+    assert float((pushed.qacc - base.qacc).abs().max()) > 1e-3
+    fresh_mx = mt.device_put(mj, dtype=torch.float64).to("cuda:0")   # no cache history
+    assert torch.equal(mt.step(fresh_mx, d).qacc, pushed.qacc)
+    d2 = d.replace(qfrc_applied=torch.full_like(d.qfrc_applied, 0.25))
+    moved = mt.step(mx, d2)
+    assert float((moved.qacc - pushed.qacc).abs().max()) > 1e-6
+    d.xfrc_applied.zero_()
+    assert torch.equal(mt.step(mx, d).qacc, base.qacc)
