@@ -326,7 +326,7 @@ def main():
     if not args.no_e2e:
         # public API for host-resident state: HostPipeline keeps qpos/qvel/qacc_warmstart/ctrl in pinned host memory and
         # runs H2D -> step -> D2H chunk by chunk on separate streams (2 chunks by default) (transfers of one chunk overlap kernels of another)
-        pipe = mt.HostPipeline(mx, d, nchunk=int(os.environ.get("MJT_E2E_CHUNKS", "2")))
+        pipe = mt.HostPipeline(mx, d, nchunk=int(os.environ["MJT_E2E_CHUNKS"]) if "MJT_E2E_CHUNKS" in os.environ else None)
         nb_in, nb_out = pipe.h2d_bytes, pipe.d2h_bytes
 
         def e2e_step():

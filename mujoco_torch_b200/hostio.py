@@ -20,7 +20,7 @@ OUT_FIELDS = ("qpos", "qvel", "qacc_warmstart")
 
 
 class HostPipeline:
-    """``pipe = HostPipeline(mx, d0, nchunk=4)``; ``pipe.step()`` advances the host-resident state by one timestep.
+    """``pipe = HostPipeline(mx, d0)`` (``nchunk`` defaults to 2 for batches of 16 384 envs and more, else 1); ``pipe.step()`` advances the host-resident state by one timestep.
 
     * ``pipe.host[c][name]`` -- pinned ``(n, B_c)`` tensors (env-minor, the layout the kernels read) per chunk ``c``;
       the caller writes ``ctrl`` (and may rewrite any state field) there between steps.
@@ -28,13 +28,15 @@ class HostPipeline:
       back into the same pinned buffers.  It returns after all streams have drained.
     """
 
-    def __init__(self, m: Model, d: Data, nchunk: int = 4, in_fields=IN_FIELDS, out_fields=OUT_FIELDS):
+    def __init__(self, m: Model, d: Data, nchunk: int | None = None, in_fields=IN_FIELDS, out_fields=OUT_FIELDS):
         if d.qpos.dim() != 2:
             raise ValueError("HostPipeline expects a batched Data with one leading batch dim")
         if not d.qpos.is_cuda:
             raise RuntimeError("HostPipeline needs the template Data on the model's CUDA device (there is no CPU path)")
         self.m, self.in_fields, self.out_fields = m, tuple(in_fields), tuple(out_fields)
         B = d.qpos.shape[0]
+        if nchunk is None:   # measured (profiles/README.md): two chunks overlap PCIe with kernels once a chunk still fills the GPU
+            nchunk = 2 if B >= 16384 else 1
         nchunk = max(1, min(nchunk, B))
         bounds = [(B * c) // nchunk for c in range(nchunk + 1)]
         self.slices = [slice(bounds[c], bounds[c + 1]) for c in range(nchunk)]

@@ -146,6 +146,7 @@ def _env_minor(t: torch.Tensor, batched: bool, dtype) -> torch.Tensor:
 # copy is kept per model and reused while the source is untouched (same storage, shape, strides and version counter), which
 # removes two strided-copy kernels from every Humanoid step.
 _CACHED_ARGS = ("qfrc_applied", "xfrc_applied", "mocap_pos", "mocap_quat", "eq_active")
+_MINOR_CACHE_SLOTS, _MINOR_CACHE_BYTES = 8, 512 << 20
 
 
 def _env_minor_cached(model, name, t: torch.Tensor, batched: bool, dtype) -> torch.Tensor:
@@ -155,12 +156,19 @@ def _env_minor_cached(model, name, t: torch.Tensor, batched: bool, dtype) -> tor
         key = (t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()), t.dtype, str(t.device), batched)
     except RuntimeError:   # inference tensors do not track versions: no reuse
         return _env_minor(t, batched, dtype)
-    cache = model.__dict__.setdefault("_minor_cache", {})
-    hit = cache.get(name)
+    cache = model.__dict__.setdefault("_minor_cache", {})   # (name, storage address) -> (key, source, env-minor copy)
+    slot = (name, key[0])
+    hit = cache.get(slot)
     if hit is not None and hit[0] == key:
         return hit[2]
     e = _env_minor(t, batched, dtype)
-    cache[name] = (key, t, e) if e.data_ptr() != t.data_ptr() else (None, None, None)   # the source is kept alive with its copy
+    if e.data_ptr() != t.data_ptr():
+        cache.pop(slot, None)
+        cache[slot] = (key, t, e)   # the source is kept alive with its copy, so its address cannot be reused meanwhile
+        # HostPipeline steps several chunk templates in turn, so a few slots per input; bounded in count and in bytes
+        while len(cache) > 1 and (len(cache) > _MINOR_CACHE_SLOTS
+                                  or sum(v[2].numel() * v[2].element_size() for v in cache.values()) > _MINOR_CACHE_BYTES):
+            cache.pop(next(iter(cache)))
     return e
 
 
