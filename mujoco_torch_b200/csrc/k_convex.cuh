@@ -328,28 +328,66 @@ __device__ void convex_convex(const ModelView<T>& m, const EnvBuf<T>& d, int g1,
   auto VA = [&](int i) { return i < MJT_VCACHE ? ldv(va, i) : tp + mat_mul(tm, ha.v(i)); };
   auto NA = [&](int f) { return mat_mul(tm, ha.n(f)); };
 
-  // separating-axis scan (:481-530): face normals of A, of B, then edge x edge; first minimum wins
+  // separating-axis scan (:481-530): face normals of A, of B, then edge x edge; first minimum wins.  Axes are projected NB at
+  // a time so that every vertex is loaded once per block instead of once per axis (each dot product and each min / max chain is
+  // the same arithmetic in the same order as the one-axis form, and the winners are compared in axis order).
   int best_k = 0, best_sign = 1;
   T best_v = T(0);
   V3<T> best_axis(0, 0, 0);
-  auto test_axis = [&](const V3<T>& ax, int k) {
-    T amax = -t_inf<T>(), amin = t_inf<T>(), bmax = -t_inf<T>(), bmin = t_inf<T>();
-    for (int i = 0; i < ha.nvert; ++i) { const T s = dot(ax, VA(i)); amax = t_max(amax, s); amin = t_min(amin, s); }
-    for (int i = 0; i < hb.nvert; ++i) { const T s = dot(ax, hb.v(i)); bmax = t_max(bmax, s); bmin = t_min(bmin, s); }
+  bool first_axis = true;
+  auto take = [&](const V3<T>& ax, int k, T amax, T amin, T bmax, T bmin) {
     const T d1 = amax - bmin, d2 = bmax - amin;
     T sup = t_min(d1, d2);
     if (ax.x == T(0) && ax.y == T(0) && ax.z == T(0)) sup = T(1e6);
-    if (k == 0 || sup < best_v || (sup == best_v && k < best_k)) { best_v = sup; best_k = k; best_sign = d1 > d2 ? -1 : 1; best_axis = ax; }
+    if (first_axis || sup < best_v || (sup == best_v && k < best_k)) { best_v = sup; best_k = k; best_sign = d1 > d2 ? -1 : 1; best_axis = ax; }
+    first_axis = false;
   };
-  for (int f = 0; f < ha.nface; ++f) test_axis(NA(f), f);
-  for (int f = 0; f < hb.nface; ++f) test_axis(hb.n(f), ha.nface + f);
-  const int nfaces = ha.nface + hb.nface;
-  for (int ia = 0; ia < ha.nedge; ++ia) {
-    const V3<T> da = VA(ha.edge[2 * ia]) - VA(ha.edge[2 * ia + 1]);
-    for (int ib = 0; ib < hb.nedge; ++ib) {
-      const V3<T> db = hb.v(hb.edge[2 * ib]) - hb.v(hb.edge[2 * ib + 1]);
-      test_axis(normalize3(cross(da, db)), nfaces + ib * ha.nedge + ia);
+  constexpr int NB = 4;
+  auto test_axes = [&](const V3<T>* ax, const int* k, int n) {   // n <= NB axes, in scan order
+    T amax[NB], amin[NB], bmax[NB], bmin[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) { amax[j] = bmax[j] = -t_inf<T>(); amin[j] = bmin[j] = t_inf<T>(); }
+    for (int i = 0; i < ha.nvert; ++i) {
+      const V3<T> v = VA(i);
+#pragma unroll
+      for (int j = 0; j < NB; ++j) { const T s = dot(ax[j], v); amax[j] = t_max(amax[j], s); amin[j] = t_min(amin[j], s); }
     }
+    for (int i = 0; i < hb.nvert; ++i) {
+      const V3<T> v = hb.v(i);
+#pragma unroll
+      for (int j = 0; j < NB; ++j) { const T s = dot(ax[j], v); bmax[j] = t_max(bmax[j], s); bmin[j] = t_min(bmin[j], s); }
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j)
+      if (j < n) take(ax[j], k[j], amax[j], amin[j], bmax[j], bmin[j]);
+  };
+  const int nfaces = ha.nface + hb.nface;
+  {
+    V3<T> ax[NB];
+    int kk[NB];
+    int n = 0;
+    auto push = [&](const V3<T>& a, int k) {
+      ax[n] = a;
+      kk[n] = k;
+      if (++n == NB) { test_axes(ax, kk, NB); n = 0; }
+    };
+    auto flush = [&]() {
+      if (n) {
+        for (int j = n; j < NB; ++j) { ax[j] = ax[0]; kk[j] = kk[0]; }   // padding lanes are computed and ignored
+        test_axes(ax, kk, n);
+        n = 0;
+      }
+    };
+    for (int f = 0; f < ha.nface; ++f) push(NA(f), f);
+    for (int f = 0; f < hb.nface; ++f) push(hb.n(f), ha.nface + f);
+    for (int ia = 0; ia < ha.nedge; ++ia) {
+      const V3<T> da = VA(ha.edge[2 * ia]) - VA(ha.edge[2 * ia + 1]);
+      for (int ib = 0; ib < hb.nedge; ++ib) {
+        const V3<T> db = hb.v(hb.edge[2 * ib]) - hb.v(hb.edge[2 * ib + 1]);
+        push(normalize3(cross(da, db)), nfaces + ib * ha.nedge + ia);
+      }
+    }
+    flush();
   }
   const bool is_edge = best_k >= nfaces;
   // reference / incident faces (:532-560)
