@@ -140,7 +140,7 @@ __device__ void collide_pair(const ModelView<T>& m, const EnvBuf<T>& d, int p) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(MJT_ENV_THREADS) k_collision(const int* __restrict__ gblob, int blob_words, T* __restrict__ out, int B) {
+__global__ void __launch_bounds__(MJT_ENV_THREADS, MJT_COLLISION_MINB) k_collision(const int* __restrict__ gblob, int blob_words, T* __restrict__ out, int B) {
   extern __shared__ __align__(16) int smem_blob[];
   __shared__ uint64_t bar;
   stage_blob(smem_blob, &bar, gblob, blob_words);

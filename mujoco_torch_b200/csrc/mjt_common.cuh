@@ -9,6 +9,9 @@
 #ifndef MJT_ENV_THREADS
 #define MJT_ENV_THREADS 128
 #endif
+#ifndef MJT_COLLISION_MINB
+#define MJT_COLLISION_MINB 1   // resident CTAs per SM the collision kernel is compiled for (register cap)
+#endif
 #ifndef MJT_SMOOTH_MINB
 #define MJT_SMOOTH_MINB 4
 #endif
