@@ -13,6 +13,7 @@ from .api import (  # noqa: F401
     solve, step, tendon, transmission,
 )
 from .data import Contact, Data  # noqa: F401
+from .devget import device_get_into  # noqa: F401
 from .hostio import HostPipeline  # noqa: F401
 from .mjmodel import (  # noqa: F401
     BiasType, ConeType, DisableBit, DynType, EnableBit, EqType, GainType, GeomType, IntegratorType, JacobianType, JointType,

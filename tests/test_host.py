@@ -172,3 +172,67 @@ def test_bench_algorithmic_counts_match_survey():
     assert 1.6e5 < fl < 1.9e5
     mj.opt.integrator = 1   # RK4: four forwards
     assert bench.algorithmic_flops(mj, mt.device_put(mj)) == pytest.approx(4 * fl)
+
+
+def test_device_get_into_follows_the_reference_rules():
+    """reference device.device_get_into :1119-1205: one struct keeps the batch dim, a list gets one env each; rotation matrices
+    travel flattened, efc_J / actuator_moment / qM / qLD are skipped, contact_dim lands in `dim`, shape mismatches are skipped."""
+    import types as pytypes
+
+    mx = mt.device_put(util.load_model("humanoid"))
+    B = 3
+    d = mt.make_data(mx).expand(B).clone()
+    d = d.replace(qpos=d.qpos + torch.arange(B, dtype=d.qpos.dtype)[:, None], xmat=torch.randn(B, mx.nbody, 3, 3, dtype=d.qpos.dtype))
+    d.contact.frame.copy_(torch.randn_like(d.contact.frame))
+
+    def blank(batch):
+        r = pytypes.SimpleNamespace(contact=pytypes.SimpleNamespace())
+        r.qvel = np.zeros(batch + (mx.nv + 1,))      # wrong shape on purpose: must be left alone
+        return r
+
+    one = blank((B,))
+    mt.device_get_into(one, d)
+    assert one.qpos.shape == (B, mx.nq) and np.array_equal(one.qpos, d.qpos.numpy())
+    assert one.xmat.shape == (B, mx.nbody, 9) and np.array_equal(one.xmat, d.xmat.reshape(B, mx.nbody, 9).numpy())
+    assert one.contact.frame.shape == (B, mx.ncon, 9) and one.contact.dim.shape == (B, mx.ncon)
+    assert not hasattr(one.contact, "contact_dim")
+    for skipped in ("efc_J", "actuator_moment", "qM", "qLD"):
+        assert not hasattr(one, skipped)
+    assert one.qvel.shape == (B, mx.nv + 1) and not one.qvel.any()
+    assert (one.ncon, one.nefc) == (mx.ncon, mx.nefc)
+
+    many = [blank(()) for _ in range(B)]
+    mt.device_get_into(many, d)
+    for i, r in enumerate(many):
+        assert r.qpos.shape == (mx.nq,) and np.array_equal(r.qpos, d.qpos[i].numpy())
+        assert r.contact.frame.shape == (mx.ncon, 9)
+    with pytest.raises(ValueError, match="doesn't match value batch size"):
+        mt.device_get_into(many[:2], d)
+    with pytest.raises(ValueError, match="unrecognizable batch dimension"):
+        mt.device_get_into([blank(())], mt.make_data(mx))
+
+
+def test_env_minor_input_cache_rules():
+    """ops._env_minor_cached (pure tensor logic, exercised here on CPU tensors): reuse while the source is untouched, refresh on
+    an in-place write or a new tensor, never for per-step inputs, bounded in slots."""
+    class M:   # stands in for a Model: only carries the cache dict
+        pass
+
+    m = M()
+    x = torch.zeros(8, 6)
+    a = ops._env_minor_cached(m, "xfrc_applied", x, True, torch.float32)
+    assert a.shape == (6, 8) and a.is_contiguous()
+    assert ops._env_minor_cached(m, "xfrc_applied", x, True, torch.float32) is a          # untouched source: reused
+    x[3, 2] = 5.0                                                                          # in-place write: new version
+    b = ops._env_minor_cached(m, "xfrc_applied", x, True, torch.float32)
+    assert b is not a and float(b[2, 3]) == 5.0
+    y = x.clone()
+    c = ops._env_minor_cached(m, "xfrc_applied", y, True, torch.float32)                   # another tensor: its own slot
+    assert c is not b and ops._env_minor_cached(m, "xfrc_applied", x, True, torch.float32) is b
+    q = torch.zeros(8, 3)
+    assert ops._env_minor_cached(m, "qpos", q, True, torch.float32) is not ops._env_minor_cached(m, "qpos", q, True, torch.float32)
+    em = torch.zeros(6, 8).t()                                                             # already env-minor: no copy, no slot
+    assert ops._env_minor_cached(m, "qfrc_applied", em, True, torch.float32).data_ptr() == em.data_ptr()
+    for _ in range(3 * ops._MINOR_CACHE_SLOTS):
+        ops._env_minor_cached(m, "mocap_pos", torch.zeros(8, 3), True, torch.float32)
+    assert len(m._minor_cache) <= ops._MINOR_CACHE_SLOTS
