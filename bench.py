@@ -208,6 +208,8 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--gather-obs", action="store_true",
+                    help="also all-gather (qpos, qvel), reward, done over the job every step on a side stream (sharding.ObsGather)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -263,9 +265,21 @@ def main():
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    gather = None
+    if args.gather_obs:   # optional collective of SURVEY 8(e): off the physics path, overlapped with the next step
+        from mujoco_torch_b200 import sharding as _sh
+
+        gather = _sh.ObsGather(mj.nq + mj.nv, B, dtype, dev)
+        zeros_b = torch.zeros(B, dtype=dtype, device=dev)
     ev0.record()
     for i in range(args.steps):
         d = mt.step(mx, d.replace(ctrl=ctrls[i % 4]))
+        if gather is not None:
+            if i:
+                gather.wait()
+            gather.launch(torch.cat([d.qpos, d.qvel], dim=1), zeros_b, zeros_b)
+    if gather is not None:
+        gather.wait()
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -373,7 +387,8 @@ def main():
         "vs_baseline": (value / pub) if pub else None, "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": workload_name(args, mj), "batch_per_gpu": B, "parallelism": f"dp{world} (envs sharded, no collective)",
                    "l2": f"per-step working set {mx.data_words * B * tsize / 1e6:.0f} MB > 126 MB L2 (inputs larger than L2)",
-                   "nv": mj.nv, "ncon": mx.ncon, "nefc": mx.nefc, "solve_envs_per_cta": _e.value, "solve_smem_bytes": _s.value,
+                   "nv": mj.nv, "ncon": mx.ncon, "nefc": mx.nefc,
+                   **({"obs_gather_bytes_per_step": gather.bytes_per_gather} if gather is not None else {}), "solve_envs_per_cta": _e.value, "solve_smem_bytes": _s.value,
                    **({"solve_live_tile": {"rows": mx.live_caps[0], "j_words": mx.live_caps[1], "overflow_frac_last_step": tile_overflow}}
                       if tile_overflow is not None else {})},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "finite": finite,

@@ -66,3 +66,62 @@ def job_rate(envs_per_rank: int, steps: int, ms_per_rank: float, device=None) ->
 
     world = td.get_world_size() if (td.is_available() and td.is_initialized()) else 1
     return world * envs_per_rank * steps / (max_over_ranks(ms_per_rank, device) * 1e-3)
+
+
+class ObsGather:
+    """Optional per-agent-step all-gather of observation + reward + done over the job: the only collective a
+    sharded rollout may want, and it is off the physics path.
+
+    Every rank packs its ``(B, obs_dim)`` observation, ``(B,)`` reward and ``(B,)`` done flag into one ``(B, obs_dim + 2)``
+    buffer and ``all_gather_into_tensor`` collects the ``(world * B, obs_dim + 2)`` result in rank order (= global env order,
+    ranks own contiguous env ranges).  On CUDA the pack and the collective run on a **side stream** that first waits for the
+    producer stream, so NCCL overlaps the next physics step; ``wait()`` makes the caller's stream wait for the result.  One
+    message per step, sized for launch latency (Humanoid: 65 536 envs x 55 words x 8 ranks = 115 MB f32 per gather).
+
+    ``gather = ObsGather(obs_dim, B, dtype, device)``; per step ``gather.launch(obs, reward, done)`` ... next ``step`` ...
+    ``obs_all, reward_all, done_all = gather.wait()``.  Without an initialised process group it degenerates to a local copy.
+    """
+
+    def __init__(self, obs_dim: int, envs_per_rank: int, dtype=torch.float32, device="cpu"):
+        import torch.distributed as td
+
+        self.dist = td.is_available() and td.is_initialized() and td.get_world_size() > 1
+        self.world = td.get_world_size() if self.dist else 1
+        self.obs_dim, self.B = int(obs_dim), int(envs_per_rank)
+        self.device = torch.device(device)
+        self.send = torch.empty((self.B, self.obs_dim + 2), dtype=dtype, device=self.device)
+        self.recv = torch.empty((self.world * self.B, self.obs_dim + 2), dtype=dtype, device=self.device)
+        self.stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
+        self._work = None
+        self.bytes_per_gather = self.recv.numel() * self.recv.element_size()
+
+    def _pack_and_gather(self, obs, reward, done):
+        import torch.distributed as td
+
+        self.send[:, : self.obs_dim].copy_(obs.reshape(self.B, self.obs_dim))
+        self.send[:, self.obs_dim].copy_(reward.reshape(self.B))
+        self.send[:, self.obs_dim + 1].copy_(done.reshape(self.B))
+        if self.dist:
+            self._work = td.all_gather_into_tensor(self.recv, self.send, async_op=True)
+        else:
+            self.recv.copy_(self.send)
+
+    def launch(self, obs: torch.Tensor, reward: torch.Tensor, done: torch.Tensor):
+        """Enqueue pack + all-gather (asynchronous; the inputs may be overwritten only after ``wait``)."""
+        if obs.shape[0] != self.B or obs[0].numel() != self.obs_dim:
+            raise ValueError(f"ObsGather: expected obs ({self.B}, {self.obs_dim}), got {tuple(obs.shape)}")
+        if self.stream is not None:
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self.stream):
+                self._pack_and_gather(obs, reward, done)
+        else:
+            self._pack_and_gather(obs, reward, done)
+
+    def wait(self):
+        """``(obs (world*B, obs_dim), reward (world*B,), done (world*B,) bool)`` of the whole job, in global env order."""
+        if self._work is not None:
+            self._work.wait()
+            self._work = None
+        if self.stream is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self.stream)
+        return self.recv[:, : self.obs_dim], self.recv[:, self.obs_dim], self.recv[:, self.obs_dim + 1] != 0

@@ -238,3 +238,18 @@ def test_cached_constant_inputs_follow_in_place_updates():
     assert float((moved.qacc - pushed.qacc).abs().max()) > 1e-6
     d.xfrc_applied.zero_()
     assert torch.equal(mt.step(mx, d).qacc, base.qacc)
+
+
+def test_obs_gather_side_stream_single_rank():
+    """sharding.ObsGather on CUDA without a process group: pack + copy run on a side stream that waits for the producer stream;
+    wait() orders the caller's stream after it."""
+    from mujoco_torch_b200 import sharding
+
+    mt, mj, mx, d = _batch(B=64)
+    out = mt.step(mx, d)
+    g = sharding.ObsGather(mj.nq + mj.nv, 64, torch.float64, "cuda:0")
+    g.launch(torch.cat([out.qpos, out.qvel], dim=1), out.time, out.time > 1e9)
+    nxt = mt.step(mx, out)                      # overlaps the gather
+    obs, rew, done = g.wait()
+    assert torch.equal(obs, torch.cat([out.qpos, out.qvel], dim=1)) and torch.equal(rew, out.time) and not bool(done.any())
+    assert torch.isfinite(nxt.qpos).all()

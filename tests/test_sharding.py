@@ -36,10 +36,21 @@ def _worker(rank, world, port, out):
         _, d = util.run_oracle(mj, qpos, qvel, ctrl[0])
         gathered = [None] * world
         td.all_gather_object(gathered, {"lo": lo, "hi": hi, "qpos_in": qpos, "qpos": d.qpos.numpy(), "qvel": d.qvel.numpy()})
+        # optional observation / reward / done all-gather (equal shards; rank-major = global env order)
+        B, od = 5, mj.nq + mj.nv
+        g = sharding.ObsGather(od, B, torch.float64)
+        obs = torch.cat([d.qpos[:B], d.qvel[:B]], dim=1)
+        g.launch(obs, torch.full((B,), float(rank + 1), dtype=torch.float64), torch.arange(B) % 2 == rank)
+        obs_all, rew_all, done_all = g.wait()
+        obs_parts = [None] * world
+        td.all_gather_object(obs_parts, obs.numpy())
+        gather_ok = (tuple(obs_all.shape) == (world * B, od) and np.array_equal(obs_all.numpy(), np.concatenate(obs_parts))
+                     and rew_all.tolist() == [1.0] * B + [2.0] * B
+                     and done_all.tolist() == [i % 2 == 0 for i in range(B)] + [i % 2 == 1 for i in range(B)])
         slow = sharding.max_over_ranks(10.0 + rank)          # rank 1 is the slow one
         rate = sharding.job_rate(100, 10, 10.0 + rank)       # 2 ranks x 100 envs x 10 steps / 11 ms
         if rank == 0:
-            torch.save({"gathered": gathered, "slow": slow, "rate": rate}, out)
+            torch.save({"gathered": gathered, "slow": slow, "rate": rate, "gather_ok": gather_ok}, out)
     finally:
         td.destroy_process_group()
 
@@ -51,6 +62,7 @@ def test_two_rank_shards_equal_single_process(tmp_path):
     g = sorted(res["gathered"], key=lambda x: x["lo"])
     assert [(x["lo"], x["hi"]) for x in g] == [(0, 19), (19, 37)]
     assert res["slow"] == 11.0
+    assert res["gather_ok"], "ObsGather: gathered observations / rewards / done flags are not the rank-ordered union"
     assert abs(res["rate"] - 2 * 100 * 10 / 11e-3) < 1e-6
     mj = util.load_model("halfcheetah")
     qpos, qvel, ctrl = sharding.initial_state(mj, "halfcheetah", 0, TOTAL, seed=42)
@@ -77,3 +89,14 @@ def test_states_cross_chunk_boundaries():
     part = sharding.initial_state(mj, "cartpole", lo, hi, seed=7)
     assert np.array_equal(part[0], full[0][lo:hi]) and np.array_equal(part[1], full[1][lo:hi])
     assert np.array_equal(part[2], full[2][:, lo:hi])
+
+
+def test_obs_gather_without_process_group_is_a_local_copy():
+    g = sharding.ObsGather(3, 4, torch.float32)
+    obs = torch.arange(12, dtype=torch.float32).reshape(4, 3)
+    g.launch(obs, torch.ones(4), torch.tensor([True, False, False, True]))
+    o, r, dn = g.wait()
+    assert torch.equal(o, obs) and r.tolist() == [1.0] * 4 and dn.tolist() == [True, False, False, True]
+    assert g.bytes_per_gather == 4 * 5 * 4
+    with pytest.raises(ValueError):
+        g.launch(torch.zeros(3, 3), torch.ones(3), torch.zeros(3))
