@@ -277,7 +277,7 @@ def main():
         if gather is not None:
             if i:
                 gather.wait()
-            gather.launch(torch.cat([d.qpos, d.qvel], dim=1), zeros_b, zeros_b)
+            gather.launch([d.qpos, d.qvel], zeros_b, zeros_b)
     if gather is not None:
         gather.wait()
     ev1.record()

@@ -78,7 +78,8 @@ class ObsGather:
     producer stream, so NCCL overlaps the next physics step; ``wait()`` makes the caller's stream wait for the result.  One
     message per step, sized for launch latency (Humanoid: 65 536 envs x 55 words x 8 ranks = 115 MB f32 per gather).
 
-    ``gather = ObsGather(obs_dim, B, dtype, device)``; per step ``gather.launch(obs, reward, done)`` ... next ``step`` ...
+    ``gather = ObsGather(obs_dim, B, dtype, device)``; per step ``gather.launch(obs, reward, done)`` (``obs`` one ``(B, obs_dim)``
+    tensor or a list of ``(B, k_i)`` pieces, e.g. ``[d.qpos, d.qvel]``, packed on the side stream) ... next ``step`` ...
     ``obs_all, reward_all, done_all = gather.wait()``.  Without an initialised process group it degenerates to a local copy.
     """
 
@@ -98,7 +99,14 @@ class ObsGather:
     def _pack_and_gather(self, obs, reward, done):
         import torch.distributed as td
 
-        self.send[:, : self.obs_dim].copy_(obs.reshape(self.B, self.obs_dim))
+        if isinstance(obs, (list, tuple)):   # pieces are packed here, on the side stream, instead of a cat on the producer stream
+            o = 0
+            for part in obs:
+                part = part.reshape(self.B, -1)
+                self.send[:, o:o + part.shape[1]].copy_(part)
+                o += part.shape[1]
+        else:
+            self.send[:, : self.obs_dim].copy_(obs.reshape(self.B, self.obs_dim))
         self.send[:, self.obs_dim].copy_(reward.reshape(self.B))
         self.send[:, self.obs_dim + 1].copy_(done.reshape(self.B))
         if self.dist:
@@ -108,8 +116,9 @@ class ObsGather:
 
     def launch(self, obs: torch.Tensor, reward: torch.Tensor, done: torch.Tensor):
         """Enqueue pack + all-gather (asynchronous; the inputs may be overwritten only after ``wait``)."""
-        if obs.shape[0] != self.B or obs[0].numel() != self.obs_dim:
-            raise ValueError(f"ObsGather: expected obs ({self.B}, {self.obs_dim}), got {tuple(obs.shape)}")
+        parts = obs if isinstance(obs, (list, tuple)) else [obs]
+        if any(p.shape[0] != self.B for p in parts) or sum(p[0].numel() for p in parts) != self.obs_dim:
+            raise ValueError(f"ObsGather: expected obs ({self.B}, {self.obs_dim}), got {[tuple(p.shape) for p in parts]}")
         if self.stream is not None:
             self.stream.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(self.stream):

@@ -98,5 +98,7 @@ def test_obs_gather_without_process_group_is_a_local_copy():
     o, r, dn = g.wait()
     assert torch.equal(o, obs) and r.tolist() == [1.0] * 4 and dn.tolist() == [True, False, False, True]
     assert g.bytes_per_gather == 4 * 5 * 4
+    g.launch([obs[:, :1], obs[:, 1:]], torch.ones(4), torch.zeros(4))     # obs given in pieces
+    assert torch.equal(g.wait()[0], obs)
     with pytest.raises(ValueError):
         g.launch(torch.zeros(3, 3), torch.ones(3), torch.zeros(3))
