@@ -72,15 +72,18 @@ class ObsGather:
     """Optional per-agent-step all-gather of observation + reward + done over the job: the only collective a
     sharded rollout may want, and it is off the physics path.
 
-    Every rank packs its ``(B, obs_dim)`` observation, ``(B,)`` reward and ``(B,)`` done flag into one ``(B, obs_dim + 2)``
-    buffer and ``all_gather_into_tensor`` collects the ``(world * B, obs_dim + 2)`` result in rank order (= global env order,
-    ranks own contiguous env ranges).  On CUDA the pack and the collective run on a **side stream** that first waits for the
-    producer stream, so NCCL overlaps the next physics step; ``wait()`` makes the caller's stream wait for the result.  One
-    message per step, sized for launch latency (Humanoid: 65 536 envs x 55 words x 8 ranks = 115 MB f32 per gather).
+    Every rank packs its ``(B, obs_dim)`` observation, ``(B,)`` reward and ``(B,)`` done flag into one **env-minor**
+    ``(obs_dim + 2, B)`` message -- the layout the step's outputs already have, so packing ``[d.qpos, d.qvel]`` is a handful of
+    contiguous row copies -- and ``all_gather_into_tensor`` collects ``(world, obs_dim + 2, B)`` in rank order (= global env
+    order, ranks own contiguous env ranges).  On CUDA the pack and the collective run on a **side stream** that first waits for
+    the producer stream, so NCCL overlaps the next physics step; ``wait()`` makes the caller's stream wait for the result.  One
+    message per step, sized for launch latency (Humanoid: 65 536 envs x 57 words x 8 ranks = 120 MB f32 per gather).
 
     ``gather = ObsGather(obs_dim, B, dtype, device)``; per step ``gather.launch(obs, reward, done)`` (``obs`` one ``(B, obs_dim)``
-    tensor or a list of ``(B, k_i)`` pieces, e.g. ``[d.qpos, d.qvel]``, packed on the side stream) ... next ``step`` ...
-    ``obs_all, reward_all, done_all = gather.wait()``.  Without an initialised process group it degenerates to a local copy.
+    tensor or a list of ``(B, k_i)`` pieces, e.g. ``[d.qpos, d.qvel]``) ... next ``step`` ...
+    ``obs_all, reward_all, done_all = gather.wait()`` with shapes ``(world, B, obs_dim)``, ``(world, B)``, ``(world, B)``
+    (strided views of the receive buffer; ``obs_all.reshape(world * B, obs_dim)`` gives the flat global batch).  Without an
+    initialised process group it degenerates to a local copy.
     """
 
     def __init__(self, obs_dim: int, envs_per_rank: int, dtype=torch.float32, device="cpu"):
@@ -90,47 +93,44 @@ class ObsGather:
         self.world = td.get_world_size() if self.dist else 1
         self.obs_dim, self.B = int(obs_dim), int(envs_per_rank)
         self.device = torch.device(device)
-        self.send = torch.empty((self.B, self.obs_dim + 2), dtype=dtype, device=self.device)
-        self.recv = torch.empty((self.world * self.B, self.obs_dim + 2), dtype=dtype, device=self.device)
+        self.send = torch.empty((self.obs_dim + 2, self.B), dtype=dtype, device=self.device)
+        self.recv = torch.empty((self.world, self.obs_dim + 2, self.B), dtype=dtype, device=self.device)
         self.stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
         self._work = None
         self.bytes_per_gather = self.recv.numel() * self.recv.element_size()
 
-    def _pack_and_gather(self, obs, reward, done):
+    def _pack_and_gather(self, parts, reward, done):
         import torch.distributed as td
 
-        if isinstance(obs, (list, tuple)):   # pieces are packed here, on the side stream, instead of a cat on the producer stream
-            o = 0
-            for part in obs:
-                part = part.reshape(self.B, -1)
-                self.send[:, o:o + part.shape[1]].copy_(part)
-                o += part.shape[1]
-        else:
-            self.send[:, : self.obs_dim].copy_(obs.reshape(self.B, self.obs_dim))
-        self.send[:, self.obs_dim].copy_(reward.reshape(self.B))
-        self.send[:, self.obs_dim + 1].copy_(done.reshape(self.B))
+        o = 0
+        for part in parts:   # (B, k) logical; env-minor sources (views of a step's output buffer) copy row by row, coalesced
+            part = part.reshape(self.B, -1)
+            self.send[o:o + part.shape[1]].copy_(part.t())
+            o += part.shape[1]
+        self.send[self.obs_dim].copy_(reward.reshape(self.B))
+        self.send[self.obs_dim + 1].copy_(done.reshape(self.B))
         if self.dist:
-            self._work = td.all_gather_into_tensor(self.recv, self.send, async_op=True)
+            self._work = td.all_gather_into_tensor(self.recv.view(self.world * (self.obs_dim + 2), self.B), self.send, async_op=True)   # dim-0 concatenation
         else:
-            self.recv.copy_(self.send)
+            self.recv[0].copy_(self.send)
 
-    def launch(self, obs: torch.Tensor, reward: torch.Tensor, done: torch.Tensor):
+    def launch(self, obs, reward: torch.Tensor, done: torch.Tensor):
         """Enqueue pack + all-gather (asynchronous; the inputs may be overwritten only after ``wait``)."""
-        parts = obs if isinstance(obs, (list, tuple)) else [obs]
+        parts = list(obs) if isinstance(obs, (list, tuple)) else [obs]
         if any(p.shape[0] != self.B for p in parts) or sum(p[0].numel() for p in parts) != self.obs_dim:
             raise ValueError(f"ObsGather: expected obs ({self.B}, {self.obs_dim}), got {[tuple(p.shape) for p in parts]}")
         if self.stream is not None:
             self.stream.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(self.stream):
-                self._pack_and_gather(obs, reward, done)
+                self._pack_and_gather(parts, reward, done)
         else:
-            self._pack_and_gather(obs, reward, done)
+            self._pack_and_gather(parts, reward, done)
 
     def wait(self):
-        """``(obs (world*B, obs_dim), reward (world*B,), done (world*B,) bool)`` of the whole job, in global env order."""
+        """``(obs (world, B, obs_dim), reward (world, B), done (world, B) bool)`` of the whole job; rank-major = global env order."""
         if self._work is not None:
             self._work.wait()
             self._work = None
         if self.stream is not None:
             torch.cuda.current_stream(self.device).wait_stream(self.stream)
-        return self.recv[:, : self.obs_dim], self.recv[:, self.obs_dim], self.recv[:, self.obs_dim + 1] != 0
+        return self.recv[:, : self.obs_dim].permute(0, 2, 1), self.recv[:, self.obs_dim], self.recv[:, self.obs_dim + 1] != 0

@@ -248,8 +248,9 @@ def test_obs_gather_side_stream_single_rank():
     mt, mj, mx, d = _batch(B=64)
     out = mt.step(mx, d)
     g = sharding.ObsGather(mj.nq + mj.nv, 64, torch.float64, "cuda:0")
-    g.launch(torch.cat([out.qpos, out.qvel], dim=1), out.time, out.time > 1e9)
+    g.launch([out.qpos, out.qvel], out.time, out.time > 1e9)
     nxt = mt.step(mx, out)                      # overlaps the gather
     obs, rew, done = g.wait()
-    assert torch.equal(obs, torch.cat([out.qpos, out.qvel], dim=1)) and torch.equal(rew, out.time) and not bool(done.any())
+    assert obs.shape == (1, 64, mj.nq + mj.nv)
+    assert torch.equal(obs[0], torch.cat([out.qpos, out.qvel], dim=1)) and torch.equal(rew[0], out.time) and not bool(done.any())
     assert torch.isfinite(nxt.qpos).all()

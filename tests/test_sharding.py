@@ -44,9 +44,10 @@ def _worker(rank, world, port, out):
         obs_all, rew_all, done_all = g.wait()
         obs_parts = [None] * world
         td.all_gather_object(obs_parts, obs.numpy())
-        gather_ok = (tuple(obs_all.shape) == (world * B, od) and np.array_equal(obs_all.numpy(), np.concatenate(obs_parts))
-                     and rew_all.tolist() == [1.0] * B + [2.0] * B
-                     and done_all.tolist() == [i % 2 == 0 for i in range(B)] + [i % 2 == 1 for i in range(B)])
+        gather_ok = (tuple(obs_all.shape) == (world, B, od)
+                     and np.array_equal(obs_all.reshape(world * B, od).numpy(), np.concatenate(obs_parts))
+                     and rew_all.reshape(-1).tolist() == [1.0] * B + [2.0] * B
+                     and done_all.reshape(-1).tolist() == [i % 2 == 0 for i in range(B)] + [i % 2 == 1 for i in range(B)])
         slow = sharding.max_over_ranks(10.0 + rank)          # rank 1 is the slow one
         rate = sharding.job_rate(100, 10, 10.0 + rank)       # 2 ranks x 100 envs x 10 steps / 11 ms
         if rank == 0:
@@ -96,9 +97,9 @@ def test_obs_gather_without_process_group_is_a_local_copy():
     obs = torch.arange(12, dtype=torch.float32).reshape(4, 3)
     g.launch(obs, torch.ones(4), torch.tensor([True, False, False, True]))
     o, r, dn = g.wait()
-    assert torch.equal(o, obs) and r.tolist() == [1.0] * 4 and dn.tolist() == [True, False, False, True]
+    assert o.shape == (1, 4, 3) and torch.equal(o[0], obs) and r[0].tolist() == [1.0] * 4 and dn[0].tolist() == [True, False, False, True]
     assert g.bytes_per_gather == 4 * 5 * 4
     g.launch([obs[:, :1], obs[:, 1:]], torch.ones(4), torch.zeros(4))     # obs given in pieces
-    assert torch.equal(g.wait()[0], obs)
+    assert torch.equal(g.wait()[0][0], obs)
     with pytest.raises(ValueError):
         g.launch(torch.zeros(3, 3), torch.ones(3), torch.zeros(3))
