@@ -236,3 +236,24 @@ def test_env_minor_input_cache_rules():
     for _ in range(3 * ops._MINOR_CACHE_SLOTS):
         ops._env_minor_cached(m, "mocap_pos", torch.zeros(8, 3), True, torch.float32)
     assert len(m._minor_cache) <= ops._MINOR_CACHE_SLOTS
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours): one JSON line with the contract's keys, the
+    metric / unit / workload of our own arm, zero transfer bytes; non-zero ranks of a torchrun launch print nothing."""
+    import json
+    import subprocess
+    import sys
+
+    cmd = [sys.executable, os.path.join(util.ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+           "--model", "halfcheetah", "--cpu-batch", "64"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=util.ROOT).stdout.strip().splitlines()
+    assert len(out) == 1
+    line = json.loads(out[0])
+    assert line["impl"] == "reference" and line["metric"] == "env-steps/sec" and line["unit"] == "env-steps/s"
+    assert line["higher_is_better"] is True and line["value"] > 0 and line["config"]["workload"].startswith("halfcheetah")
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    silent = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=util.ROOT, env=env)
+    assert silent.returncode == 0 and silent.stdout.strip() == ""
