@@ -123,6 +123,11 @@ class ObsGather:
             self.stream.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(self.stream):
                 self._pack_and_gather(parts, reward, done)
+            for t in (*parts, reward, done):   # the caching allocator must not recycle the inputs before the side stream has read them
+                try:
+                    t.record_stream(self.stream)
+                except RuntimeError:           # memory not owned by the caching allocator
+                    pass
         else:
             self._pack_and_gather(parts, reward, done)
 
