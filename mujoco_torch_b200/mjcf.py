@@ -863,7 +863,18 @@ class Compiler:
                 s_ = _f(a.get("solimp"), None, np.zeros(0))
                 si[: s_.size] = s_
                 e["solimp"] = si
-                if ee.tag in ("connect", "weld"):
+                if ee.tag in ("connect", "weld") and "site1" in a:
+                    # Site semantic (MuJoCo >= 3.1): the objects are sites, eq_objtype = mjOBJ_SITE and the anchors / relative pose
+                    # come from the site frames at run time, so eq_data carries only the torque scale.  NOTE: the reference ignores
+                    # eq_objtype and indexes *bodies* with these ids (device.py:306-307, constraint.py:116-212); device_put keeps
+                    # that behaviour for parity and refuses ids that are not valid body ids.
+                    if "site2" not in a or "body1" in a or "body2" in a:
+                        raise ValueError(f"equality {ee.tag}: site1 and site2 must be given together, without body1 / body2")
+                    e.update(type=int(EqType.CONNECT if ee.tag == "connect" else EqType.WELD), obj1=name2id["site"][a["site1"]],
+                             obj2=name2id["site"][a["site2"]], objtype=int(ObjType.SITE))
+                    if ee.tag == "weld":
+                        data[10] = float(a.get("torquescale", 1))
+                elif ee.tag in ("connect", "weld"):
                     b1 = name2id["body"][a["body1"]]
                     b2 = name2id["body"][a["body2"]] if "body2" in a else 0
                     e.update(type=int(EqType.CONNECT if ee.tag == "connect" else EqType.WELD), obj1=b1, obj2=b2,
@@ -1411,7 +1422,9 @@ def set_const(m: MjModelLite) -> None:
 
 
 def from_xml_string(xml: str, basedir: str = ".") -> MjModelLite:
-    root = ET.fromstring(xml)
+    # MuJoCo's parser (tinyxml2) accepts "--" inside comments (ASCII-art tables in the reference's satellite_small.xml); expat
+    # does not.  Comments carry no model content, so they are dropped before parsing.
+    root = ET.fromstring(re.sub(r"<!--.*?-->", "", xml, flags=re.S))
     if root.tag != "mujoco":
         raise ValueError("root element must be <mujoco>")
     return Compiler(root, basedir).compile()

@@ -82,6 +82,11 @@ def _validate(mj):
     for t in np.asarray(mj.eq_type):
         if int(t) not in (EqType.CONNECT, EqType.WELD, EqType.JOINT):
             raise NotImplementedError(f"{EqType(int(t))!r} not implemented.")
+    # Site-based connect / weld (eq_objtype = mjOBJ_SITE = 6): the reference never reads eq_objtype and indexes bodies with the
+    # object ids (device.py:306-307).  Kept for parity; ids that are not body ids would index out of range there.
+    for i, t in enumerate(np.asarray(mj.eq_type)):
+        if int(t) in (EqType.CONNECT, EqType.WELD) and max(int(mj.eq_obj1id[i]), int(mj.eq_obj2id[i])) >= int(mj.nbody):
+            raise NotImplementedError(f"equality {i}: object id beyond nbody (site-based equalities are indexed as bodies, like the reference)")
     for t in np.asarray(mj.actuator_trntype):
         if int(t) not in (TrnType.JOINT, TrnType.JOINTINPARENT, TrnType.TENDON):
             raise NotImplementedError(f"{TrnType(int(t))!r} not implemented.")

@@ -17,7 +17,7 @@ OUT = os.path.join(ROOT, "assets", "models")
 os.makedirs(OUT, exist_ok=True)
 
 MODELS = ["cartpole", "humanoid", "halfcheetah", "ant", "hopper", "walker2d", "swimmer", "convex", "pendula", "equality",
-          "frictionloss_dof"]
+          "frictionloss_dof", "satellite_small", "satellite_large"]
 for name in MODELS:
     path = os.path.join(SRC, name + ".xml")
     try:

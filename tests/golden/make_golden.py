@@ -91,6 +91,12 @@ CASES = [
     ("shapes", "shapes", {}, 4, -1.0, 1),
     ("shapes_elliptic", "shapes", {"cone": 1}, 6, -1.0, 1),
     ("stack_rk4", "stack", {}, 8, -2.0, 1),
+    # the reference's own equality.xml (site-based weld / connect, inactive; joint equality; box, sphere and plane contacts).
+    # Recorded into cpu_only/: it pins the oracle now, the CUDA path joins once it has been run against it on a GPU.
+    ("cpu_only/equality_sites", "equality", {}, 4, 0.3, 1),
+    # the reference's control-moment-gyro satellites (free-floating, no contacts: smooth dynamics + actuation only)
+    ("cpu_only/satellite_small", "satellite_small", {}, 3, 0.0, 2),
+    ("cpu_only/satellite_large", "satellite_large", {}, 3, 0.0, 2),
 ]
 
 
@@ -124,6 +130,7 @@ def run_case(name, model, opt, B, drop, nsteps):
     for k, v in cons.items():
         save["contact_" + k] = np.stack(v)
     path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
     np.savez_compressed(path, **save)
     print(f"{name}: B={B} steps={nsteps} qpos[0,:3]={save['out_qpos'][0, :3]} -> {os.path.relpath(path, ROOT)}")
 

@@ -17,6 +17,8 @@ import torch
 from tests import util
 
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz")))
+# recordings that so far pin the oracle only: the CUDA path has not been run against them on a GPU yet (golden/cpu_only/)
+GOLDEN_CPU_ONLY = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cpu_only", "*.npz")))
 FIELDS = ["qpos", "qvel", "qacc", "qacc_warmstart", "act", "time", "xpos", "xquat", "xmat", "xipos", "ximat", "xanchor", "xaxis",
           "geom_xpos", "geom_xmat", "subtree_com", "cinert", "crb", "cdof", "cdof_dot", "cvel", "qM", "qLD", "actuator_length",
           "actuator_moment", "actuator_velocity", "actuator_force", "qfrc_bias", "qfrc_passive", "qfrc_actuator", "qfrc_smooth",
@@ -103,7 +105,7 @@ def _recorded_branch(z, mj, get_contact, get):
     return sel, {k: (z[k][sel] if batched(k) else z[k]) for k in z.files}
 
 
-@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+@pytest.mark.parametrize("path", GOLDEN + GOLDEN_CPU_ONLY, ids=[os.path.basename(p)[:-4] for p in GOLDEN + GOLDEN_CPU_ONLY])
 def test_oracle_matches_reference(path):
     z, mj = _load(path)
     mo, do = util.run_oracle(mj, z["in_qpos"], z["in_qvel"], z["in_ctrl"], torch.float64, nsteps=int(z["nsteps"]),

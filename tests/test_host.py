@@ -15,7 +15,8 @@ from oracle import model as om
 from tests import util
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-MODELS = ["cartpole", "humanoid", "halfcheetah", "ant", "ant_zoo", "hopper", "walker2d", "swimmer", "pendula", "frictionloss_dof", "convex"]
+MODELS = ["cartpole", "humanoid", "halfcheetah", "ant", "ant_zoo", "hopper", "walker2d", "swimmer", "pendula", "frictionloss_dof", "convex",
+          "equality", "satellite_small", "satellite_large", "equality_bodies", "sink", "shapes", "stack"]
 
 
 def test_library_exports_every_declared_symbol():
@@ -257,3 +258,27 @@ def test_bench_reference_arm_prints_one_contract_line():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
     silent = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=util.ROOT, env=env)
     assert silent.returncode == 0 and silent.stdout.strip() == ""
+
+
+def test_mjcf_site_equalities_and_comment_tables():
+    """MJCF surface of the reference's own test files: site-based weld / connect (`equality.xml`: eq_objtype = mjOBJ_SITE, ids
+    are site ids, only the torque scale in eq_data) and comments containing "--" (`satellite_small.xml`), which expat rejects."""
+    xml = """<mujoco><!-- table  | a -- b |
+      ------+------ -->
+      <worldbody>
+        <body name="a" pos="0 0 1"><freejoint/><geom size="0.1"/><site name="sa" pos="0.1 0 0"/></body>
+        <body name="b" pos="0 0 2"><freejoint/><geom size="0.1"/><site name="sb" pos="0 0.1 0"/></body>
+      </worldbody>
+      <equality>
+        <weld name="w" site1="sa" site2="sb" torquescale="2" active="false"/>
+        <connect name="c" site1="sb" site2="sa"/>
+        <connect name="cb" body1="a" body2="b" anchor="0 0 0.5"/>
+      </equality></mujoco>"""
+    mj = mt.mjcf.load(xml)
+    assert mj.eq_type.tolist() == [1, 0, 0] and mj.eq_objtype.tolist() == [6, 6, 1]
+    assert mj.eq_obj1id.tolist() == [0, 1, 1] and mj.eq_obj2id.tolist() == [1, 0, 2] and mj.eq_active0.tolist() == [0, 1, 1]
+    assert mj.eq_data[0, 10] == 2.0 and not mj.eq_data[0, :10].any() and not mj.eq_data[1].any()
+    assert np.allclose(mj.eq_data[2, :3], [0, 0, 0.5]) and np.allclose(mj.eq_data[2, 3:6], [0, 0, -0.5])
+    mt.device_put(mj)   # ids are valid body ids: accepted (indexed as bodies, like the reference)
+    with pytest.raises(ValueError, match="site1 and site2"):
+        mt.mjcf.load(xml.replace('site1="sb" site2="sa"', 'site1="sb" body2="a"'))
