@@ -83,7 +83,8 @@ int mjt_step_launches(const mjtModel* m);
 void mjt_profile_begin(void);
 int mjt_profile_end(char* buf, size_t nbuf);
 
-/* Launch configuration of the solver kernel (environments = warps per CTA, dynamic shared memory bytes). */
+/* Launch configuration of the solver launch that visits every env (environments per CTA, dynamic shared memory bytes): the
+ * live-tile pass for models that have one (many, mostly inactive constraint rows), else the single full-tile launch. */
 int mjt_solve_config(const mjtModel* m, int* envs_per_cta, int* smem_bytes);
 
 /* Measured FMA-pipe throughput of the current device in TFLOP/s (FMA = 2 flops), FP64 if is_f64 else FP32: register-resident
