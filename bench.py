@@ -65,6 +65,11 @@ def algorithmic_flops(mj, mx):
     return (4 * fwd if integ == 1 else fwd + refactor)
 
 
+def stock_options(args):
+    """True when the run uses the XML's own integrator / solver / cone (what the committed ncu captures were taken on)."""
+    return args.integrator is None and args.solver is None and args.cone is None
+
+
 def load_model(name, args):
     from mujoco_torch_b200.mjmodel import MjModelLite
 
@@ -92,6 +97,19 @@ def measured_traffic(kernel, model, dtype, B):
         return t.get(f"{kernel}:{model}:{dtype}:{B}")
     except Exception:  # noqa: BLE001
         return None
+
+
+def issue_roofline(kernel, model, dtype, B, kernel_ms, sm_count, sm_mhz):
+    """Issue-slot roofline of the dominant kernel: warp instructions per launch (ncu `smsp__inst_executed.sum` of the committed
+    capture, profiles/traffic.json) over the live launch time, against the SMs' issue peak (4 schedulers x 1 warp instruction
+    per clock).  This is the roof k_solve actually runs under; None when no capture matches the workload."""
+    inst = measured_traffic("inst:" + kernel, model, dtype, B)
+    if not inst or not kernel_ms or not sm_count or not sm_mhz:
+        return None
+    ach = inst / (kernel_ms * 1e-3) / 1e9
+    peak = sm_count * 4 * sm_mhz * 1e6 / 1e9
+    return {"bound": "issue", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "G warp-instr/s", "frac": ach / peak,
+            "warp_instructions_per_launch": inst, "source": "ncu smsp__inst_executed.sum (profiles/) / live CUDA-event launch time"}
 
 
 class ClockSampler:
@@ -334,6 +352,14 @@ def main():
                            "scope": "whole step; solver body counted once, line search at ls_iterations"}
     except Exception as exc:  # noqa: BLE001
         roofline["fma"] = {"error": str(exc)}
+
+    try:
+        issue = issue_roofline(top, args.model, args.dtype, B, kern[top] if stock_options(args) else None,
+                               torch.cuda.get_device_properties(dev).multi_processor_count, (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz"))
+        if issue:
+            roofline["issue"] = issue
+    except Exception:  # noqa: BLE001
+        pass
 
     # ---- end to end through the public API from pinned host buffers
     e2e = None
