@@ -97,11 +97,18 @@ CASES = [
     # the reference's control-moment-gyro satellites (free-floating, no contacts: smooth dynamics + actuation only)
     ("cpu_only/satellite_small", "satellite_small", {}, 3, 0.0, 2),
     ("cpu_only/satellite_large", "satellite_large", {}, 3, 0.0, 2),
+    # step(..., fixed_iterations=True): exactly `iterations` solver and `ls_iterations` line-search iterations, no termination
+    # test (solver.py:484-487, 536-537).  "fixed_iterations" is not a model option: it is passed to step() and stripped here.
+    ("cpu_only/halfcheetah_fixed_iterations", "halfcheetah", {"iterations": 6, "ls_iterations": 5, "fixed_iterations": 1}, 4, 0.6, 1),
+    # CG run past convergence: the early-exit path stops at `tolerance` (2e-7 relative away in qacc), the fixed path keeps going.
+    # (A short unconverged CG run is not usable as a pin: the oracle's own answer moves by 3e-3 under 2e-16 input perturbations.)
+    ("cpu_only/ant_zoo_cg_fixed_iterations", "ant_zoo", {"cone": 1, "solver": 1, "iterations": 60, "ls_iterations": 20, "fixed_iterations": 1}, 4, 0.2, 1),
 ]
 
 
 def run_case(name, model, opt, B, drop, nsteps):
-    lite = util.load_model(model, **opt)
+    fixed = bool(opt.get("fixed_iterations", 0))
+    lite = util.load_model(model, **{k: v for k, v in opt.items() if k != "fixed_iterations"})
     qpos, qvel, ctrl = util.seeded_state(lite, B, drop=drop)
     act = None
     if drop < -2.5:
@@ -117,7 +124,7 @@ def run_case(name, model, opt, B, drop, nsteps):
         if act is not None:
             d = d.replace(act=torch.as_tensor(act[b]))
         for _ in range(nsteps):
-            d = ref_forward.step(mx, d)
+            d = ref_forward.step(mx, d, fixed_iterations=fixed)
         for k in OUT_FIELDS:
             outs[k].append(np.asarray(getattr(d, k)))
         for k in CONTACT_FIELDS:

@@ -29,8 +29,13 @@ TOL = 1e-9
 def _load(path):
     z = np.load(path)
     opt = {str(k): (int(v) if float(v).is_integer() else float(v)) for k, v in zip(z["opt_keys"], z["opt_vals"])}
+    opt.pop("fixed_iterations", None)   # an argument of step(), recorded next to the model options (see _fixed)
     mj = util.load_model(str(z["model"]), **opt)
     return z, mj
+
+
+def _fixed(z):
+    return bool(dict(zip((str(k) for k in z["opt_keys"]), z["opt_vals"])).get("fixed_iterations", 0))
 
 
 def _rel(a, b):
@@ -109,7 +114,7 @@ def _recorded_branch(z, mj, get_contact, get):
 def test_oracle_matches_reference(path):
     z, mj = _load(path)
     mo, do = util.run_oracle(mj, z["in_qpos"], z["in_qvel"], z["in_ctrl"], torch.float64, nsteps=int(z["nsteps"]),
-                             act=z["in_act"] if "in_act" in z.files else None)
+                             act=z["in_act"] if "in_act" in z.files else None, fixed_iterations=_fixed(z))
     ocon = {"dist": "contact_dist", "pos": "contact_pos", "frame": "contact_frame"}
 
     def get_contact(k):
@@ -137,3 +142,16 @@ def test_cuda_matches_reference(path):
                            act=z["in_act"] if "in_act" in z.files else None)
     sel, zs = _recorded_branch(z, mj, lambda k: getattr(dc.contact, k).cpu().numpy(), lambda k: getattr(dc, k).cpu().numpy())
     _check(zs, lambda k: getattr(dc, k).cpu().numpy()[sel], lambda k: getattr(dc.contact, k).cpu().numpy()[sel], "cuda")
+
+
+def test_fixed_iterations_recording_differs_from_early_exit():
+    """The CG `fixed_iterations=True` recording must tell the two solver modes apart: the oracle's early-exit path stops at
+    `tolerance` and lands ~4e-6 away from it, far beyond the 1e-9 bar the fixed path is held to above."""
+    path = [p for p in GOLDEN_CPU_ONLY if p.endswith("ant_zoo_cg_fixed_iterations.npz")][0]
+    z, mj = _load(path)
+    assert _fixed(z)
+    _, early = util.run_oracle(mj, z["in_qpos"], z["in_qvel"], z["in_ctrl"], torch.float64, fixed_iterations=False)
+    _, fixed = util.run_oracle(mj, z["in_qpos"], z["in_qvel"], z["in_ctrl"], torch.float64, fixed_iterations=True)
+    scale = np.abs(z["out_qfrc_smooth"]).max()
+    assert np.abs(early.qfrc_constraint.numpy() - z["out_qfrc_constraint"]).max() / scale > 1e-7
+    assert np.abs(fixed.qfrc_constraint.numpy() - z["out_qfrc_constraint"]).max() / scale < 1e-9

@@ -95,7 +95,7 @@ def sink_state(mj, B, seed=9):
     return qpos, qvel, rng.uniform(-1.5, 1.5, size=(B, mj.nu)), rng.uniform(-0.6, 0.6, size=(B, mj.na))
 
 
-def run_oracle(mj, qpos, qvel, ctrl, dtype=torch.float64, nsteps=1, warm=None, act=None):
+def run_oracle(mj, qpos, qvel, ctrl, dtype=torch.float64, nsteps=1, warm=None, act=None, fixed_iterations=False):
     from oracle import forward as of
     from oracle import model as om
 
@@ -107,7 +107,7 @@ def run_oracle(mj, qpos, qvel, ctrl, dtype=torch.float64, nsteps=1, warm=None, a
     if act is not None:
         d.act = torch.as_tensor(act).to(dtype)
     for _ in range(nsteps):
-        d = of.step(m, d)
+        d = of.step(m, d, fixed_iterations=fixed_iterations)
     return m, d
 
 
