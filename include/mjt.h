@@ -59,21 +59,40 @@ const char* mjt_last_error(void);
 int mjt_model_create(const void* blob_host, size_t nbytes, int device, mjtModel** out);
 void mjt_model_destroy(mjtModel* m);
 
-/* Sizes a caller needs to allocate buffers: words per env of the output Data buffer, of the scratch buffer
- * (RK4 stage buffer + accumulators; 0 for the other integrators) and sizeof(compute dtype). */
+/* Output layout of the model, fixed by the blob it was created from (mujoco_torch_b200/layout.py):
+ *   0 = full:  `out` receives the complete new Data, state and every derived field, like the reference's step;
+ *   1 = state: `out` receives only qpos, qvel, act, time, qacc, qacc_warmstart, act_dot, sensordata (+ qfrc_constraint for
+ *              a model without constraint rows); everything derived lives in the `work` buffer the caller lends to the call,
+ *              in the reduced form the next kernel reads (packed qM, support-compacted efc_J), and what nothing reads is
+ *              never written.  Same kernels, same arithmetic: the state fields are bit-identical to layout 0. */
+int mjt_model_layout(const mjtModel* m);
+
+/* Sizes a caller needs to allocate buffers: words per env of the `out` buffer, of the `work` buffer (state layout: the
+ * workspace; RK4: one more stage buffer + accumulators; 0 if neither applies) and sizeof(compute dtype). */
 int mjt_model_data_words(const mjtModel* m);
 int mjt_model_scratch_words(const mjtModel* m);
 int mjt_model_dtype_size(const mjtModel* m);
-/* Word offset and word count of a named Data field inside the output buffer; -1 if unknown. */
+/* Word offset and word count of a named Data field inside the `out` buffer; -1 if unknown or not part of this layout. */
 int mjt_model_field(const mjtModel* m, const char* name, int* offset, int* words);
 
-/* step(model, data): reference forward.step :463-496.  `out` is a (data_words, nenv) device buffer that receives
- * the complete new Data (state + every derived field); `scratch` is (scratch_words, nenv) or NULL when
- * scratch_words == 0.  The input is never modified.  Launches on `stream` (a cudaStream_t) and returns immediately. */
-int mjt_step(const mjtModel* m, const mjtStateIn* in, void* out, void* scratch, int nenv, void* stream);
+/* Call flags.  FIXED_ITERATIONS = the reference's `fixed_iterations=True` argument of step / forward / solve
+ * (forward.py:463, solver.py:484-487,536-537): the solver runs exactly opt.iterations bodies and its line search
+ * exactly opt.ls_iterations, with no termination test.  UPTO_* (mjt_forward, full layout only) stop the pass after the
+ * named stage -- what the reference's stage functions (kinematics ... make_constraint, __init__.py:41-108) need. */
+enum {
+  MJT_FLAG_FIXED_ITERATIONS = 1,
+  MJT_FLAG_UPTO_SMOOTH = 2,      /* kinematics .. rne, passive, actuation, qfrc_smooth (k_smooth) */
+  MJT_FLAG_UPTO_COLLISION = 4,   /* + contacts (k_collision) */
+  MJT_FLAG_UPTO_CONSTRAINT = 8   /* + efc rows (k_constraint) */
+};
 
-/* forward(model, data): reference forward.forward :373-401 (no integration). */
-int mjt_forward(const mjtModel* m, const mjtStateIn* in, void* out, int nenv, void* stream);
+/* step(model, data, fixed_iterations): reference forward.step :463-496.  `out` is a (data_words, nenv) device buffer
+ * that receives the new Data in the model's layout; `work` is (scratch_words, nenv) or NULL when scratch_words == 0.
+ * The input is never modified.  Launches on `stream` (a cudaStream_t) and returns immediately. */
+int mjt_step(const mjtModel* m, const mjtStateIn* in, void* out, void* work, int nenv, int flags, void* stream);
+
+/* forward(model, data, fixed_iterations): reference forward.forward :373-401 (no integration, no _check_state). */
+int mjt_forward(const mjtModel* m, const mjtStateIn* in, void* out, void* work, int nenv, int flags, void* stream);
 
 /* Number of kernel launches mjt_step issues for this model (used by bench.py's gpu_launches claim). */
 int mjt_step_launches(const mjtModel* m);

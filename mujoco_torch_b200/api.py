@@ -74,9 +74,29 @@ def make_data(m: Model) -> Data:
     return Data(f, dict(ne=m.ne, nf=m.nf, nl=m.nl, ncon=m.ncon, nefc=m.nefc))
 
 
-def _run(m: Model, d: Data, mode: int) -> Data:
+def _run_state(m: Model, d: Data, mode: int, args, lead, flat) -> Data:
+    """outputs="state": only the state fields come back (views of one small env-minor buffer); every derived field of the
+    returned Data is the input's, untouched."""
+    out = torch.ops.mjt.run(m._id, mode | ops.MODE_STATE, *args)
+    if flat:
+        out = out.reshape(*lead, out.shape[-1])
+    sl = m.state_layout
+    new = dict(d._fields)
+    for name, off in sl["pub_off"].items():
+        if off < 0:
+            continue
+        shp = m.field_shape[name]
+        n = int(np.prod(shp)) if shp else 1
+        v = out[..., off:off + n]
+        new[name] = v.reshape(tuple(lead) + tuple(shp)) if len(shp) != 1 else v
+    return Data(new, dict(d._meta))
+
+
+def _run(m: Model, d: Data, mode: int, outputs: str = "full") -> Data:
     if not isinstance(m, Model):
         raise TypeError("first argument must be a mujoco_torch_b200 Model (see device_put)")
+    if outputs not in ("full", "state"):
+        raise ValueError(f"outputs must be 'full' or 'state', got {outputs!r}")
     lead = tuple(d.qpos.shape[:-1])
     flat = len(lead) > 1
     args = []
@@ -89,6 +109,8 @@ def _run(m: Model, d: Data, mode: int) -> Data:
         if flat:
             t = t.reshape(-1, t.shape[-1])
         args.append(t)
+    if outputs == "state":
+        return _run_state(m, d, mode, args, lead, flat)
     out = torch.ops.mjt.run(m._id, mode, *args)
     if flat:
         out = out.reshape(*lead, out.shape[-1])
@@ -121,22 +143,26 @@ def _run(m: Model, d: Data, mode: int) -> Data:
     return Data(new, meta)
 
 
-def step(m: Model, d: Data, fixed_iterations: bool = False) -> Data:
+def step(m: Model, d: Data, fixed_iterations: bool = False, *, outputs: str | None = None) -> Data:
     """Advance the simulation by one timestep (reference forward.step :463-496).
 
-    ``fixed_iterations`` exists for signature compatibility; the kernels always implement true per-env early exit,
-    which is what the reference computes in eager mode.
+    ``fixed_iterations=True`` runs the constraint solver for exactly ``opt.iterations`` iterations and its line search for
+    exactly ``opt.ls_iterations`` (no termination test), like the reference's static-graph mode (solver.py:484-487,
+    536-537); the default is per-env early exit, which is what the reference computes in eager mode.
+
+    ``outputs`` (an extension; default ``"full"``, or the model's ``default_outputs``): ``"full"`` materialises every field
+    of ``Data`` like the reference; ``"state"`` produces only ``qpos, qvel, act, time, qacc, qacc_warmstart, act_dot,
+    sensordata`` -- bit-identical values -- and leaves every derived field of the returned ``Data`` as it was in ``d``.
+    A rollout that only feeds the state back in (and reads observations from it) moves 20x less memory per step.
     """
-    if fixed_iterations:
-        raise NotImplementedError("fixed_iterations=True (static-graph mode of the reference) is not needed by the CUDA path")
-    return _run(m, d, ops.MODE_STEP)
+    mode = ops.MODE_STEP | (ops.MODE_FIXED if fixed_iterations else 0)
+    return _run(m, d, mode, outputs or getattr(m, "default_outputs", "full"))
 
 
-def forward(m: Model, d: Data, fixed_iterations: bool = False) -> Data:
+def forward(m: Model, d: Data, fixed_iterations: bool = False, *, outputs: str | None = None) -> Data:
     """Forward dynamics without integration (reference forward.forward :373-401)."""
-    if fixed_iterations:
-        raise NotImplementedError("fixed_iterations=True is not supported")
-    return _run(m, d, ops.MODE_FORWARD)
+    mode = ops.MODE_FORWARD | (ops.MODE_FIXED if fixed_iterations else 0)
+    return _run(m, d, mode, outputs or "full")
 
 
 # ---- stage-level API (reference __init__.py:41-108): each stage returns `d` with that stage's write-set refreshed
@@ -164,13 +190,23 @@ _STAGE_FIELDS = {
 }
 
 
+# how far the fused forward pass has to run for each stage (include/mjt.h MJT_FLAG_UPTO_*): 1 = k_smooth, 2 = + k_collision,
+# 3 = + k_constraint, 0 = the whole pass (stages whose outputs come from the solver kernel: factorisation, solve, sensors)
+_STAGE_UPTO = {"kinematics": 1, "com_pos": 1, "crb": 1, "tendon": 1, "transmission": 1, "com_vel": 1, "rne": 1, "passive": 1,
+               "fwd_velocity": 1, "fwd_actuation": 1, "collision": 2, "make_constraint": 3}
+
+
 def _make_stage(name):
+    upto = _STAGE_UPTO.get(name, 0)
+
     def stage(m: Model, d: Data) -> Data:
-        full = forward(m, d)
+        full = _run(m, d, ops.MODE_FORWARD | (upto << ops.MODE_UPTO_SHIFT), "full")
         return d.replace(**{k: full._fields[k] for k in _STAGE_FIELDS[name]})
 
     stage.__name__ = name
-    stage.__doc__ = f"Stage ``{name}``: refreshes {_STAGE_FIELDS[name]} from the state in ``d``."
+    stage.__doc__ = (f"Stage ``{name}``: recomputed FROM THE STATE in ``d`` (qpos, qvel, act, ctrl, applied forces, mocap) by the fused "
+                     f"kernels{', stopping after stage ' + str(upto) if upto else ''}, then {_STAGE_FIELDS[name]} are refreshed in the "
+                     "returned Data.  Unlike the reference's stage functions it does not consume derived fields the caller edited in ``d``.")
     return stage
 
 

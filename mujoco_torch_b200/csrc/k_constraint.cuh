@@ -34,15 +34,53 @@ __device__ __forceinline__ void kbi(const ModelView<T>& m, const T* solref, cons
   *k = kk; *b = bb; *imp = im;
 }
 
+// Jacobian writer of one source.  Full layout: dense efc_J rows (every column written, zeros included).  State layout: efc_J
+// is stored compacted to the source's static column support (model.py _row_supports; the form k_solve keeps in shared
+// memory): entry (row, support position k) at row_jadr[row] + k.  Columns outside the support are exactly zero by construction
+// and are not stored.  Writers visit the columns of a row in ascending order, so the support position is a running cursor.
 template <typename T>
 struct RowOut {
   const ModelView<T>& m;
   const EnvBuf<T>& d;
   int nv;
-  __device__ __forceinline__ void J(int row, int i, T v) const { d.set(m.D(D_efc_J) + row * nv + i, v); }
-  __device__ __forceinline__ void zero(int row0, int nrows) const {
-    for (int r = row0; r < row0 + nrows; ++r)
-      for (int i = 0; i < nv; ++i) J(r, i, T(0));
+  bool compact;
+  const int* col;   // support columns of this source (ascending)
+  int ns, row0, jadr0;
+  int cur;          // cursor into col
+  __device__ __forceinline__ void begin(int s) {
+    compact = m.h(H_layout_state) != 0;
+    col = m.I(I_sup_col) + m.I(I_src_cadr)[s];
+    ns = m.I(I_src_nsup)[s];
+    row0 = m.I(I_src_row)[s];
+    jadr0 = m.I(I_row_jadr)[row0];
+    cur = 0;
+  }
+  // true when column i has to be produced (dense: always; compact: only support columns); positions the cursor on it
+  __device__ __forceinline__ bool want(int i) {
+    if (!compact) return true;
+    while (cur < ns && col[cur] < i) ++cur;
+    return cur < ns && col[cur] == i;
+  }
+  __device__ __forceinline__ void J(int row, int i, T v) const {
+    if (compact) d.set(m.D(D_efc_J) + jadr0 + (row - row0) * ns + cur, v);
+    else d.set(m.D(D_efc_J) + row * nv + i, v);
+  }
+  // random-access variant for the few writers that do not walk the columns in order
+  __device__ __forceinline__ void Jat(int row, int i, T v) {
+    if (compact) {
+      for (int k = 0; k < ns; ++k)
+        if (col[k] == i) d.set(m.D(D_efc_J) + jadr0 + (row - row0) * ns + k, v);
+    } else {
+      d.set(m.D(D_efc_J) + row * nv + i, v);
+    }
+  }
+  __device__ __forceinline__ void zero(int r0, int nrows) const {
+    if (compact) {
+      for (int k = 0; k < nrows * ns; ++k) d.set(m.D(D_efc_J) + jadr0 + (r0 - row0) * ns + k, T(0));
+      return;
+    }
+    for (int r = r0; r < r0 + nrows; ++r)
+      for (int i = 0; i < nv; ++i) d.set(m.D(D_efc_J) + r * nv + i, T(0));
   }
   // finish one row: impedance, regulariser, reference acceleration
   __device__ __forceinline__ void finish(int row, T jv, T pos, T pos_norm, T invweight, const T* solref, const T* solimp, T floss) const {
@@ -51,7 +89,7 @@ struct RowOut {
     const T r = t_max(invweight * (T(1) - imp) / imp, T(MJT_MINVAL));
     d.set(m.D(D_efc_D) + row, T(1) / r);
     d.set(m.D(D_efc_aref) + row, -b * jv - k * imp * pos);
-    d.set(m.D(D_efc_frictionloss) + row, floss);
+    if (m.D(D_efc_frictionloss) >= 0) d.set(m.D(D_efc_frictionloss) + row, floss);
   }
 };
 
@@ -74,7 +112,8 @@ template <typename T>
 __device__ void constraint_source(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T>& d, size_t B, int env, int s) {
   const int type = m.I(I_src_type)[s], id = m.I(I_src_id)[s], row0 = m.I(I_src_row)[s];
   const int nv = m.h(H_nv);
-  const RowOut<T> out{m, d, nv};
+  RowOut<T> out{m, d, nv};
+  out.begin(s);
   const int oQpos = m.D(D_qpos), oQvel = m.D(D_qvel), oCom = m.D(D_subtree_com);
   const int* body_root = m.I(I_body_rootid);
   const T* dof_iw = m.F(F_dof_invweight0);
@@ -91,7 +130,7 @@ __device__ void constraint_source(const ModelView<T>& m, const MjtIn& in, const 
       live = act != T(0);
       pos *= act;
       out.zero(row0, 1);
-      out.J(row0, da, val * act);
+      out.Jat(row0, da, val * act);
       out.finish(row0, val * act * d.get(oQvel + da), pos, pos, dof_iw[da], m.F(F_jnt_solref) + 2 * id, m.F(F_jnt_solimp) + 5 * id, T(0));
     } break;
     case SRC_LIM_BALL: {  // :302-335
@@ -107,7 +146,7 @@ __device__ void constraint_source(const ModelView<T>& m, const MjtIn& in, const 
       out.zero(row0, 1);
       const T j3[3] = {-axis.x * act, -axis.y * act, -axis.z * act};
       T jv = 0;
-      for (int k = 0; k < 3; ++k) { out.J(row0, da + k, j3[k]); jv += j3[k] * d.get(oQvel + da + k); }
+      for (int k = 0; k < 3; ++k) { out.Jat(row0, da + k, j3[k]); jv += j3[k] * d.get(oQvel + da + k); }
       out.finish(row0, jv, pos, pos, dof_iw[da], m.F(F_jnt_solref) + 2 * id, m.F(F_jnt_solimp) + 5 * id, T(0));
     } break;
     case SRC_LIM_TEN: {  // :375-405
@@ -120,6 +159,7 @@ __device__ void constraint_source(const ModelView<T>& m, const MjtIn& in, const 
       pos *= act;
       T jv = 0;
       for (int i = 0; i < nv; ++i) {
+        if (!out.want(i)) continue;
         const T v = d.get(m.D(D_ten_J) + id * nv + i) * sign;
         out.J(row0, i, v);
         jv += v * d.get(oQvel + i);
@@ -128,12 +168,13 @@ __device__ void constraint_source(const ModelView<T>& m, const MjtIn& in, const 
     } break;
     case SRC_FRIC_DOF: {  // :215-251
       out.zero(row0, 1);
-      out.J(row0, id, T(1));
+      out.Jat(row0, id, T(1));
       out.finish(row0, d.get(oQvel + id), T(0), T(0), dof_iw[id], m.F(F_dof_solref) + 2 * id, m.F(F_dof_solimp) + 5 * id, m.F(F_dof_frictionloss)[id]);
     } break;
     case SRC_FRIC_TEN: {
       T jv = 0;
       for (int i = 0; i < nv; ++i) {
+        if (!out.want(i)) continue;
         const T v = d.get(m.D(D_ten_J) + id * nv + i);
         out.J(row0, i, v);
         jv += v * d.get(oQvel + i);
@@ -160,8 +201,8 @@ __device__ void constraint_source(const ModelView<T>& m, const MjtIn& in, const 
       for (int k = 0; k < 5; ++k) poly += data[k] * pw[k];
       out.zero(row0, 1);
       T jv = 0;
-      out.J(row0, da1, T(1) * active);
-      out.J(row0, da2, -deriv * active);  // same dof: the second write wins, as in the reference's scatter order
+      out.Jat(row0, da1, T(1) * active);
+      out.Jat(row0, da2, -deriv * active);  // same dof: the second write wins, as in the reference's scatter order
       jv = (da1 == da2) ? (-deriv * active * d.get(oQvel + da2)) : (active * d.get(oQvel + da1) - deriv * active * d.get(oQvel + da2));
       const T pos = (pos1 - ref1 - poly) * active;
       out.finish(row0, jv, pos, pos, dof_iw[da1] + dof_iw[da2] * has2, m.F(F_eq_solref) + 2 * id, m.F(F_eq_solimp) + 5 * id, T(0));
@@ -204,6 +245,7 @@ __device__ void constraint_source(const ModelView<T>& m, const MjtIn& in, const 
         crot = V3<T>(cr.x, cr.y, cr.z);
       }
       for (int i = 0; i < nv; ++i) {
+        if (!out.want(i)) continue;
         const bool in1 = dof_in_body(m, b1, i), in2 = dof_in_body(m, b2, i);
         V3<T> p(0, 0, 0), r(0, 0, 0);
         if (in1 || in2) {
@@ -260,6 +302,7 @@ __device__ void constraint_source(const ModelView<T>& m, const MjtIn& in, const 
         const V3<T> off1 = pt - c1, off2 = pt - c2;
         const V3<T> f0(fr[0], fr[1], fr[2]), f1(fr[3], fr[4], fr[5]), f2(fr[6], fr[7], fr[8]);
         for (int i = 0; i < nv; ++i) {
+          if (!out.want(i)) continue;
           const bool in1 = dof_in_body(m, b1, i), in2 = dof_in_body(m, b2, i);
           T dd[6] = {0, 0, 0, 0, 0, 0};
           if (in1 != in2) {  // common ancestors cancel exactly

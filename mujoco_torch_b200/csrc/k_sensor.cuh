@@ -116,10 +116,10 @@ __device__ __forceinline__ Q4<T> sensor_quat(const ModelView<T>& m, const EnvBuf
 }
 
 template <typename T>
-__device__ void sensor_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T>& d, size_t B, int env, int stage) {
-  const int ns = m.h(H_nsensor), oS = m.D(D_sensordata);
+__device__ void sensor_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T>& d, const EnvBuf<T>& pub, size_t B, int env, int stage) {
+  const int ns = m.h(H_nsensor), oS = m.P(P_sensordata);   // sensordata lives in the caller's buffer (layout.py P table)
   if (stage == 1) {  // first stage seeds the output with the caller's sensordata (untouched slots persist)
-    for (int k = 0; k < m.h(H_nsensordata); ++k) d.set(oS + k, in_get<T>(in.sensordata, B, env, k));
+    for (int k = 0; k < m.h(H_nsensordata); ++k) pub.set(oS + k, in_get<T>(in.sensordata, B, env, k));
   }
   if (m.h(H_disableflags) & DSBL_SENSOR) return;
   const int* body_root = m.I(I_body_rootid);
@@ -242,26 +242,26 @@ __device__ void sensor_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<
       val[0] = isinf(best) ? T(-1) : best;
       dim = 1;
     }
-    for (int k = 0; k < dim; ++k) d.set(oS + adr + k, cutoff(val[k], cut, dtp));
+    for (int k = 0; k < dim; ++k) pub.set(oS + adr + k, cutoff(val[k], cut, dtp));
   }
 }
 
 template <typename T>
-__global__ void __launch_bounds__(MJT_ENV_THREADS) k_sensor(const int* __restrict__ gblob, int blob_words, MjtIn in, T* __restrict__ out, int B, int stage_mask) {
+__global__ void __launch_bounds__(MJT_ENV_THREADS) k_sensor(const int* __restrict__ gblob, int blob_words, MjtIn in, T* __restrict__ out, T* __restrict__ pubbuf, int B, int stage_mask) {
   extern __shared__ __align__(16) int smem_blob[];
   __shared__ uint64_t bar;
   stage_blob(smem_blob, &bar, gblob, blob_words);
   const ModelView<T> m = make_view<T>(smem_blob);
   const int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= B) return;
-  EnvBuf<T> d{out + env, (size_t)B};
+  EnvBuf<T> d{out + env, (size_t)B}, pub{pubbuf + env, (size_t)B};
   for (int st = 1; st <= 3; ++st)
-    if (stage_mask & (1 << st)) sensor_env<T>(m, in, d, (size_t)B, env, st);
+    if (stage_mask & (1 << st)) sensor_env<T>(m, in, d, pub, (size_t)B, env, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// RK4 sequencing (reference forward._rungekutta4 :331-370).  `t0` is the buffer of the first forward pass (it becomes
-// the returned Data), `prev` the buffer of the previous stage, `tail` the stage-input / accumulator arrays:
+// RK4 sequencing (reference forward._rungekutta4 :331-370).  `t0` is the caller's (public) buffer of the first forward pass (it
+// becomes the returned Data), `prev` the public buffer of the previous stage (fields addressed through the P table), `tail` the stage-input / accumulator arrays:
 //   tail = [kqpos nq | kqvel nv | kact na | ktime 1 | sum_qvel nv | sum_qacc nv | sum_actdot na]
 template <typename T>
 __device__ __forceinline__ void integrate_pos(const ModelView<T>& m, const EnvBuf<T>& src, int oSrc, const EnvBuf<T>& dst, int oDst,
@@ -300,43 +300,43 @@ __global__ void __launch_bounds__(MJT_ENV_THREADS) k_rk4_stage(const int* __rest
   const T h = m.opt(OPT_timestep);
   // stage in {0,1,2}: build the inputs of forward pass stage+1; stage 3: final advance
   if (stage == 0) {
-    for (int i = 0; i < nv; ++i) { tl.set(oSv + i, Bw[0] * d0.get(m.D(D_qvel) + i)); tl.set(oSa + i, Bw[0] * d0.get(m.D(D_qacc) + i)); }
-    for (int i = 0; i < na; ++i) tl.set(oSd + i, Bw[0] * d0.get(m.D(D_act_dot) + i));
+    for (int i = 0; i < nv; ++i) { tl.set(oSv + i, Bw[0] * d0.get(m.P(P_qvel) + i)); tl.set(oSa + i, Bw[0] * d0.get(m.P(P_qacc) + i)); }
+    for (int i = 0; i < na; ++i) tl.set(oSd + i, Bw[0] * d0.get(m.P(P_act_dot) + i));
   } else {
     // accumulate the stage that just finished: kqvel (its input velocity, still in tail), its qacc and act_dot
     for (int i = 0; i < nv; ++i) {
       tl.set(oSv + i, tl.get(oSv + i) + Bw[stage] * tl.get(oKv + i));
-      tl.set(oSa + i, tl.get(oSa + i) + Bw[stage] * dp.get(m.D(D_qacc) + i));
+      tl.set(oSa + i, tl.get(oSa + i) + Bw[stage] * dp.get(m.P(P_qacc) + i));
     }
-    for (int i = 0; i < na; ++i) tl.set(oSd + i, tl.get(oSd + i) + Bw[stage] * dp.get(m.D(D_act_dot) + i));
+    for (int i = 0; i < na; ++i) tl.set(oSd + i, tl.get(oSd + i) + Bw[stage] * dp.get(m.P(P_act_dot) + i));
   }
   if (stage < 3) {
     const T a = A[stage];
     // kqpos = integrate(qpos_t0, a * kqvel_prev); kqvel_prev is t0.qvel for stage 0, else tail.kqvel
-    if (stage == 0) integrate_pos(m, d0, m.D(D_qpos), tl, oKq, d0, m.D(D_qvel), a, h);
-    else integrate_pos(m, d0, m.D(D_qpos), tl, oKq, tl, oKv, a, h);
-    for (int i = 0; i < na; ++i) tl.set(oKa + i, d0.get(m.D(D_act) + i) + a * dp.get(m.D(D_act_dot) + i) * h);
-    for (int i = 0; i < nv; ++i) tl.set(oKv + i, d0.get(m.D(D_qvel) + i) + a * dp.get(m.D(D_qacc) + i) * h);
+    if (stage == 0) integrate_pos(m, d0, m.P(P_qpos), tl, oKq, d0, m.P(P_qvel), a, h);
+    else integrate_pos(m, d0, m.P(P_qpos), tl, oKq, tl, oKv, a, h);
+    for (int i = 0; i < na; ++i) tl.set(oKa + i, d0.get(m.P(P_act) + i) + a * dp.get(m.P(P_act_dot) + i) * h);
+    for (int i = 0; i < nv; ++i) tl.set(oKv + i, d0.get(m.P(P_qvel) + i) + a * dp.get(m.P(P_qacc) + i) * h);
     const T C[3] = {T(0.5), T(0.5), T(1.0)};
-    tl.set(oKt, d0.get(m.D(D_time)) + C[stage] * h);
+    tl.set(oKt, d0.get(m.P(P_time)) + C[stage] * h);
   } else {
     // _advance(d_t0, act_dot_sum, qacc_sum, qvel_sum)
     for (int u = 0; u < m.h(H_nu); ++u) {
       const int adr = m.I(I_act_actadr)[u];
       if (adr < 0) continue;
       for (int k = adr; k < adr + m.I(I_act_actnum)[u]; ++k) {
-        const T act = d0.get(m.D(D_act) + k), ad = tl.get(oSd + k);
+        const T act = d0.get(m.P(P_act) + k), ad = tl.get(oSd + k);
         T nx;
         if (m.I(I_act_dyntype)[u] == DYN_FILTEREXACT) {
           const T tau = t_max(m.F(F_act_dynprm)[10 * u], T(MJT_MINVAL));
           nx = act + ad * tau * (T(1) - t_exp(-h / tau));
         } else nx = act + ad * h;
         if (m.I(I_act_actlimited)[u]) nx = t_clamp(nx, m.F(F_act_actrange)[2 * u], m.F(F_act_actrange)[2 * u + 1]);
-        d0.set(m.D(D_act) + k, nx);
+        d0.set(m.P(P_act) + k, nx);
       }
     }
-    integrate_pos(m, d0, m.D(D_qpos), d0, m.D(D_qpos), tl, oSv, T(1), h);
-    for (int i = 0; i < nv; ++i) d0.set(m.D(D_qvel) + i, d0.get(m.D(D_qvel) + i) + tl.get(oSa + i) * h);
-    d0.set(m.D(D_time), d0.get(m.D(D_time)) + h);
+    integrate_pos(m, d0, m.P(P_qpos), d0, m.P(P_qpos), tl, oSv, T(1), h);
+    for (int i = 0; i < nv; ++i) d0.set(m.P(P_qvel) + i, d0.get(m.P(P_qvel) + i) + tl.get(oSa + i) * h);
+    d0.set(m.P(P_time), d0.get(m.P(P_time)) + h);
   }
 }

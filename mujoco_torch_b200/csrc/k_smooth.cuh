@@ -29,13 +29,16 @@ __device__ __forceinline__ void for_ancestor_dofs(const ModelView<T>& m, int b, 
 }
 
 template <typename T>
-__device__ void smooth_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T>& d, size_t B, int env) {
+__device__ void smooth_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T>& d, size_t B, int env, int mode) {
   const int nq = m.h(H_nq), nv = m.h(H_nv), nu = m.h(H_nu), na = m.h(H_na), nbody = m.h(H_nbody), njnt = m.h(H_njnt);
   const int ngeom = m.h(H_ngeom), nsite = m.h(H_nsite), ntendon = m.h(H_ntendon), flags = m.h(H_disableflags);
   const int oQpos = m.D(D_qpos), oQvel = m.D(D_qvel), oXpos = m.D(D_xpos), oXquat = m.D(D_xquat), oXmat = m.D(D_xmat);
   const int oXipos = m.D(D_xipos), oXimat = m.D(D_ximat), oAnchor = m.D(D_xanchor), oAxis = m.D(D_xaxis);
   const int oCom = m.D(D_subtree_com), oCinert = m.D(D_cinert), oCrb = m.D(D_crb), oCdof = m.D(D_cdof), oCdofdot = m.D(D_cdof_dot);
   const int oCvel = m.D(D_cvel), oM = m.D(D_qM);
+  // state layout (layout.py): fields nothing downstream reads have offset -1 and are not produced; qM is a packed lower triangle
+  const bool mpacked = m.h(H_layout_state) != 0;
+  const bool check = (mode & MJT_MODE_CHECK) != 0;
   const int* body_parent = m.I(I_body_parentid);
   const int* body_root = m.I(I_body_rootid);
   const int* body_jntadr = m.I(I_body_jntadr);
@@ -53,12 +56,12 @@ __device__ void smooth_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<
   // ---- _check_state (forward.py:44-59) + copy of pass-through state
   for (int i = 0; i < nq; ++i) {
     T q = in_get<T>(in.qpos, B, env, i);
-    if (!t_finite(q) || t_abs(q) > T(MJT_MAXVAL)) q = qpos0[i];
+    if (check && (!t_finite(q) || t_abs(q) > T(MJT_MAXVAL))) q = qpos0[i];
     d.set(oQpos + i, q);
   }
   for (int i = 0; i < nv; ++i) {
     T v = in_get<T>(in.qvel, B, env, i);
-    if (!t_finite(v) || t_abs(v) > T(MJT_MAXVAL)) v = T(0);
+    if (check && (!t_finite(v) || t_abs(v) > T(MJT_MAXVAL))) v = T(0);
     d.set(oQvel + i, v);
   }
   for (int i = 0; i < na; ++i) d.set(m.D(D_act) + i, in_get<T>(in.act, B, env, i));
@@ -135,14 +138,18 @@ __device__ void smooth_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<
       st3(d, oXpos + 3 * b, pos);
       d.set(oXquat + 4 * b, quat.w); d.set(oXquat + 4 * b + 1, quat.x); d.set(oXquat + 4 * b + 2, quat.y); d.set(oXquat + 4 * b + 3, quat.z);
       T mat[9];
-      q2mat(quat, mat);
+      if (oXmat >= 0) {
+        q2mat(quat, mat);
 #pragma unroll
-      for (int k = 0; k < 9; ++k) d.set(oXmat + 9 * b + k, mat[k]);
+        for (int k = 0; k < 9; ++k) d.set(oXmat + 9 * b + k, mat[k]);
+      }
       const V3<T> ipos = pos + qrot(f3(m.F(F_body_ipos) + 3 * b), quat);
       st3(d, oXipos + 3 * b, ipos);
-      q2mat(qmul(quat, f4(m.F(F_body_iquat) + 4 * b)), mat);
+      if (oXimat >= 0) {
+        q2mat(qmul(quat, f4(m.F(F_body_iquat) + 4 * b)), mat);
 #pragma unroll
-      for (int k = 0; k < 9; ++k) d.set(oXimat + 9 * b + k, mat[k]);
+        for (int k = 0; k < 9; ++k) d.set(oXimat + 9 * b + k, mat[k]);
+      }
       st3(d, oCom + 3 * b, ipos * body_mass[b]);
       for (int pass = 0; pass < 2; ++pass) {
         const int* list = m.I(pass == 0 ? I_body_geom : I_body_site) + m.I(pass == 0 ? I_body_geomadr : I_body_siteadr)[b];
@@ -150,8 +157,11 @@ __device__ void smooth_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<
         const T* lp = m.F(pass == 0 ? F_geom_pos : F_site_pos);
         const T* lq = m.F(pass == 0 ? F_geom_quat : F_site_quat);
         const int oP = m.D(pass == 0 ? D_geom_xpos : D_site_xpos), oR = m.D(pass == 0 ? D_geom_xmat : D_site_xmat);
+        if (oP < 0) continue;
+        const int* gneed = m.I(I_geom_need);   // state layout: only geoms a collision pair or a sensor reads are placed
         for (int k = 0; k < n; ++k) {
           const int g = list[k];
+          if (pass == 0 && !gneed[g]) continue;
           st3(d, oP + 3 * g, pos + qrot(f3(lp + 3 * g), quat));
           q2mat(qmul(quat, f4(lq + 4 * g)), mat);
 #pragma unroll
@@ -214,7 +224,7 @@ __device__ void smooth_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<
         }
         ci[6] = off.x * ms; ci[7] = off.y * ms; ci[8] = off.z * ms; ci[9] = ms;
 #pragma unroll
-        for (int k = 0; k < 10; ++k) { d.set(oCinert + 10 * b + k, ci[k]); d.set(oCrb + 10 * b + k, ci[k]); }
+        for (int k = 0; k < 10; ++k) { if (oCinert >= 0) d.set(oCinert + 10 * b + k, ci[k]); d.set(oCrb + 10 * b + k, ci[k]); }
       }
       // parent's cvel / cacc
       T v[6], a[6];
@@ -248,7 +258,7 @@ __device__ void smooth_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<
             for (int c = 0; c < 6; ++c) {
               const T e = (c == 3 + k) ? T(1) : T(0);
               d.set(oCdof + 6 * (da + k) + c, e);
-              d.set(oCdofdot + 6 * (da + k) + c, T(0));
+              if (oCdofdot >= 0) d.set(oCdofdot + 6 * (da + k) + c, T(0));
               v[c] += e * qv;
             }
           }
@@ -277,7 +287,7 @@ __device__ void smooth_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<
 #pragma unroll
           for (int c = 0; c < 6; ++c) {
             d.set(oCdof + 6 * (first + k) + c, cd[k][c]);
-            d.set(oCdofdot + 6 * (first + k) + c, dd[c]);
+            if (oCdofdot >= 0) d.set(oCdofdot + 6 * (first + k) + c, dd[c]);
             a[c] += dd[c] * qv;
           }
         }
@@ -322,6 +332,12 @@ __device__ void smooth_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<
   // ---- pass 4, leaves -> root: composite inertia (smooth.py:291-308), the backward half of rne (:453-467) and,
   // while a body's crb / cfrc are in registers, its rows of the dense M (support.make_m :50-69) and qfrc_bias.
   // A child that directly follows its parent hands its sums over in registers; every entry of M is written once.
+  if (mpacked && ntendon) {   // tendon armature couples dofs outside the tree pattern: start the packed triangle from zeros
+    bool any = false;
+    for (int t = 0; t < ntendon; ++t) any |= (m.F(F_ten_armature)[t] != T(0));
+    if (any)
+      for (int p = 0; p < nv * (nv + 1) / 2; ++p) d.set(oM + p, T(0));
+  }
   {
     T hc[10], hf[6];   // crb / cfrc of body b+1 when that body's parent is b
     bool have = false;
@@ -386,16 +402,21 @@ __device__ void smooth_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<
 #pragma unroll
               for (int c = 0; c < 6; ++c) sm += f[k][c] * cd[l][c];
               if (l == k) sm += m.F(F_dof_armature)[g0 + k];
-              d.set(oM + (g0 + k) * nv + g0 + l, sm);
-              if (l != k) d.set(oM + (g0 + l) * nv + g0 + k, sm);
+              if (mpacked) {
+                d.set(oM + (((g0 + k) * (g0 + k + 1)) >> 1) + g0 + l, sm);
+              } else {
+                d.set(oM + (g0 + k) * nv + g0 + l, sm);
+                if (l != k) d.set(oM + (g0 + l) * nv + g0 + k, sm);
+              }
             }
         // ancestors below the group, zero-filling the gaps between them
         int prev = g0;
         for (int j = dof_parent[g0]; ; j = dof_parent[j]) {
           const int stop = j < 0 ? -1 : j;
-          for (int z = prev - 1; z > stop; --z)
-            for (int k = 0; k < 3; ++k)
-              if (k < gn) { d.set(oM + (g0 + k) * nv + z, T(0)); d.set(oM + z * nv + g0 + k, T(0)); }
+          if (!mpacked)
+            for (int z = prev - 1; z > stop; --z)
+              for (int k = 0; k < 3; ++k)
+                if (k < gn) { d.set(oM + (g0 + k) * nv + z, T(0)); d.set(oM + z * nv + g0 + k, T(0)); }
           if (j < 0) break;
           T cj[6];
 #pragma unroll
@@ -405,8 +426,12 @@ __device__ void smooth_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<
               T sm = 0;
 #pragma unroll
               for (int c = 0; c < 6; ++c) sm += f[k][c] * cj[c];
-              d.set(oM + (g0 + k) * nv + j, sm);
-              d.set(oM + j * nv + g0 + k, sm);
+              if (mpacked) {
+                d.set(oM + (((g0 + k) * (g0 + k + 1)) >> 1) + j, sm);
+              } else {
+                d.set(oM + (g0 + k) * nv + j, sm);
+                d.set(oM + j * nv + g0 + k, sm);
+              }
             }
           prev = j;
         }
@@ -422,7 +447,14 @@ __device__ void smooth_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<
       for (int i = 0; i < nv; ++i) {
         const T ji = d.get(oJ + t * nv + i);
         if (ji == T(0)) continue;
-        for (int j = 0; j < nv; ++j) d.set(oM + i * nv + j, d.get(oM + i * nv + j) + ji * arm * d.get(oJ + t * nv + j));
+        if (mpacked) {
+          for (int j = 0; j <= i; ++j) {
+            const T add = ji * arm * d.get(oJ + t * nv + j);
+            if (add != T(0)) d.set(oM + ((i * (i + 1)) >> 1) + j, d.get(oM + ((i * (i + 1)) >> 1) + j) + add);
+          }
+        } else {
+          for (int j = 0; j < nv; ++j) d.set(oM + i * nv + j, d.get(oM + i * nv + j) + ji * arm * d.get(oJ + t * nv + j));
+        }
       }
     }
   }
@@ -605,9 +637,11 @@ __device__ void smooth_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<
     int mfirst, mcnt;
     T mom[6], len, vel;
     transmission(u, &mfirst, &mcnt, mom, &len, &vel);
-    d.set(oAlen + u, len);
-    d.set(oAvel + u, vel);
-    if (mcnt < 0) {
+    if (oAlen >= 0) d.set(oAlen + u, len);
+    if (oAvel >= 0) d.set(oAvel + u, vel);
+    if (oAmom < 0) {
+      // state layout without a reader of the dense moment rows (ImplicitFast with ball / free / tendon transmissions keeps them)
+    } else if (mcnt < 0) {
       const T g0 = m.F(F_act_gear)[6 * u];
       const int id = m.I(I_act_trnid)[u];
       for (int i = 0; i < nv; ++i) d.set(oAmom + u * nv + i, d.get(m.D(D_ten_J) + id * nv + i) * g0);
@@ -661,7 +695,7 @@ __device__ void smooth_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<
       if (bt == BIAS_AFFINE) bias = bp[0] + bp[1] * len + bp[2] * vel;
       T force = gain * ctrl_act + bias;
       if (m.I(I_act_forcelimited)[u]) force = t_min(t_max(force, m.F(F_act_forcerange)[2 * u]), m.F(F_act_forcerange)[2 * u + 1]);
-      d.set(oForce + u, force);
+      if (oForce >= 0) d.set(oForce + u, force);
       if (force != T(0)) {
         if (mcnt < 0) {
           const T g0 = m.F(F_act_gear)[6 * u];
@@ -676,7 +710,7 @@ __device__ void smooth_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<
             if (c < mcnt && mom[c] != T(0)) d.set(oQfa + mfirst + c, d.get(oQfa + mfirst + c) + mom[c] * force);
         }
       }
-    } else {
+    } else if (oForce >= 0) {
       d.set(oForce + u, T(0));
     }
   }
@@ -714,7 +748,7 @@ __device__ void smooth_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<
 }
 
 template <typename T>
-__global__ void __launch_bounds__(MJT_ENV_THREADS, MJT_SMOOTH_MINB) k_smooth(const int* __restrict__ gblob, int blob_words, MjtIn in, T* __restrict__ out, int B) {
+__global__ void __launch_bounds__(MJT_ENV_THREADS, MJT_SMOOTH_MINB) k_smooth(const int* __restrict__ gblob, int blob_words, MjtIn in, T* __restrict__ out, int B, int mode) {
   extern __shared__ __align__(16) int smem_blob[];
   __shared__ uint64_t bar;
   stage_blob(smem_blob, &bar, gblob, blob_words);
@@ -722,5 +756,5 @@ __global__ void __launch_bounds__(MJT_ENV_THREADS, MJT_SMOOTH_MINB) k_smooth(con
   const int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= B) return;
   EnvBuf<T> d{out + env, (size_t)B};
-  smooth_env<T>(m, in, d, (size_t)B, env);
+  smooth_env<T>(m, in, d, (size_t)B, env, mode);
 }

@@ -181,11 +181,12 @@ struct SolveCtx {
       if (flossv) flossv[idx] = d.get(oF + r);
     }
     T* J = Jc();
+    const bool jcompact = m.h(H_layout_state) != 0;   // state layout: efc_J already is the support-compacted form
     for (int idx = 0; idx < base; ++idx) {   // one live row at a time, lanes over its support columns
       const int r = lr[idx], sidx = row_src[r], ns = src_nsup[sidx];
       const int* col = sup_col + src_cadr[sidx];
       T* dst = J + jp[sidx] + (r - src_row[sidx]) * ns;
-      for (int k = lane; k < ns; k += G) dst[k] = d.get(oJ + r * nv + col[k]);
+      for (int k = lane; k < ns; k += G) dst[k] = d.get(jcompact ? oJ + row_jadr[r] + k : oJ + r * nv + col[k]);
     }
     __syncwarp(gm);
     return base;
@@ -450,7 +451,7 @@ struct SolveCtx {
 };
 
 template <typename T, int DPL, bool COMPACT, int G, bool TILE>
-__device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T>& d, size_t B, int env,
+__device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T>& d, const EnvBuf<T>& pub, size_t B, int env,
                           const SolveCtx<T, DPL, COMPACT, G, TILE>& c, const Vec<T, DPL>& qfrc_smooth, const Vec<T, DPL>& qacc_smooth, int mode) {
   typedef Vec<T, DPL> V;
   const int lane = c.lane;
@@ -473,10 +474,13 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
     for (int k = 0; k < DPL; ++k) { const int i = lane + G * k; r.v[k] = i < nv ? d.get(off + i) : T(0); }
     return r;
   };
+  // results go to the caller's buffer through the P table (layout.py); an absent field (offset -1) is not stored
   auto storev = [&](int off, const V& x) {
+    if (off < 0) return;
 #pragma unroll
-    for (int k = 0; k < DPL; ++k) { const int i = lane + G * k; if (i < nv) d.set(off + i, x.v[k]); }
+    for (int k = 0; k < DPL; ++k) { const int i = lane + G * k; if (i < nv) pub.set(off + i, x.v[k]); }
   };
+  const bool fixed = (mode & MJT_MODE_FIXED) != 0;   // step(..., fixed_iterations=True): no termination tests
   auto axpy = [&](const V& a, T s, const V& b) {
     V r;
 #pragma unroll
@@ -500,7 +504,7 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
       const int i = lane + G * k;
       if (i < nv) {
         qfrc_con.v[k] = in_get<T>(in.qfrc_constraint, B, env, i);
-        d.set(m.D(D_qacc_warmstart) + i, in_get<T>(in.qacc_warmstart, B, env, i));
+        pub.set(m.P(P_qacc_warmstart) + i, in_get<T>(in.qacc_warmstart, B, env, i));
       }
     }
   } else {
@@ -642,9 +646,11 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
       int it = 0;
       while (true) {
         bool done = it >= ls_iterations;
-        done = done || !swap;
-        done = done || (lo.d0 < T(0) && lo.d0 > -gtol);
-        done = done || (hi.d0 > T(0) && hi.d0 < gtol);
+        if (!fixed) {   // solver.py:484-487: the fixed loop runs ls_iterations bodies whatever the bracket looks like
+          done = done || !swap;
+          done = done || (lo.d0 < T(0) && lo.d0 > -gtol);
+          done = done || (hi.d0 > T(0) && hi.d0 < gtol);
+        }
         if (done) break;
         Pt cand[3];
         al[0] = lo.alpha - lo.d0 / lo.d1;
@@ -735,7 +741,7 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
     // follows, so the termination test is evaluated first (identical outputs, one factorisation less per solve).
     int niter = 0;
     bool run = true;
-    if (iterations != 1) {
+    if (iterations != 1 && !fixed) {
       const T improvement = (prev_cost - cost) / scale;
       const T gradient = t_sqrt(c.dotv(grad, grad)) / scale;
       run = !(niter >= iterations || improvement < tolerance || gradient < tolerance);
@@ -747,9 +753,13 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
       compute_grad();
       ++niter;
       if (iterations == 1) break;
-      const T improvement = (prev_cost - cost) / scale;
-      const T gradient = t_sqrt(c.dotv(grad, grad)) / scale;
-      if (niter >= iterations || improvement < tolerance || gradient < tolerance) break;
+      if (fixed) {   // solver.py:536-537: exactly `iterations` bodies
+        if (niter >= iterations) break;
+      } else {
+        const T improvement = (prev_cost - cost) / scale;
+        const T gradient = t_sqrt(c.dotv(grad, grad)) / scale;
+        if (niter >= iterations || improvement < tolerance || gradient < tolerance) break;
+      }
       compute_mgrad();
       if (newton) {
         search = neg(Mgrad);
@@ -763,8 +773,10 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
         for (int k = 0; k < DPL; ++k) search.v[k] = -Mgrad.v[k] + beta * search.v[k];
       }
     }
-    storev(m.D(D_qacc_warmstart), qacc);
-    if (TILE) {   // dead rows carry no force; live rows scatter from their slots
+    storev(m.P(P_qacc_warmstart), qacc);
+    if (m.D(D_efc_force) < 0) {
+      // state layout: efc_force is not an output
+    } else if (TILE) {   // dead rows carry no force; live rows scatter from their slots
       for (int r = lane; r < nefc; r += G) d.set(m.D(D_efc_force) + r, T(0));
       __syncwarp(gm);
       for (int idx = lane; idx < nlive; idx += G) d.set(m.D(D_efc_force) + c.lrow()[idx], force[idx]);
@@ -772,12 +784,23 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
       for (int r = lane; r < nefc; r += G) d.set(m.D(D_efc_force) + r, force[r]);
     }
   }
-  storev(m.D(D_qacc), qacc);
-  storev(m.D(D_qfrc_constraint), qfrc_con);
+  storev(m.P(P_qacc), qacc);
+  storev(m.P(P_qfrc_constraint), qfrc_con);
 
-  if (mode != MJT_MODE_STEP) return;
   const int integrator = m.h(H_integrator);
-  if (integrator == INT_RK4) return;  // RK4 is sequenced on the host from forward passes
+  const bool split = pub.p != d.p;   // state layout: the workspace holds the pre-integration working copies
+  if ((mode & MJT_MODE_KIND) != MJT_MODE_STEP || integrator == INT_RK4) {   // RK4 is sequenced on the host from forward passes
+    if (split) {   // forward(): the (sanitised / normalised) state and act_dot still have to reach the caller's buffer
+      for (int i = lane; i < m.h(H_nq); i += G) pub.set(m.P(P_qpos) + i, d.get(m.D(D_qpos) + i));
+      for (int i = lane; i < nv; i += G) pub.set(m.P(P_qvel) + i, d.get(m.D(D_qvel) + i));
+      for (int i = lane; i < m.h(H_na); i += G) {
+        pub.set(m.P(P_act) + i, d.get(m.D(D_act) + i));
+        pub.set(m.P(P_act_dot) + i, d.get(m.D(D_act_dot) + i));
+      }
+      if (lane == 0) pub.set(m.P(P_time), d.get(m.D(D_time)));
+    }
+    return;
+  }
 
   // ---- integrator: velocity-implicit re-solve (forward.py:313-328 / 404-416)
   const T dt = m.opt(OPT_timestep);
@@ -880,37 +903,46 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
         nx = act + ad * dt;
       }
       if (m.I(I_act_actlimited)[u]) nx = t_clamp(nx, m.F(F_act_actrange)[2 * u], m.F(F_act_actrange)[2 * u + 1]);
-      d.set(m.D(D_act) + a, nx);
+      pub.set(m.P(P_act) + a, nx);
+    }
+  }
+  if (split) {   // activations without an owning actuator keep their value; act_dot is an output of the step
+    const int* actadr = m.I(I_act_actadr);
+    for (int a = lane; a < m.h(H_na); a += G) {
+      bool owned = false;
+      for (int u = 0; u < nu; ++u) owned |= actadr[u] >= 0 && a >= actadr[u] && a < actadr[u] + m.I(I_act_actnum)[u];
+      if (!owned) pub.set(m.P(P_act) + a, d.get(m.D(D_act) + a));
+      pub.set(m.P(P_act_dot) + a, d.get(m.D(D_act_dot) + a));
     }
   }
   V qvel = loadv(m.D(D_qvel));
   qvel = axpy(qvel, dt, qacc_int);
-  storev(m.D(D_qvel), qvel);
+  storev(m.P(P_qvel), qvel);
   c.to_smem(qvel, c.xs());
   const T* nvel = c.xs();
-  const int oQ = m.D(D_qpos);
+  const int oQ = m.D(D_qpos), pQ = m.P(P_qpos);
   for (int j = lane; j < m.h(H_njnt); j += G) {
     const int jt = m.I(I_jnt_type)[j], qa = m.I(I_jnt_qposadr)[j], da = m.I(I_jnt_dofadr)[j];
     if (jt == JNT_FREE || jt == JNT_BALL) {
       int qq = qa, dd = da;
       if (jt == JNT_FREE) {
-        for (int k = 0; k < 3; ++k) d.set(oQ + qa + k, d.get(oQ + qa + k) + dt * nvel[da + k]);
+        for (int k = 0; k < 3; ++k) pub.set(pQ + qa + k, d.get(oQ + qa + k) + dt * nvel[da + k]);
         qq = qa + 3;
         dd = da + 3;
       }
       Q4<T> q(d.get(oQ + qq), d.get(oQ + qq + 1), d.get(oQ + qq + 2), d.get(oQ + qq + 3));
       q = qintegrate(q, V3<T>(nvel[dd], nvel[dd + 1], nvel[dd + 2]), dt);
-      d.set(oQ + qq, q.w); d.set(oQ + qq + 1, q.x); d.set(oQ + qq + 2, q.y); d.set(oQ + qq + 3, q.z);
+      pub.set(pQ + qq, q.w); pub.set(pQ + qq + 1, q.x); pub.set(pQ + qq + 2, q.y); pub.set(pQ + qq + 3, q.z);
     } else {
-      d.set(oQ + qa, d.get(oQ + qa) + dt * nvel[da]);
+      pub.set(pQ + qa, d.get(oQ + qa) + dt * nvel[da]);
     }
   }
-  if (lane == 0) d.set(m.D(D_time), d.get(m.D(D_time)) + dt);
+  if (lane == 0) pub.set(m.P(P_time), d.get(m.D(D_time)) + dt);
 }
 
 template <typename T, int DPL, bool COMPACT, int G, bool TILE>
 __global__ void __launch_bounds__((sizeof(T) == 4 ? 512 : MJT_SOLVE_F64_THREADS), (sizeof(T) == 4 ? 2 : MJT_SOLVE_F64_MINB)) k_solve(const int* __restrict__ gfull, const int* __restrict__ gblob, int blob_words, MjtIn in,
-                                               T* __restrict__ out, int B, int mode, int only_flagged) {
+                                               T* __restrict__ out, T* __restrict__ pubbuf, int B, int mode, int only_flagged) {
   extern __shared__ __align__(16) int smem_blob[];
   __shared__ uint64_t bar;
   if (only_flagged) {
@@ -941,18 +973,26 @@ __global__ void __launch_bounds__((sizeof(T) == 4 ? 512 : MJT_SOLVE_F64_THREADS)
   T* const crg = region + (size_t)ce * Lo.words;
   T* const cout = out + env0 + ce;
   const int* tri_ab = m.I(I_tri_ab);   // packed lower index p -> (a, b): dense word a*nv+b, mirrored word b*nv+a
+  const bool lstate = m.h(H_layout_state) != 0;   // state layout: qM is a packed triangle, efc_J the support-compacted rows
   {
-    const int oM = m.D(D_qM);
+    // M: only the entries that can be non-zero (kinematic-tree pattern, model.py m_nz) are fetched; the rest of the tile is zeroed
+    const int oM = m.D(D_qM), nmz = m.h(H_n_mnz);
+    const int* mnz = m.I(I_m_nz);
+    if (nmz < Lo.nP) {
+      if (cvalid)
+        for (int p = ck0; p < Lo.nP; p += cks) crg[Lo.oM + p] = T(0);
+      __syncthreads();
+    }
     if (cvalid)
-      for (int p = ck0; p < Lo.nP; p += cks) {
-        const int ab = tri_ab[p];
-        cp_async_word(crg + Lo.oM + p, cout + (size_t)(oM + (ab & 0xffff) * nv + (ab >> 16)) * Bs);
+      for (int q = ck0; q < nmz; q += cks) {
+        const int p = mnz[q], ab = tri_ab[p];
+        cp_async_word(crg + Lo.oM + p, cout + (size_t)(lstate ? oM + p : oM + (ab & 0xffff) * nv + (ab >> 16)) * Bs);
       }
     if (nefc && !TILE) {   // the live tile gathers its rows per env once it knows which sources are live
       const int oJ = m.D(D_efc_J), jcw = m.h(H_jc_words);
       const int* jsrc = m.I(I_jc_src);   // compact J entry -> dense word row*nv+col
       if (cvalid)
-        for (int k = ck0; k < jcw; k += cks) cp_async_word(crg + Lo.oJ + k, cout + (size_t)(oJ + jsrc[k]) * Bs);
+        for (int k = ck0; k < jcw; k += cks) cp_async_word(crg + Lo.oJ + k, cout + (size_t)(oJ + (lstate ? k : jsrc[k])) * Bs);
       const int oD = m.D(D_efc_D), oA = m.D(D_efc_aref), oF = m.D(D_efc_frictionloss);
       const bool hasf = m.h(H_nf) > 0;
       if (cvalid)
@@ -969,6 +1009,7 @@ __global__ void __launch_bounds__((sizeof(T) == 4 ? 512 : MJT_SOLVE_F64_THREADS)
   const int env = env0 + warp;
   const bool valid = env < B && (!only_flagged || out[(size_t)m.D(D_scr_ovf) * Bs + (env < B ? env : 0)] != T(0));
   EnvBuf<T> d{out + (valid ? env : 0), Bs};
+  EnvBuf<T> pub{pubbuf + (valid ? env : 0), Bs};   // the caller's buffer (same as `out` in the full layout)
   SolveCtx<T, DPL, COMPACT, G, TILE> c{m, region + (size_t)warp * Lo.words, Lo, nv, nefc, lane,
                      m.I(I_row_src), m.I(I_row_jadr), m.I(I_src_nsup), m.I(I_src_cadr), m.I(I_src_row), m.I(I_src_nrows), m.I(I_sup_col), m.I(I_tri_ab), m.I(I_dof_sadr), m.I(I_dof_sent), group_mask<G>()};
   Vec<T, DPL> qfrc_smooth = c.zero(), qacc_smooth = c.zero();
@@ -982,11 +1023,13 @@ __global__ void __launch_bounds__((sizeof(T) == 4 ? 512 : MJT_SOLVE_F64_THREADS)
 #pragma unroll
     for (int k = 0; k < DPL; ++k) { const int i = lane + G * k; qfrc_smooth.v[k] = i < nv ? d.get(m.D(D_qfrc_smooth) + i) : T(0); }
     qacc_smooth = c.cho_solve(Lm, qfrc_smooth);
+    if (m.D(D_qacc_smooth) >= 0) {
 #pragma unroll
-    for (int k = 0; k < DPL; ++k) { const int i = lane + G * k; if (i < nv) d.set(m.D(D_qacc_smooth) + i, qacc_smooth.v[k]); }
+      for (int k = 0; k < DPL; ++k) { const int i = lane + G * k; if (i < nv) d.set(m.D(D_qacc_smooth) + i, qacc_smooth.v[k]); }
+    }
   }
-  __syncthreads();
-  {  // cooperative store of qLD = chol(M) (dense lower, zeros above the diagonal)
+  if (m.D(D_qLD) >= 0) {  // cooperative store of qLD = chol(M) (dense lower, zeros above the diagonal); not an output of the state layout
+    __syncthreads();
     const int oL = m.D(D_qLD);
     if (cvalid) {
       for (int p = ck0; p < Lo.nP; p += cks) {
@@ -995,8 +1038,8 @@ __global__ void __launch_bounds__((sizeof(T) == 4 ? 512 : MJT_SOLVE_F64_THREADS)
         if (a != b) cout[(size_t)(oL + b * nv + a) * Bs] = T(0);
       }
     }
+    __syncthreads();
   }
-  __syncthreads();
   if (!valid) return;
-  solve_env<T, DPL, COMPACT, G, TILE>(m, in, d, Bs, env, c, qfrc_smooth, qacc_smooth, mode);
+  solve_env<T, DPL, COMPACT, G, TILE>(m, in, d, pub, Bs, env, c, qfrc_smooth, qacc_smooth, mode);
 }

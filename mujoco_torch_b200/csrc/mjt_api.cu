@@ -69,7 +69,11 @@ struct mjtModel {
   bool tile;
   int tile_envs;
   size_t tile_smem, tile_region_bytes;
+  // tuning knobs, read from the environment once at mjt_model_create (never on the launch path)
+  int constraint_split;   // CTAs per env block in k_constraint
+  int ovf_envs;           // envs per CTA of the live-tile overflow pass
   int hv(int k) const { return h[k]; }
+  bool state_layout() const { return h[H_layout_state] != 0; }
 };
 
 static const char* kFieldNames[] = {
@@ -168,6 +172,10 @@ extern "C" int mjt_model_create(const void* blob_host, size_t nbytes, int device
     delete m;
     return fail("mjt_model_create: model blob exceeds shared memory");
   }
+  m->constraint_split = w[H_nsrc] < MJT_CONSTRAINT_SPLIT ? w[H_nsrc] : MJT_CONSTRAINT_SPLIT;
+  if (const char* fs = getenv("MJT_CONSTRAINT_SPLIT")) { const int v = atoi(fs); if (v >= 1) m->constraint_split = v < w[H_nsrc] ? v : w[H_nsrc]; }
+  m->ovf_envs = 32 / G;   // one warp per CTA: CTAs without a flagged env leave at once, flagged envs pack the SMs
+  if (const char* fe = getenv("MJT_OVF_E")) { const int v = atoi(fe); if (v >= 32 / G && v <= best_e && v % (32 / G) == 0) m->ovf_envs = v; }
   *out = m;
   return 0;
 }
@@ -179,16 +187,29 @@ extern "C" void mjt_model_destroy(mjtModel* m) {
   delete m;
 }
 
-extern "C" int mjt_model_data_words(const mjtModel* m) { return m->hv(H_data_words); }
+extern "C" int mjt_model_layout(const mjtModel* m) { return m->state_layout() ? 1 : 0; }
+extern "C" int mjt_model_data_words(const mjtModel* m) { return m->hv(H_pub_words); }
 extern "C" int mjt_model_dtype_size(const mjtModel* m) { return m->f64 ? 8 : 4; }
+static int rk4_tail_words(const mjtModel* m) { return m->hv(H_nq) + 3 * m->hv(H_nv) + 2 * m->hv(H_na) + 1; }
+// work buffer = [workspace (state layout only) | RK4: one more caller-side buffer for the stage passes | RK4 tail]
 extern "C" int mjt_model_scratch_words(const mjtModel* m) {
-  if (m->hv(H_integrator) != INT_RK4) return 0;
-  return m->hv(H_data_words) + m->hv(H_nq) + 3 * m->hv(H_nv) + 2 * m->hv(H_na) + 1;
+  int n = m->state_layout() ? m->hv(H_data_words) : 0;
+  if (m->hv(H_integrator) == INT_RK4) n += m->hv(H_pub_words) + rk4_tail_words(m);
+  return n;
 }
 extern "C" int mjt_model_field(const mjtModel* m, const char* name, int* offset, int* words) {
   for (int k = 0; k < NUM_D; ++k)
     if (strcmp(name, kFieldNames[k]) == 0) {
-      if (offset) *offset = m->hv(MJT_OFF_D + k);
+      // offsets are those of the caller's buffer: the D table in the full layout, the P table in the state layout
+      int off = m->hv(MJT_OFF_D + k);
+      if (m->state_layout()) {
+        off = -1;
+        static const int pd[NUM_P] = {D_qpos, D_qvel, D_act, D_time, D_qacc, D_qacc_warmstart, D_act_dot, D_sensordata, D_qfrc_constraint};
+        for (int q = 0; q < NUM_P; ++q)
+          if (pd[q] == k) off = m->hv(MJT_OFF_P + q);
+        if (off < 0) return -1;
+      }
+      if (offset) *offset = off;
       if (words) *words = m->hv(MJT_OFF_DSZ + k);
       return 0;
     }
@@ -204,12 +225,12 @@ static MjtIn to_in(const mjtStateIn* s) {
 }
 
 static cudaError_t launch_solve(int lanes, int dpl, int compact, int only_flagged, int grid, int threads, size_t smem, size_t smem_attr,
-                                cudaStream_t st, const int* blob, const int* sblob, int solve_words, const MjtIn& in, float* out, int B, int mode) {
-  return mjt_launch_solve_f32(lanes, dpl, compact, 0, 0, only_flagged, grid, threads, smem, smem_attr, st, blob, sblob, solve_words, in, out, B, mode);
+                                cudaStream_t st, const int* blob, const int* sblob, int solve_words, const MjtIn& in, float* out, float* pub, int B, int mode) {
+  return mjt_launch_solve_f32(lanes, dpl, compact, 0, 0, only_flagged, grid, threads, smem, smem_attr, st, blob, sblob, solve_words, in, out, pub, B, mode);
 }
 static cudaError_t launch_solve(int lanes, int dpl, int compact, int only_flagged, int grid, int threads, size_t smem, size_t smem_attr,
-                                cudaStream_t st, const int* blob, const int* sblob, int solve_words, const MjtIn& in, double* out, int B, int mode) {
-  return mjt_launch_solve_f64(lanes, dpl, compact, 0, 0, only_flagged, grid, threads, smem, smem_attr, st, blob, sblob, solve_words, in, out, B, mode);
+                                cudaStream_t st, const int* blob, const int* sblob, int solve_words, const MjtIn& in, double* out, double* pub, int B, int mode) {
+  return mjt_launch_solve_f64(lanes, dpl, compact, 0, 0, only_flagged, grid, threads, smem, smem_attr, st, blob, sblob, solve_words, in, out, pub, B, mode);
 }
 
 template <typename T>
@@ -230,35 +251,46 @@ static int env_threads(const mjtModel* m, int B) {
   return t;
 }
 
+// One forward pass (optionally followed by the in-kernel integrator).  `pub` is the caller's buffer; `ws` is where the derived
+// quantities go: the same buffer in the full layout, the lent workspace in the state layout.  `upto` stops the sequence after
+// a stage (the stage-level API: kinematics() needs k_smooth only, collision() k_smooth + k_collision ...).
+enum { UPTO_ALL = 0, UPTO_SMOOTH = 1, UPTO_COLLISION = 2, UPTO_CONSTRAINT = 3 };
 template <typename T>
-static int run_forward(const mjtModel* m, const MjtIn& in, T* out, int B, int mode, cudaStream_t st, int* launches) {
+static int run_forward(const mjtModel* m, const MjtIn& in, T* pub, T* ws, int B, int mode, int upto, cudaStream_t st, int* launches) {
   const int threads = env_threads(m, B);
   const int gx = (B + threads - 1) / threads;
   const size_t blob_b = ((size_t)m->blob_words + 3) / 4 * 16;
   const int nsens = m->hv(H_nsensordata);
   int n = 0;
+  auto done = [&](void) {
+    if (launches) *launches = n;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(std::string("kernel launch: ") + cudaGetErrorString(e));
+    return 0;
+  };
   if (set_smem<T>((const void*)k_smooth<T>, blob_b)) return 1;
-  LAUNCH("k_smooth", st, k_smooth<T><<<gx, threads, blob_b, st>>>(m->d_blob, m->blob_words, in, out, B));
+  LAUNCH("k_smooth", st, k_smooth<T><<<gx, threads, blob_b, st>>>(m->d_blob, m->blob_words, in, ws, B, mode));
   ++n;
+  if (upto == UPTO_SMOOTH) return done();
   if (m->hv(H_npair_cand) > 0) {
     if (set_smem<T>((const void*)k_collision<T>, blob_b)) return 1;
     dim3 grid(m->hv(H_npair_cand), gx < 65535 ? gx : 65535);
-    LAUNCH("k_collision", st, k_collision<T><<<grid, threads, blob_b, st>>>(m->d_blob, m->blob_words, out, B));
+    LAUNCH("k_collision", st, k_collision<T><<<grid, threads, blob_b, st>>>(m->d_blob, m->blob_words, ws, B));
     ++n;
   }
+  if (upto == UPTO_COLLISION) return done();
   if (m->hv(H_nsrc) > 0) {
     if (set_smem<T>((const void*)k_constraint<T>, blob_b)) return 1;
     // grid.x CTAs share one env block and split its row sources; each CTA stages the model blob once, so a few sources
     // per CTA amortise the staging while still spreading an env block's rows over several SMs
-    int sx = m->hv(H_nsrc) < MJT_CONSTRAINT_SPLIT ? m->hv(H_nsrc) : MJT_CONSTRAINT_SPLIT;
-    if (const char* fs = getenv("MJT_CONSTRAINT_SPLIT")) { const int v = atoi(fs); if (v >= 1) sx = v < m->hv(H_nsrc) ? v : m->hv(H_nsrc); }
-    dim3 grid(sx, gx < 65535 ? gx : 65535);
-    LAUNCH("k_constraint", st, k_constraint<T><<<grid, threads, blob_b, st>>>(m->d_blob, m->blob_words, in, out, B));
+    dim3 grid(m->constraint_split, gx < 65535 ? gx : 65535);
+    LAUNCH("k_constraint", st, k_constraint<T><<<grid, threads, blob_b, st>>>(m->d_blob, m->blob_words, in, ws, B));
     ++n;
   }
+  if (upto == UPTO_CONSTRAINT) return done();
   if (nsens > 0) {
     if (set_smem<T>((const void*)k_sensor<T>, blob_b)) return 1;
-    LAUNCH("k_sensor", st, k_sensor<T><<<gx, threads, blob_b, st>>>(m->d_blob, m->blob_words, in, out, B, (1 << 1) | (1 << 2)));
+    LAUNCH("k_sensor", st, k_sensor<T><<<gx, threads, blob_b, st>>>(m->d_blob, m->blob_words, in, ws, pub, B, (1 << 1) | (1 << 2)));
     ++n;
   }
   {
@@ -276,51 +308,51 @@ static int run_forward(const mjtModel* m, const MjtIn& in, T* out, int B, int mo
       const size_t tsmem = m->solve_blob_bytes + m->tile_region_bytes * TE;
       ProfScope prof__("k_solve", st);
       se = launch_solve(lanes, dpl, 2, 0, (B + TE - 1) / TE, lanes * TE, tsmem, m->tile_smem, st, m->d_blob, m->d_blob + m->blob_words,
-                        m->solve_words, in, out, B, mode);
+                        m->solve_words, in, ws, pub, B, mode);
       ++n;
       if (se == cudaSuccess) {
-        // one warp per CTA: CTAs without a flagged env leave at once, flagged envs pack the SMs regardless of where they sit
-        int E2 = 32 / lanes;
-        if (const char* fe = getenv("MJT_OVF_E")) { const int v = atoi(fe); if (v >= E2 && v <= E && v % E2 == 0) E2 = v; }
+        const int E2 = m->ovf_envs;
         const size_t smem2 = m->solve_blob_bytes + m->solve_region_bytes * E2;
         se = launch_solve(lanes, dpl, compact, 1, (B + E2 - 1) / E2, lanes * E2, smem2, m->solve_smem, st, m->d_blob, m->d_blob + m->blob_words,
-                          m->solve_words, in, out, B, mode);
+                          m->solve_words, in, ws, pub, B, mode);
       }
     } else {
       ProfScope prof__("k_solve", st);
       se = launch_solve(lanes, dpl, compact, 0, gs, lanes * E, smem, m->solve_smem, st, m->d_blob, m->d_blob + m->blob_words, m->solve_words,
-                        in, out, B, mode);
+                        in, ws, pub, B, mode);
     }
     if (se != cudaSuccess) return fail(std::string("k_solve launch: ") + cudaGetErrorString(se));
     ++n;
   }
   // acc-stage sensors run only when the solver ran (reference forward.py:390-401 returns early when nefc == 0)
   if (nsens > 0 && m->hv(H_nsens_acc) > 0 && m->hv(H_nefc) > 0) {
-    LAUNCH("k_sensor", st, k_sensor<T><<<gx, threads, blob_b, st>>>(m->d_blob, m->blob_words, in, out, B, 1 << 3));
+    LAUNCH("k_sensor", st, k_sensor<T><<<gx, threads, blob_b, st>>>(m->d_blob, m->blob_words, in, ws, pub, B, 1 << 3));
     ++n;
   }
-  if (launches) *launches = n;
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return fail(std::string("kernel launch: ") + cudaGetErrorString(e));
-  return 0;
+  return done();
 }
 
 template <typename T>
-static int run_step(const mjtModel* m, const MjtIn& in, T* out, T* scratch, int B, cudaStream_t st, int* launches) {
+static int run_step(const mjtModel* m, const MjtIn& in, T* out, T* work, int B, int flags, cudaStream_t st, int* launches) {
   int total = 0, n = 0;
+  const int fixed = (flags & MJT_FLAG_FIXED_ITERATIONS) ? MJT_MODE_FIXED : 0;
+  const bool split = m->state_layout();
+  if (split && !work) return fail("mjt_step: the state layout needs the work buffer (mjt_model_scratch_words)");
+  T* ws = split ? work : out;
   if (m->hv(H_integrator) != INT_RK4) {
-    if (run_forward<T>(m, in, out, B, MJT_MODE_STEP, st, &n)) return 1;
+    if (run_forward<T>(m, in, out, ws, B, MJT_MODE_STEP | MJT_MODE_CHECK | fixed, UPTO_ALL, st, &n)) return 1;
     if (launches) *launches = n;
     return 0;
   }
-  if (!scratch) return fail("mjt_step: RK4 needs a scratch buffer (mjt_model_scratch_words)");
+  if (!work) return fail("mjt_step: RK4 needs a work buffer (mjt_model_scratch_words)");
   const int threads = env_threads(m, B), gx = (B + threads - 1) / threads;
   const size_t blob_b = ((size_t)m->blob_words + 3) / 4 * 16;
   const int nq = m->hv(H_nq), nv = m->hv(H_nv), na = m->hv(H_na);
-  T* stage_buf = scratch;
-  T* tail = scratch + (size_t)m->hv(H_data_words) * B;
+  T* stage_pub = work + (split ? (size_t)m->hv(H_data_words) * B : 0);   // caller-side buffer of the stage passes
+  T* stage_ws = split ? work : stage_pub;                                  // state layout: every pass reuses the one workspace
+  T* tail = stage_pub + (size_t)m->hv(H_pub_words) * B;
   if (set_smem<T>((const void*)k_rk4_stage<T>, blob_b)) return 1;
-  if (run_forward<T>(m, in, out, B, MJT_MODE_FORWARD, st, &n)) return 1;
+  if (run_forward<T>(m, in, out, ws, B, MJT_MODE_FORWARD | MJT_MODE_CHECK | fixed, UPTO_ALL, st, &n)) return 1;
   total += n;
   T* prev = out;
   for (int i = 0; i < 3; ++i) {
@@ -332,11 +364,11 @@ static int run_step(const mjtModel* m, const MjtIn& in, T* out, T* scratch, int 
     sin.act = tail + (size_t)(nq + nv) * B;
     sin.time = tail + (size_t)(nq + nv + na) * B;
     // warm start carried from the previous stage's solution (the running Data of the reference's loop)
-    sin.qacc_warmstart = prev + (size_t)m->hv(MJT_OFF_D + D_qacc_warmstart) * B;
-    sin.sensordata = prev + (size_t)m->hv(MJT_OFF_D + D_sensordata) * B;
-    if (run_forward<T>(m, sin, stage_buf, B, MJT_MODE_FORWARD, st, &n)) return 1;
+    sin.qacc_warmstart = prev + (size_t)m->hv(MJT_OFF_P + P_qacc_warmstart) * B;
+    sin.sensordata = m->hv(H_nsensordata) > 0 ? prev + (size_t)m->hv(MJT_OFF_P + P_sensordata) * B : nullptr;
+    if (run_forward<T>(m, sin, stage_pub, stage_ws, B, MJT_MODE_FORWARD | fixed, UPTO_ALL, st, &n)) return 1;
     total += n;
-    prev = stage_buf;
+    prev = stage_pub;
   }
   LAUNCH("k_rk4_stage", st, k_rk4_stage<T><<<gx, threads, blob_b, st>>>(m->d_blob, m->blob_words, out, prev, tail, B, 3));
   ++total;
@@ -356,20 +388,29 @@ static int check_args(const mjtModel* m, const mjtStateIn* in, void* out, int ne
   return 0;
 }
 
-extern "C" int mjt_step(const mjtModel* m, const mjtStateIn* in, void* out, void* scratch, int nenv, void* stream) {
+extern "C" int mjt_step(const mjtModel* m, const mjtStateIn* in, void* out, void* work, int nenv, int flags, void* stream) {
   if (check_args(m, in, out, nenv)) return 1;
+  if (flags & ~MJT_FLAG_FIXED_ITERATIONS) return fail("mjt_step: unknown flag (only MJT_FLAG_FIXED_ITERATIONS applies to a step)");
   const MjtIn i = to_in(in);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return m->f64 ? run_step<double>(m, i, (double*)out, (double*)scratch, nenv, st, nullptr)
-                : run_step<float>(m, i, (float*)out, (float*)scratch, nenv, st, nullptr);
+  return m->f64 ? run_step<double>(m, i, (double*)out, (double*)work, nenv, flags, st, nullptr)
+                : run_step<float>(m, i, (float*)out, (float*)work, nenv, flags, st, nullptr);
 }
 
-extern "C" int mjt_forward(const mjtModel* m, const mjtStateIn* in, void* out, int nenv, void* stream) {
+extern "C" int mjt_forward(const mjtModel* m, const mjtStateIn* in, void* out, void* work, int nenv, int flags, void* stream) {
   if (check_args(m, in, out, nenv)) return 1;
+  const bool split = m->state_layout();
+  if (split && !work) return fail("mjt_forward: the state layout needs the work buffer (mjt_model_scratch_words)");
+  int upto = UPTO_ALL;
+  if (flags & MJT_FLAG_UPTO_SMOOTH) upto = UPTO_SMOOTH;
+  else if (flags & MJT_FLAG_UPTO_COLLISION) upto = UPTO_COLLISION;
+  else if (flags & MJT_FLAG_UPTO_CONSTRAINT) upto = UPTO_CONSTRAINT;
+  if (upto != UPTO_ALL && split) return fail("mjt_forward: partial forward passes need the full layout (their outputs are derived fields)");
+  const int mode = MJT_MODE_FORWARD | ((flags & MJT_FLAG_FIXED_ITERATIONS) ? MJT_MODE_FIXED : 0);
   const MjtIn i = to_in(in);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return m->f64 ? run_forward<double>(m, i, (double*)out, nenv, MJT_MODE_FORWARD, st, nullptr)
-                : run_forward<float>(m, i, (float*)out, nenv, MJT_MODE_FORWARD, st, nullptr);
+  return m->f64 ? run_forward<double>(m, i, (double*)out, split ? (double*)work : (double*)out, nenv, mode, upto, st, nullptr)
+                : run_forward<float>(m, i, (float*)out, split ? (float*)work : (float*)out, nenv, mode, upto, st, nullptr);
 }
 
 extern "C" int mjt_step_launches(const mjtModel* m) {

@@ -41,8 +41,11 @@ enum { DYN_NONE = 0, DYN_INTEGRATOR = 1, DYN_FILTER = 2, DYN_FILTEREXACT = 3, DY
 enum { GAIN_FIXED = 0, GAIN_AFFINE = 1, GAIN_MUSCLE = 2 };
 enum { BIAS_NONE = 0, BIAS_AFFINE = 1, BIAS_MUSCLE = 2 };
 
-// run-mode flags shared with the host API
-enum { MJT_MODE_STEP = 1, MJT_MODE_FORWARD = 2 };
+// run-mode flags shared with the host API: the low two bits select step / forward; MJT_MODE_CHECK runs the reference's
+// _check_state sanitisation (forward.py:44-59: once, at the start of step(); not in forward() nor in the RK4 sub-stages);
+// MJT_MODE_FIXED = step(..., fixed_iterations=True): the solver and its line search run their configured iteration counts
+// with no termination test (solver.py:484-487, 536-537)
+enum { MJT_MODE_STEP = 1, MJT_MODE_FORWARD = 2, MJT_MODE_KIND = 3, MJT_MODE_CHECK = 4, MJT_MODE_FIXED = 8 };
 
 // ---------------------------------------------------------------------------------------------------------
 // Input state: device pointers to env-minor arrays with batch stride B (one (n, B) array per field).
@@ -62,6 +65,7 @@ struct ModelView {
   __device__ __forceinline__ const int* I(int k) const { return w + w[MJT_OFF_I + k]; }
   __device__ __forceinline__ const T* F(int k) const { return f + w[MJT_OFF_F + k]; }
   __device__ __forceinline__ int D(int k) const { return w[MJT_OFF_D + k]; }
+  __device__ __forceinline__ int P(int k) const { return w[MJT_OFF_P + k]; }   // public-buffer offset (layout.py P_FIELDS)
   __device__ __forceinline__ T opt(int k) const { return F(F_opt)[k]; }
 };
 

@@ -49,7 +49,9 @@ __host__ __device__ inline SolveLayout solve_layout(int nv, int nefc, int jc_wor
   s.oMask = o; o += s.nchunk;  // active-row bitmask over the *live* rows (one word per G rows, stored in T-sized slots)
   // ints: live-row list (nrow), compact position of every source (nsrc) and, for the live tile, its J offset (nsrc)
   s.oLive = o; o += compact ? ((nrow + nsrc * (rcap > 0 ? 2 : 1)) * 4 + tsize - 1) / tsize : 0;
-  s.words = (o + 3) & ~3;
+  // odd region stride: the cooperative load / store phase has consecutive threads serve consecutive envs (one region apart),
+  // which is conflict-free across the shared-memory banks only when the stride is odd in units of T
+  s.words = o | 1;
   return s;
 }
 
@@ -59,6 +61,6 @@ struct MjtIn;
 // compact: 0 = every row in place, 1 = live-row list over the full tile, 2 = live tile (rcap row slots, jcap J words);
 // only_flagged: process only envs whose overflow flag (hidden Data field scr_ovf) was set by a compact == 2 launch.
 cudaError_t mjt_launch_solve_f32(int lanes, int dpl, int compact, int rcap, int jcap, int only_flagged, int grid, int threads, size_t smem, size_t smem_attr, cudaStream_t st,
-                                 const int* blob, const int* sblob, int solve_words, const MjtIn& in, float* out, int B, int mode);
+                                 const int* blob, const int* sblob, int solve_words, const MjtIn& in, float* out, float* pub, int B, int mode);
 cudaError_t mjt_launch_solve_f64(int lanes, int dpl, int compact, int rcap, int jcap, int only_flagged, int grid, int threads, size_t smem, size_t smem_attr, cudaStream_t st,
-                                 const int* blob, const int* sblob, int solve_words, const MjtIn& in, double* out, int B, int mode);
+                                 const int* blob, const int* sblob, int solve_words, const MjtIn& in, double* out, double* pub, int B, int mode);

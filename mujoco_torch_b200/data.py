@@ -107,7 +107,16 @@ class _TensorBag:
     def clone(self, recurse: bool = True):
         if not recurse:
             return type(self)({k: (v.clone(False) if isinstance(v, _TensorBag) else v) for k, v in self._fields.items()}, self._meta)
-        return self._map(lambda t: t.clone())
+        nb = len(self.batch_size)
+
+        def env_minor_clone(t, ne):
+            # A batched container is cloned into env-minor memory (batch index fastest; same logical shape and values): the
+            # layout the kernels read, so stepping a freshly cloned batch needs no per-step transposes of its inputs.
+            if nb == 1 and ne >= 1 and t.shape[0] > 1:
+                return t.movedim(0, -1).contiguous().movedim(-1, 0)
+            return t.clone()
+
+        return self._map_batched(env_minor_clone)
 
     def to(self, *args, **kw):
         device = kw.get("device")

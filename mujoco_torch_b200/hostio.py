@@ -17,6 +17,8 @@ from .model import Model
 
 IN_FIELDS = ("qpos", "qvel", "qacc_warmstart", "ctrl")
 OUT_FIELDS = ("qpos", "qvel", "qacc_warmstart")
+# State that does not travel by default (activations, time) is carried on the device from step to step.
+CARRIED_FIELDS = ("act", "time")
 
 
 class HostPipeline:
@@ -24,16 +26,19 @@ class HostPipeline:
 
     * ``pipe.host[c][name]`` -- pinned ``(n, B_c)`` tensors (env-minor, the layout the kernels read) per chunk ``c``;
       the caller writes ``ctrl`` (and may rewrite any state field) there between steps.
-    * ``step()`` copies the inputs of every chunk to the device, steps it, and copies ``qpos, qvel, qacc_warmstart``
-      back into the same pinned buffers.  It returns after all streams have drained.
+    * ``step()`` copies the inputs of every chunk to the device, steps it (``outputs="state"`` by default: nothing but the
+      state is materialised), and copies ``qpos, qvel, qacc_warmstart`` back into the same pinned buffers.  It returns after
+      all streams have drained.  Activations and time stay on the device and are carried from step to step.
     """
 
-    def __init__(self, m: Model, d: Data, nchunk: int | None = None, in_fields=IN_FIELDS, out_fields=OUT_FIELDS):
+    def __init__(self, m: Model, d: Data, nchunk: int | None = None, in_fields=IN_FIELDS, out_fields=OUT_FIELDS, outputs: str = "state"):
         if d.qpos.dim() != 2:
             raise ValueError("HostPipeline expects a batched Data with one leading batch dim")
         if not d.qpos.is_cuda:
             raise RuntimeError("HostPipeline needs the template Data on the model's CUDA device (there is no CPU path)")
-        self.m, self.in_fields, self.out_fields = m, tuple(in_fields), tuple(out_fields)
+        self.m, self.in_fields, self.out_fields, self.outputs = m, tuple(in_fields), tuple(out_fields), outputs
+        # every state field the step advances is either sent from the host each step or kept current on the device
+        self.carried = tuple(k for k in CARRIED_FIELDS if k not in self.in_fields and getattr(d, k).numel() > 0)
         B = d.qpos.shape[0]
         if nchunk is None:   # measured (profiles/README.md): two chunks overlap PCIe with kernels once a chunk still fills the GPU
             nchunk = 2 if B >= 16384 else 1
@@ -65,7 +70,9 @@ class HostPipeline:
         for c, st in enumerate(self.streams):
             with torch.cuda.stream(st):
                 dev = {k: self.host[c][k].to(self.base[c].qpos.device, non_blocking=True).t() for k in self.in_fields}
-                out = api.step(self.m, self.base[c].replace(**dev))
+                out = api.step(self.m, self.base[c].replace(**dev), outputs=self.outputs)
+                if self.carried:
+                    self.base[c] = self.base[c].replace(**{k: getattr(out, k) for k in self.carried})
                 for k in self.out_fields:
                     v = getattr(out, k)
                     self.host[c][k].copy_(v.reshape(v.shape[0], -1).t(), non_blocking=True)

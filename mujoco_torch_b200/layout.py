@@ -4,7 +4,7 @@
 kernels and the Python packer agree on every slot index.
 
 ModelBlob (one contiguous int32 buffer, copied to shared memory once per CTA with a TMA bulk copy):
-    [ H scalars | I offsets | F offsets | D offsets | D sizes | int arrays ... | pad16 | float arrays ... ]
+    [ H scalars | I offsets | F offsets | D offsets | D sizes | P offsets | int arrays ... | pad16 | float arrays ... ]
 Float arrays are stored in the compute dtype (f32 or f64); F offsets are in elements from the float base.
 The Data buffer is a (W, B) array, env-minor: word k of env e lives at buf[k * B + e].
 """
@@ -22,6 +22,7 @@ disableflags solver cone integrator iterations ls_iterations
 data_words has_gravcomp has_fluid nv_pad nlim_sh nlim_ball nfric_dof nfric_ten nlim_ten
 ne_connect ne_weld ne_joint maskwords nsens_pos nsens_vel nsens_acc
 nconvex nrfgeom jc_words solve_blob_words live_rcap live_jcap
+layout_state pub_words n_mnz
 """.split()
 
 # ---- int arrays ---------------------------------------------------------------------------
@@ -43,6 +44,7 @@ sens_type sens_objid sens_adr sens_dim sens_datatype sens_stage sens_objtype sen
 rf_geom
 body_geomadr body_geomnum body_geom body_siteadr body_sitenum body_site
 cvx_geom cvx_nvert cvx_nface cvx_nfv cvx_nedge cvx_vertadr cvx_faceadr cvx_edgeadr cvx_normadr geom_cvx cvx_face cvx_edge
+m_nz geom_need
 """.split()
 
 # ---- float arrays -------------------------------------------------------------------------
@@ -103,6 +105,18 @@ PAIR_NCON = dict(PLANE_SPHERE=1, PLANE_CAPSULE=2, SPHERE_SPHERE=1, SPHERE_CAPSUL
                  SPHERE_CONVEX=1, CAPSULE_CONVEX=2, CONVEX_CONVEX=4)
 
 HIDDEN_FIELDS = {"scr_cacc", "scr_cfrc", "scr_live", "scr_ovf"}
+
+# ---- the "state" output layout (``step(..., outputs="state")``) --------------------------------------------------
+# Same kernels, second blob: its D-offset table describes a split buffer.  Words [0, pub_words) are the PUBLIC part -- the
+# fields below, a small (pub_words, B) buffer returned to the caller; words >= pub_words live in a WORKSPACE the caller
+# lends to the step (scratch, reused from step to step).  Fields nothing downstream reads (xmat, cinert, cdof_dot, dense qM /
+# qLD / efc_J / actuator_moment, qacc_smooth, efc_force ...) get offset -1 and are never written; qM is stored as a packed
+# lower triangle and efc_J compacted to each row's column support (the form k_solve keeps in shared memory anyway).
+STATE_PUBLIC = ("qpos", "qvel", "act", "time", "qacc", "qacc_warmstart", "act_dot", "sensordata", "qfrc_constraint")
+# P table of the blob header: word offsets of the public fields inside the buffer handed back to the caller.  Full layout:
+# the same buffer and offsets as the D table.  State layout: offsets inside the small public buffer (-1 = absent); the D
+# table then addresses the workspace, which keeps its own pre-integration working copies of qpos / qvel / act / time.
+P_FIELDS = STATE_PUBLIC
 MAGIC = 0x4D4A5431  # "MJT1"
 
 
@@ -125,6 +139,7 @@ def header_text() -> str:
     enum("I_", I_ARRAYS, "NUM_I")
     enum("F_", F_ARRAYS, "NUM_F")
     enum("D_", [n for n, _ in D_FIELDS], "NUM_D")
+    enum("P_", list(P_FIELDS), "NUM_P")
     enum("OPT_", OPT_SLOTS, "NUM_OPT")
     enum("SRC_", SRC_TYPES, "NUM_SRC")
     enum("FN_", PAIR_FNS, "NUM_FN")
@@ -133,7 +148,8 @@ def header_text() -> str:
     out.append("#define MJT_OFF_F (NUM_H + NUM_I)")
     out.append("#define MJT_OFF_D (NUM_H + NUM_I + NUM_F)")
     out.append("#define MJT_OFF_DSZ (NUM_H + NUM_I + NUM_F + NUM_D)")
-    out.append("#define MJT_HDR_WORDS (NUM_H + NUM_I + NUM_F + 2 * NUM_D)")
+    out.append("#define MJT_OFF_P (NUM_H + NUM_I + NUM_F + 2 * NUM_D)")
+    out.append("#define MJT_HDR_WORDS (NUM_H + NUM_I + NUM_F + 2 * NUM_D + NUM_P)")
     out.append("")
     return "\n".join(out)
 

@@ -215,6 +215,7 @@ class Model:
         self._static()
         self._pack()
         self._handle = None
+        self._handles = {}   # layout name -> device handle (ops.model_handle)
         self._mid = None
 
     # ---- tensors mirroring MjModel fields on demand (qpos0, body_mass, ...)
@@ -536,7 +537,22 @@ class Model:
         F["cvx_vert"] = np.concatenate(vert_all) if vert_all else f([])
         F["cvx_norm"] = np.concatenate(norm_all) if norm_all else f([])
 
-        # Data field table
+        # structurally non-zero entries of the packed lower triangle of M: (a, b) with dof b an ancestor-or-self of dof a
+        # (support.make_m :50-80); a tendon armature couples arbitrary dofs, so then every entry counts
+        nP = self.nv * (self.nv + 1) // 2
+        if self.ntendon and np.any(np.asarray(mj.tendon_armature) != 0):
+            m_nz = list(range(nP))
+        else:
+            m_nz = []
+            for a in range(self.nv):
+                b = a
+                while b >= 0:
+                    m_nz.append(a * (a + 1) // 2 + b)
+                    b = int(mj.dof_parentid[b])
+            m_nz.sort()
+        I["m_nz"] = i32(m_nz)
+
+        # Data field tables of the two output layouts (layout.py)
         sizes = dict(nq=self.nq, nv=self.nv, nu=self.nu, na=self.na, nbody=self.nbody, njnt=self.njnt, ngeom=self.ngeom,
                      nsite=self.nsite, ntendon=self.ntendon, ncon=self.ncon, nefc=self.nefc, nsensordata=self.nsensordata,
                      nsrc=len(self.src))
@@ -546,6 +562,57 @@ class Model:
             self.field_shape[name], self.field_off[name] = shp, off
             off += int(np.prod(shp)) if shp else 1
         self.data_words = off
+        nwords = lambda shp: int(np.prod(shp)) if shp else 1
+        # -- "state" layout: public buffer (P table) + workspace (D table); see layout.py
+        S_ = {n: i for i, n in enumerate(L.SRC_TYPES)}
+        has_sens = self.nsensordata > 0
+        simple_trn = all(int(t) in (TrnType.JOINT, TrnType.JOINTINPARENT) and int(mj.jnt_type[int(np.asarray(mj.actuator_trnid).reshape(-1, 2)[u, 0])]) in (JointType.HINGE, JointType.SLIDE)
+                         for u, t in enumerate(np.asarray(mj.actuator_trntype)))
+        need = set("qpos qvel act time act_dot xpos xquat xipos xanchor xaxis subtree_com crb cdof cvel qM qfrc_bias qfrc_passive "
+                   "qfrc_gravcomp qfrc_actuator qfrc_smooth scr_cacc scr_cfrc scr_ovf".split())
+        if len(self.pairs) or has_sens:
+            need |= {"geom_xpos", "geom_xmat"}
+        if has_sens:
+            need |= {"site_xpos", "site_xmat", "xmat", "ximat", "actuator_length", "actuator_velocity", "actuator_force"}
+        if any(t in (S_["EQ_CONNECT"], S_["EQ_WELD"]) for t, _, _ in self.src):
+            need.add("xmat")
+        if self.opt.has_fluid_params:
+            need.add("ximat")
+        if self.ntendon:
+            need |= {"ten_length", "ten_J", "ten_velocity"}
+        if int(mj.opt.integrator) == IntegratorType.IMPLICITFAST and not simple_trn:
+            need.add("actuator_moment")
+        if self.ncon:
+            need |= {"contact_dist", "contact_pos", "contact_frame"}
+        if self.nefc:
+            need |= {"efc_J", "efc_D", "efc_aref", "scr_live"}
+            if self.nf:
+                need.add("efc_frictionloss")
+        ws_shape = dict(self.field_shape)
+        ws_shape["qM"], ws_shape["efc_J"] = (nP,), (self.sup["jc_words"],)
+        ws_off, off = {}, 0
+        for name, _ in L.D_FIELDS:
+            if name in need:
+                ws_off[name] = off
+                off += nwords(ws_shape[name])
+            else:
+                ws_off[name] = -1
+        ws_words = off
+        pub_off, off = {}, 0
+        for name in L.P_FIELDS:
+            if name == "qfrc_constraint" and self.nefc:
+                pub_off[name] = -1   # only a model without constraint rows passes it through (forward.py:390-396)
+                continue
+            pub_off[name] = off
+            off += nwords(self.field_shape[name])
+        pub_words = off
+        # geoms the state layout has to place: members of a collision pair, or everything when sensors may read them
+        geom_need = np.zeros(self.ngeom, np.int32)
+        if has_sens:
+            geom_need[:] = 1
+        for pr in self.pairs:
+            geom_need[pr["g1"]] = geom_need[pr["g2"]] = 1
+        self.state_layout = dict(pub_off=pub_off, pub_words=pub_words, ws_off=ws_off, ws_words=ws_words, ws_shape=ws_shape)
 
         S = {n: i for i, n in enumerate(L.SRC_TYPES)}
         cnt = lambda t: sum(1 for s in self.src if s[0] == S[t])
@@ -560,13 +627,19 @@ class Model:
                  nfric_dof=cnt("FRIC_DOF"), nfric_ten=cnt("FRIC_TEN"), nlim_ten=cnt("LIM_TEN"), ne_connect=cnt("EQ_CONNECT"),
                  ne_weld=cnt("EQ_WELD"), ne_joint=cnt("EQ_JOINT"), maskwords=self.maskwords, nsens_pos=int((st == 1).sum()),
                  nsens_vel=int((st == 2).sum()), nsens_acc=int((st == 3).sum()), nconvex=len(cv), nrfgeom=len(rf), jc_words=self.sup["jc_words"],
-                 live_rcap=self.live_caps[0], live_jcap=self.live_caps[1])
-        nH, nI, nF, nD = len(L.H_SCALARS), len(L.I_ARRAYS), len(L.F_ARRAYS), len(L.D_FIELDS)
-        def assemble(keep=None, extra=None):
+                 live_rcap=self.live_caps[0], live_jcap=self.live_caps[1], n_mnz=len(m_nz))
+        nH, nI, nF, nD, nPf = len(L.H_SCALARS), len(L.I_ARRAYS), len(L.F_ARRAYS), len(L.D_FIELDS), len(L.P_FIELDS)
+        def assemble(keep=None, extra=None, state=False):
             """One blob; with ``keep`` only the named arrays carry data (the others get length 0)."""
             Hh = dict(H)
             Hh.update(extra or {})
-            hdr = np.zeros(nH + nI + nF + 2 * nD, dtype=np.int32)
+            if state:
+                Hh.update(layout_state=1, data_words=ws_words, pub_words=pub_words)
+                I["geom_need"] = geom_need
+            else:
+                Hh.update(layout_state=0, pub_words=self.data_words)
+                I["geom_need"] = np.ones(self.ngeom, np.int32)
+            hdr = np.zeros(nH + nI + nF + 2 * nD + nPf, dtype=np.int32)
             ints, pos = [], hdr.size
             for k, name in enumerate(L.I_ARRAYS):
                 a = I[name] if keep is None or name in keep else np.zeros(0, np.int32)
@@ -584,8 +657,10 @@ class Model:
                     flts.append(np.zeros(1))
                     fpos += 1
             for k, (name, _) in enumerate(L.D_FIELDS):
-                hdr[nH + nI + nF + k] = self.field_off[name]
-                hdr[nH + nI + nF + nD + k] = int(np.prod(self.field_shape[name])) if self.field_shape[name] else 1
+                hdr[nH + nI + nF + k] = ws_off[name] if state else self.field_off[name]
+                hdr[nH + nI + nF + nD + k] = nwords(ws_shape[name] if state else self.field_shape[name])
+            for k, name in enumerate(L.P_FIELDS):
+                hdr[nH + nI + nF + 2 * nD + k] = pub_off[name] if state else self.field_off[name]
             fl_arr = np.concatenate(flts) if flts else np.zeros(0)
             fl_bytes = fl_arr.astype(np.float64 if f64 else np.float32).view(np.int32)
             Hh["float_base_words"] = pos_pad
@@ -601,13 +676,16 @@ class Model:
 
         # the solver kernel stages a reduced blob (only the tables it reads) so that more envs fit in shared memory
         solve_keep = set("jnt_type jnt_qposadr jnt_dofadr act_trntype act_trnid act_gear act_dyntype act_gaintype act_biastype act_actadr act_actnum act_actlimited "
-                         "src_row src_nrows src_nsup src_cadr sup_col row_src row_jadr tri_ab dof_sadr dof_sent jc_src "
+                         "src_row src_nrows src_nsup src_cadr sup_col row_src row_jadr tri_ab dof_sadr dof_sent jc_src m_nz "
                          "opt dof_damping act_actrange act_gainprm act_biasprm act_dynprm ten_damping".split())
-        solve_blob = assemble(solve_keep)
-        full = assemble(None, {"solve_blob_words": int(solve_blob.size)})
-        blob = np.concatenate([full, solve_blob])
-        self.blob_np = blob
-        self.blob = torch.from_numpy(blob.copy())
+        def both(state):
+            solve_blob = assemble(solve_keep, None, state)
+            full = assemble(None, {"solve_blob_words": int(solve_blob.size)}, state)
+            return np.concatenate([full, solve_blob])
+
+        self.blob_np = both(False)
+        self.state_layout["blob_np"] = both(True)
+        self.blob = torch.from_numpy(self.blob_np.copy())
         self._I, self._F = I, F
 
     # ---- device movement (reference types._model_to :991-1010)
@@ -620,6 +698,7 @@ class Model:
         new.device = device
         new.blob = self.blob.to(device)
         new._handle = None
+        new._handles = {}
         new._mid = None
         new.__dict__.pop("_static_contact_cache", None)
         return new

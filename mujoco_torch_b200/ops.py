@@ -17,7 +17,12 @@ import torch
 _LIB_PATH = os.environ.get("MJT_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libmjt_b200.so")
 _lib = None
 
+# `mode` argument of the op: kind (step / forward) in the low two bits, then the options below
 MODE_STEP, MODE_FORWARD = 1, 2
+MODE_STATE = 4        # outputs="state": the model's state layout (layout.py) -- only the state fields are produced
+MODE_FIXED = 8        # fixed_iterations=True (reference forward.step :463)
+MODE_UPTO_SHIFT = 4   # bits 4-5: stop a forward pass after k_smooth (1) / k_collision (2) / k_constraint (3); 0 = all stages
+FLAG_FIXED, FLAG_UPTO = 1, {1: 2, 2: 4, 3: 8}   # include/mjt.h MJT_FLAG_*
 
 
 class StateIn(ctypes.Structure):
@@ -42,14 +47,14 @@ def lib():
     L.mjt_model_create.restype = ctypes.c_int
     L.mjt_model_destroy.argtypes = [ctypes.c_void_p]
     L.mjt_model_destroy.restype = None
-    for fn in ("mjt_model_data_words", "mjt_model_scratch_words", "mjt_model_dtype_size", "mjt_step_launches"):
+    for fn in ("mjt_model_data_words", "mjt_model_scratch_words", "mjt_model_dtype_size", "mjt_step_launches", "mjt_model_layout"):
         getattr(L, fn).argtypes = [ctypes.c_void_p]
         getattr(L, fn).restype = ctypes.c_int
     L.mjt_model_field.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
     L.mjt_model_field.restype = ctypes.c_int
-    L.mjt_step.argtypes = [ctypes.c_void_p, ctypes.POINTER(StateIn), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    L.mjt_step.argtypes = [ctypes.c_void_p, ctypes.POINTER(StateIn), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     L.mjt_step.restype = ctypes.c_int
-    L.mjt_forward.argtypes = [ctypes.c_void_p, ctypes.POINTER(StateIn), ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    L.mjt_forward.argtypes = [ctypes.c_void_p, ctypes.POINTER(StateIn), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     L.mjt_forward.restype = ctypes.c_int
     L.mjt_profile_begin.restype = None
     L.mjt_profile_end.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
@@ -85,7 +90,7 @@ def profile_end() -> dict:
     return out
 
 
-EXPORTS = ("mjt_version", "mjt_last_error", "mjt_model_create", "mjt_model_destroy", "mjt_model_data_words",
+EXPORTS = ("mjt_version", "mjt_last_error", "mjt_model_create", "mjt_model_destroy", "mjt_model_layout", "mjt_model_data_words",
            "mjt_model_scratch_words", "mjt_model_dtype_size", "mjt_model_field", "mjt_step", "mjt_forward", "mjt_step_launches",
            "mjt_profile_begin", "mjt_profile_end", "mjt_solve_config", "mjt_fma_peak")
 
@@ -108,20 +113,24 @@ def register_model(model) -> int:
     return mid
 
 
-def model_handle(model):
-    """Device handle of a Model (created lazily on the model's CUDA device)."""
-    if model._handle is not None:
-        return model._handle
+def model_handle(model, layout: str = "full"):
+    """Device handle of a Model for one output layout ("full" / "state"), created lazily on the model's CUDA device."""
+    h = model._handles.get(layout)
+    if h is not None:
+        return h
     if model.device.type != "cuda":
         raise RuntimeError("mujoco_torch_b200 runs on CUDA only: move the model with .to('cuda') (there is no CPU path)")
     L = lib()
-    blob = model.blob_np
+    blob = model.blob_np if layout == "full" else model.state_layout["blob_np"]
     h = ctypes.c_void_p()
     dev = model.device.index if model.device.index is not None else torch.cuda.current_device()
     _check(L.mjt_model_create(blob.ctypes.data_as(ctypes.c_void_p), blob.nbytes, dev, ctypes.byref(h)))
-    model._handle = h
+    model._handles[layout] = h
+    if layout == "full":
+        model._handle = h
     weakref.finalize(model, L.mjt_model_destroy, h)
-    assert L.mjt_model_data_words(h) == model.data_words
+    assert L.mjt_model_layout(h) == (0 if layout == "full" else 1)
+    assert L.mjt_model_data_words(h) == (model.data_words if layout == "full" else model.state_layout["pub_words"])
     return h
 
 
@@ -142,36 +151,6 @@ def _env_minor(t: torch.Tensor, batched: bool, dtype) -> torch.Tensor:
     return t.t().contiguous()
 
 
-# Inputs that usually stay the same tensor from step to step (user forces, mocap targets, equality switches): their env-minor
-# copy is kept per model and reused while the source is untouched (same storage, shape, strides and version counter), which
-# removes two strided-copy kernels from every Humanoid step.
-_CACHED_ARGS = ("qfrc_applied", "xfrc_applied", "mocap_pos", "mocap_quat", "eq_active")
-_MINOR_CACHE_SLOTS, _MINOR_CACHE_BYTES = 8, 512 << 20
-
-
-def _env_minor_cached(model, name, t: torch.Tensor, batched: bool, dtype) -> torch.Tensor:
-    if name not in _CACHED_ARGS or t.numel() == 0:
-        return _env_minor(t, batched, dtype)
-    try:
-        key = (t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()), t.dtype, str(t.device), batched)
-    except RuntimeError:   # inference tensors do not track versions: no reuse
-        return _env_minor(t, batched, dtype)
-    cache = model.__dict__.setdefault("_minor_cache", {})   # (name, storage address) -> (key, source, env-minor copy)
-    slot = (name, key[0])
-    hit = cache.get(slot)
-    if hit is not None and hit[0] == key:
-        return hit[2]
-    e = _env_minor(t, batched, dtype)
-    if e.data_ptr() != t.data_ptr():
-        cache.pop(slot, None)
-        cache[slot] = (key, t, e)   # the source is kept alive with its copy, so its address cannot be reused meanwhile
-        # HostPipeline steps several chunk templates in turn, so a few slots per input; bounded in count and in bytes
-        while len(cache) > 1 and (len(cache) > _MINOR_CACHE_SLOTS
-                                  or sum(v[2].numel() * v[2].element_size() for v in cache.values()) > _MINOR_CACHE_BYTES):
-            cache.pop(next(iter(cache)))
-    return e
-
-
 def _launch(model_id: int, mode: int, tensors) -> torch.Tensor:
     model = _MODELS.get(model_id)
     if model is None:
@@ -179,27 +158,35 @@ def _launch(model_id: int, mode: int, tensors) -> torch.Tensor:
     qpos = tensors[0]
     if not qpos.is_cuda:
         raise RuntimeError("mjt::step is CUDA-only; got a CPU tensor (no CPU fallback exists)")
+    if qpos.device != model.device and not (model.device.index is None and model.device.type == "cuda"):
+        raise RuntimeError(f"mjt: Data is on {qpos.device} but the Model is on {model.device} (move one of them with .to())")
     batched = qpos.dim() == 2
     B = qpos.shape[0] if batched else 1
-    h = model_handle(model)
+    layout = "state" if mode & MODE_STATE else "full"
+    h = model_handle(model, layout)
     L = lib()
     keep = []
     st = StateIn()
     for name, t in zip(_STATE_ARGS, tensors):
         want = torch.int32 if name == "eq_active" else model.dtype
-        e = _env_minor_cached(model, name, t, batched, want)
+        e = _env_minor(t, batched, want)   # no copy when the tensor already is an env-minor view (every output of a step is)
         keep.append(e)
         setattr(st, name, e.data_ptr() if e.numel() else None)
     st.qacc = None
+    flags = FLAG_FIXED if mode & MODE_FIXED else 0
     with torch.cuda.device(qpos.device):
-        out = torch.empty((model.data_words, B), dtype=model.dtype, device=qpos.device)
+        out = torch.empty((L.mjt_model_data_words(h), B), dtype=model.dtype, device=qpos.device)
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        if mode == MODE_STEP:
-            sw = L.mjt_model_scratch_words(h)
-            scratch = torch.empty((sw, B), dtype=model.dtype, device=qpos.device) if sw else None
-            _check(L.mjt_step(h, ctypes.byref(st), out.data_ptr(), scratch.data_ptr() if sw else None, B, stream))
+        # the work buffer (state layout: the workspace of derived quantities; RK4: stage buffers) goes back to the caching
+        # allocator when this call returns: stream-ordered reuse, nothing outlives the step
+        sw = L.mjt_model_scratch_words(h)
+        work = torch.empty((sw, B), dtype=model.dtype, device=qpos.device) if sw else None
+        wp = work.data_ptr() if sw else None
+        if mode & 3 == MODE_STEP:
+            _check(L.mjt_step(h, ctypes.byref(st), out.data_ptr(), wp, B, flags, stream))
         else:
-            _check(L.mjt_forward(h, ctypes.byref(st), out.data_ptr(), B, stream))
+            upto = (mode >> MODE_UPTO_SHIFT) & 3
+            _check(L.mjt_forward(h, ctypes.byref(st), out.data_ptr(), wp, B, flags | FLAG_UPTO.get(upto, 0), stream))
     return out.t() if batched else out[:, 0]
 
 
@@ -216,9 +203,10 @@ def run(model_id: int, mode: int, qpos: torch.Tensor, qvel: torch.Tensor, act: t
 @run.register_fake
 def _(model_id, mode, qpos, *rest):
     model = _MODELS[model_id]
+    words = model.state_layout["pub_words"] if mode & MODE_STATE else model.data_words
     if qpos.dim() == 2:
-        return qpos.new_empty((model.data_words, qpos.shape[0])).t()
-    return qpos.new_empty((model.data_words,))
+        return qpos.new_empty((words, qpos.shape[0]), dtype=model.dtype).t()
+    return qpos.new_empty((words,), dtype=model.dtype)
 
 
 @run.register_vmap

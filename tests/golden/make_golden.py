@@ -92,21 +92,27 @@ CASES = [
     ("shapes_elliptic", "shapes", {"cone": 1}, 6, -1.0, 1),
     ("stack_rk4", "stack", {}, 8, -2.0, 1),
     # the reference's own equality.xml (site-based weld / connect, inactive; joint equality; box, sphere and plane contacts).
-    # Recorded into cpu_only/: it pins the oracle now, the CUDA path joins once it has been run against it on a GPU.
-    ("cpu_only/equality_sites", "equality", {}, 4, 0.3, 1),
+
+    ("equality_sites", "equality", {}, 4, 0.3, 1),
     # the reference's control-moment-gyro satellites (free-floating, no contacts: smooth dynamics + actuation only)
-    ("cpu_only/satellite_small", "satellite_small", {}, 3, 0.0, 2),
-    ("cpu_only/satellite_large", "satellite_large", {}, 3, 0.0, 2),
+    ("satellite_small", "satellite_small", {}, 3, 0.0, 2),
+    ("satellite_large", "satellite_large", {}, 3, 0.0, 2),
     # step(..., fixed_iterations=True): exactly `iterations` solver and `ls_iterations` line-search iterations, no termination
     # test (solver.py:484-487, 536-537).  "fixed_iterations" is not a model option: it is passed to step() and stripped here.
-    ("cpu_only/halfcheetah_fixed_iterations", "halfcheetah", {"iterations": 6, "ls_iterations": 5, "fixed_iterations": 1}, 4, 0.6, 1),
+    ("halfcheetah_fixed_iterations", "halfcheetah", {"iterations": 6, "ls_iterations": 5, "fixed_iterations": 1}, 4, 0.6, 1),
     # CG run past convergence: the early-exit path stops at `tolerance` (2e-7 relative away in qacc), the fixed path keeps going.
     # (A short unconverged CG run is not usable as a pin: the oracle's own answer moves by 3e-3 under 2e-16 input perturbations.)
-    ("cpu_only/ant_zoo_cg_fixed_iterations", "ant_zoo", {"cone": 1, "solver": 1, "iterations": 60, "ls_iterations": 20, "fixed_iterations": 1}, 4, 0.2, 1),
+    ("ant_zoo_cg_fixed_iterations", "ant_zoo", {"cone": 1, "solver": 1, "iterations": 60, "ls_iterations": 20, "fixed_iterations": 1}, 4, 0.2, 1),
 ]
 
 
+# every fixture records at least this many envs (the per-fixture counts in CASES are the historical minimum)
+MIN_ENVS = int(os.environ.get("MJT_GOLDEN_ENVS", "32"))
+OUT_DIR = os.environ.get("MJT_GOLDEN_OUT", os.path.join(ROOT, "tests", "golden"))
+
+
 def run_case(name, model, opt, B, drop, nsteps):
+    B = max(B, MIN_ENVS)
     fixed = bool(opt.get("fixed_iterations", 0))
     lite = util.load_model(model, **{k: v for k, v in opt.items() if k != "fixed_iterations"})
     qpos, qvel, ctrl = util.seeded_state(lite, B, drop=drop)
@@ -136,10 +142,10 @@ def run_case(name, model, opt, B, drop, nsteps):
         save["out_" + k] = np.stack(v)
     for k, v in cons.items():
         save["contact_" + k] = np.stack(v)
-    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    path = os.path.join(OUT_DIR, name + ".npz")
     os.makedirs(os.path.dirname(path), exist_ok=True)
     np.savez_compressed(path, **save)
-    print(f"{name}: B={B} steps={nsteps} qpos[0,:3]={save['out_qpos'][0, :3]} -> {os.path.relpath(path, ROOT)}")
+    print(f"{name}: B={B} steps={nsteps} qpos[0,:3]={save['out_qpos'][0, :3]} -> {os.path.relpath(path, ROOT)}", flush=True)
 
 
 if __name__ == "__main__":

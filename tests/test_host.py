@@ -219,30 +219,27 @@ def test_device_get_into_follows_the_reference_rules():
         mt.device_get_into([blank(())], mt.make_data(mx))
 
 
-def test_env_minor_input_cache_rules():
-    """ops._env_minor_cached (pure tensor logic, exercised here on CPU tensors): reuse while the source is untouched, refresh on
-    an in-place write or a new tensor, never for per-step inputs, bounded in slots."""
-    class M:   # stands in for a Model: only carries the cache dict
-        pass
+def test_env_minor_inputs_need_no_copy():
+    """The op reads env-minor (n, B) arrays.  A batched Data cloned from `make_data(...).expand(B)` and every output of a step
+    already have that memory layout, so `ops._env_minor` hands their storage to the kernels as it is; only a row-major tensor
+    the caller puts into the Data is transposed (once per step -- there is no cache that could go stale)."""
+    import mujoco_torch_b200 as mt
 
-    m = M()
-    x = torch.zeros(8, 6)
-    a = ops._env_minor_cached(m, "xfrc_applied", x, True, torch.float32)
-    assert a.shape == (6, 8) and a.is_contiguous()
-    assert ops._env_minor_cached(m, "xfrc_applied", x, True, torch.float32) is a          # untouched source: reused
-    x[3, 2] = 5.0                                                                          # in-place write: new version
-    b = ops._env_minor_cached(m, "xfrc_applied", x, True, torch.float32)
-    assert b is not a and float(b[2, 3]) == 5.0
-    y = x.clone()
-    c = ops._env_minor_cached(m, "xfrc_applied", y, True, torch.float32)                   # another tensor: its own slot
-    assert c is not b and ops._env_minor_cached(m, "xfrc_applied", x, True, torch.float32) is b
-    q = torch.zeros(8, 3)
-    assert ops._env_minor_cached(m, "qpos", q, True, torch.float32) is not ops._env_minor_cached(m, "qpos", q, True, torch.float32)
-    em = torch.zeros(6, 8).t()                                                             # already env-minor: no copy, no slot
-    assert ops._env_minor_cached(m, "qfrc_applied", em, True, torch.float32).data_ptr() == em.data_ptr()
-    for _ in range(3 * ops._MINOR_CACHE_SLOTS):
-        ops._env_minor_cached(m, "mocap_pos", torch.zeros(8, 3), True, torch.float32)
-    assert len(m._minor_cache) <= ops._MINOR_CACHE_SLOTS
+    mx = mt.device_put(util.load_model("humanoid"), dtype=torch.float32)
+    d = mt.make_data(mx).expand(8).clone()
+    for name in ("qpos", "qvel", "qfrc_applied", "xfrc_applied", "ctrl"):
+        t = getattr(d, name)
+        flat = t.reshape(t.shape[0], -1)
+        e = ops._env_minor(flat, True, torch.float32)
+        assert e.is_contiguous() and e.shape == (flat.shape[1], 8)
+        assert e.data_ptr() == t.data_ptr(), f"{name}: a cloned batch should already be env-minor"
+    assert torch.equal(d.qpos, mt.make_data(mx).qpos.expand(8, -1))            # same values, same logical shape
+    d.xfrc_applied[3, 2, 1] = 5.0                                                 # in-place writes are seen (no copy in between)
+    assert float(ops._env_minor(d.xfrc_applied.reshape(8, -1), True, torch.float32)[2 * 6 + 1, 3]) == 5.0
+    x = torch.zeros(8, 6)                                                         # row-major: transposed copy
+    a = ops._env_minor(x, True, torch.float32)
+    assert a.shape == (6, 8) and a.is_contiguous() and a.data_ptr() != x.data_ptr()
+    assert not hasattr(ops, "_env_minor_cached")
 
 
 def test_bench_reference_arm_prints_one_contract_line():

@@ -111,7 +111,8 @@ def run_oracle(mj, qpos, qvel, ctrl, dtype=torch.float64, nsteps=1, warm=None, a
     return m, d
 
 
-def run_cuda(mj, qpos, qvel, ctrl, dtype=torch.float64, nsteps=1, warm=None, device="cuda:0", act=None):
+def run_cuda(mj, qpos, qvel, ctrl, dtype=torch.float64, nsteps=1, warm=None, device="cuda:0", act=None, fixed_iterations=False,
+             outputs="full"):
     import mujoco_torch_b200 as mt
 
     mx = mt.device_put(mj, dtype=dtype).to(device)
@@ -124,7 +125,7 @@ def run_cuda(mj, qpos, qvel, ctrl, dtype=torch.float64, nsteps=1, warm=None, dev
         kw["act"] = torch.as_tensor(act, device=device).to(dtype)
     d = d.replace(**kw)
     for _ in range(nsteps):
-        d = mt.step(mx, d)
+        d = mt.step(mx, d, fixed_iterations=fixed_iterations, outputs=outputs)
     torch.cuda.synchronize()
     return mx, d
 
