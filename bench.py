@@ -223,6 +223,9 @@ def main():
     ap.add_argument("--integrator", default=None, choices=["euler", "rk4", "implicitfast"])
     ap.add_argument("--solver", default=None, choices=["cg", "newton"])
     ap.add_argument("--cone", default=None, choices=["pyramidal", "elliptic"])
+    ap.add_argument("--outputs", default="state", choices=["state", "full"],
+                    help="what a step materialises: 'state' = the state fields only (what a rollout feeds back in), 'full' = every "
+                         "field of Data like the reference; the physics is identical (tests/test_gpu_api.py)")
     ap.add_argument("--cpu-batch", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -276,7 +279,7 @@ def main():
     # ---- device-resident throughput
     d = d0
     for i in range(args.warmup):
-        d = mt.step(mx, d.replace(ctrl=ctrls[i % 4]))
+        d = mt.step(mx, d.replace(ctrl=ctrls[i % 4]), outputs=args.outputs)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -291,7 +294,7 @@ def main():
         zeros_b = torch.zeros(B, dtype=dtype, device=dev)
     ev0.record()
     for i in range(args.steps):
-        d = mt.step(mx, d.replace(ctrl=ctrls[i % 4]))
+        d = mt.step(mx, d.replace(ctrl=ctrls[i % 4]), outputs=args.outputs)
         if gather is not None:
             if i:
                 gather.wait()
@@ -322,7 +325,7 @@ def main():
     ops.profile_begin()
     nprof = min(20, args.steps)
     for i in range(nprof):
-        d = mt.step(mx, d.replace(ctrl=ctrls[i % 4]))
+        d = mt.step(mx, d.replace(ctrl=ctrls[i % 4]), outputs=args.outputs)
     prof = ops.profile_end()
     kern = {k: v[0] / v[1] for k, v in prof.items()}
     per_step = {k: v[0] / nprof for k, v in prof.items()}

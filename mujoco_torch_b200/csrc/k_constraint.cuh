@@ -25,9 +25,10 @@ __device__ __forceinline__ void kbi(const ModelView<T>& m, const T* solref, cons
   if (dampratio <= T(0)) kk = -dampratio / (dmax * dmax);
   if (timeconst <= T(0)) bb = -timeconst / dmax;
   const T imp_x = t_abs(pos) / width;
-  const T imp_a = (T(1) / t_pow(mid, power - T(1))) * t_pow(imp_x, power);
-  const T imp_b = T(1) - (T(1) / t_pow(T(1) - mid, power - T(1))) * t_pow(T(1) - imp_x, power);
-  const T imp_y = imp_x < mid ? imp_a : imp_b;
+  // only the branch that is selected is evaluated (each costs two pow() calls); same expressions as the reference's imp_a / imp_b
+  T imp_y;
+  if (imp_x < mid) imp_y = (T(1) / t_pow(mid, power - T(1))) * t_pow(imp_x, power);
+  else imp_y = T(1) - (T(1) / t_pow(T(1) - mid, power - T(1))) * t_pow(T(1) - imp_x, power);
   T im = dmin + imp_y * (dmax - dmin);
   im = t_min(t_max(im, dmin), dmax);
   if (imp_x > T(1)) im = dmax;
@@ -86,6 +87,11 @@ struct RowOut {
   __device__ __forceinline__ void finish(int row, T jv, T pos, T pos_norm, T invweight, const T* solref, const T* solimp, T floss) const {
     T k, b, imp;
     kbi(m, solref, solimp, pos_norm, &k, &b, &imp);
+    finish_kbi(row, jv, pos, invweight, k, b, imp, floss);
+  }
+  // the same with (k, b, imp) already evaluated: the rows of one contact share them (same solref / solimp / penetration), and
+  // _kbi costs four pow() calls
+  __device__ __forceinline__ void finish_kbi(int row, T jv, T pos, T invweight, T k, T b, T imp, T floss) const {
     const T r = t_max(invweight * (T(1) - imp) / imp, T(MJT_MINVAL));
     d.set(m.D(D_efc_D) + row, T(1) / r);
     d.set(m.D(D_efc_aref) + row, -b * jv - k * imp * pos);
@@ -273,9 +279,11 @@ __device__ void constraint_source(const ModelView<T>& m, const MjtIn& in, const 
       nrm = t_sqrt(nrm) * active;
       const T* iw1 = m.F(F_body_invweight0) + 2 * b1;
       const T* iw2 = m.F(F_body_invweight0) + 2 * b2;
+      T kk, bb, imp;
+      kbi(m, m.F(F_eq_solref) + 2 * id, m.F(F_eq_solimp) + 5 * id, nrm, &kk, &bb, &imp);   // one evaluation for the 3 / 6 rows
       for (int k = 0; k < nrows; ++k) {
         const T iw = (k < 3) ? (iw1[0] + iw2[0]) : (iw1[1] + iw2[1]);
-        out.finish(row0 + k, jv[k], pos[k] * active, nrm, iw, m.F(F_eq_solref) + 2 * id, m.F(F_eq_solimp) + 5 * id, T(0));
+        out.finish_kbi(row0 + k, jv[k], pos[k] * active, iw, kk, bb, imp, T(0));
       }
     } break;
     case SRC_CONTACT: {  // :408-583
@@ -339,16 +347,21 @@ __device__ void constraint_source(const ModelView<T>& m, const MjtIn& in, const 
       } else if (!elliptic) {
         const T mu = fri[0];
         const T iw = (t + mu * mu * t) * T(2) * mu * mu / m.opt(OPT_impratio);
-        for (int e = 0; e < nrows; ++e) out.finish(row0 + e, jv[e], posa, posa, iw, solref, solimp, T(0));
+        T k, b, imp;
+        kbi(m, solref, solimp, posa, &k, &b, &imp);   // identical for every row of the pyramid
+        for (int e = 0; e < nrows; ++e) out.finish_kbi(row0 + e, jv[e], posa, iw, k, b, imp, T(0));
       } else {
         const T* srf0 = m.F(F_con_solreffriction) + 2 * c;
         const bool any = srf0[0] != T(0) || srf0[1] != T(0);
         const T srf[2] = {any ? srf0[0] : srf0[0] + solref[0], any ? srf0[1] : srf0[1] + solref[1]};
+        T k0, b0, imp0, k1, b1, imp1;   // normal row / friction rows (the impedance is the same: it depends on dist and solimp only)
+        kbi(m, solref, solimp, dist, &k0, &b0, &imp0);
+        kbi(m, srf, solimp, dist, &k1, &b1, &imp1);
         for (int e = 0; e < nrows; ++e) {
           T iw = t;
           if (e >= 1) iw = t / m.opt(OPT_impratio);
           if (e >= 2) iw = iw * (fri[0] * fri[0]) / (fri[e - 1] * fri[e - 1]);
-          out.finish(row0 + e, jv[e], e == 0 ? posa : T(0), dist, iw, e == 0 ? solref : srf, solimp, T(0));
+          out.finish_kbi(row0 + e, jv[e], e == 0 ? posa : T(0), iw, e == 0 ? k0 : k1, e == 0 ? b0 : b1, e == 0 ? imp0 : imp1, T(0));
         }
       }
     } break;

@@ -50,6 +50,13 @@ __device__ __forceinline__ T vec_bcast(const Vec<T, 2>& x, int i, unsigned gm) {
 
 __device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
 
+// A warp is an environment (G == 32), so every data-dependent decision of the solver is warp-uniform -- but the compiler
+// cannot see that a value reduced by shuffles is the same on all lanes, treats the branch as divergent and wraps every
+// shuffle behind it in a WARPSYNC.COLLECTIVE / ENDCOLLECTIVE pair plus BSSY / BSYNC reconvergence code.  Broadcasting the
+// decision from lane 0 (one SHFL) makes the uniformity visible.  Half-warp envs (G == 16) do diverge: value passes through.
+template <int G> __device__ __forceinline__ int uni(int v) { return G == 32 ? __shfl_sync(0xffffffffu, v, 0) : v; }
+template <int G> __device__ __forceinline__ bool unib(bool v) { return G == 32 ? (__shfl_sync(0xffffffffu, v ? 1 : 0, 0) != 0) : v; }
+
 // In-place Cholesky of a packed lower triangle for n <= G (one row per lane): lane i keeps row i of L in registers, so
 // the inner product reads only row j from shared memory (a broadcast) instead of two strided rows.  A free function of
 // scalars and pointers only: MJT_CHOL_CALL = 1 compiles it once per kernel (__noinline__; the unrolled body is ~1.5 k
@@ -108,7 +115,10 @@ struct SolveCtx {
   const int* tri_ab;
   const int* dof_sadr;
   const int* dof_sent;
-  unsigned gm;   // shuffle / barrier mask of this env's G lanes
+  unsigned gm_;   // shuffle / barrier mask of this env's G lanes (half-warp envs); use gmask()
+  // A full warp per env: the mask is the compile-time constant 0xffffffff, which lets the compiler emit plain SHFL / WARPSYNC.ALL
+  // instead of the mask-checking collective sequence it needs for a run-time mask.
+  __device__ __forceinline__ unsigned gmask() const { return G == 32 ? 0xffffffffu : gm_; }
   // COMPACT: row loops walk the live list (host picks it for models with more than two 32-row chunks); otherwise every
   // row is visited in place with no indirection
   static constexpr bool compact = COMPACT;
@@ -158,7 +168,7 @@ struct SolveCtx {
       int incl = cnt, jincl = jw;
 #pragma unroll
       for (int o = 1; o < G; o <<= 1) {
-        const int v = __shfl_up_sync(gm, incl, o, G), w = __shfl_up_sync(gm, jincl, o, G);
+        const int v = __shfl_up_sync(gmask(), incl, o, G), w = __shfl_up_sync(gmask(), jincl, o, G);
         if (lane >= o) { incl += v; jincl += w; }
       }
       const int start = base + incl - cnt, jstart = jbase + jincl - jw;
@@ -168,10 +178,10 @@ struct SolveCtx {
         if (start + cnt <= rcap)
           for (int e = 0; e < cnt; ++e) lr[start + e] = r0 + e;
       }
-      base += __shfl_sync(gm, incl, G - 1, G);
-      jbase += __shfl_sync(gm, jincl, G - 1, G);
+      base += __shfl_sync(gmask(), incl, G - 1, G);
+      jbase += __shfl_sync(gmask(), jincl, G - 1, G);
     }
-    __syncwarp(gm);
+    __syncwarp(gmask());
     if (base > rcap || jbase > jcap) return -1;
     const int oD = m.D(D_efc_D), oA = m.D(D_efc_aref), oF = m.D(D_efc_frictionloss), oJ = m.D(D_efc_J);
     for (int idx = lane; idx < base; idx += G) {
@@ -188,7 +198,7 @@ struct SolveCtx {
       T* dst = J + jp[sidx] + (r - src_row[sidx]) * ns;
       for (int k = lane; k < ns; k += G) dst[k] = d.get(jcompact ? oJ + row_jadr[r] + k : oJ + r * nv + col[k]);
     }
-    __syncwarp(gm);
+    __syncwarp(gmask());
     return base;
   }
   // Returns the number of live rows (warp-uniform).  The context itself stays immutable so that it lives in registers.
@@ -217,7 +227,7 @@ struct SolveCtx {
       int incl = cnt;
 #pragma unroll
       for (int o = 1; o < G; o <<= 1) {
-        const int v = __shfl_up_sync(gm, incl, o, G);
+        const int v = __shfl_up_sync(gmask(), incl, o, G);
         if (lane >= o) incl += v;
       }
       const int start = base + incl - cnt;
@@ -225,9 +235,9 @@ struct SolveCtx {
         sp[sidx] = live ? start : -1;
         for (int e = 0; e < cnt; ++e) lr[start + e] = r0 + e;
       }
-      base += __shfl_sync(gm, incl, G - 1, G);
+      base += __shfl_sync(gmask(), incl, G - 1, G);
     }
-    __syncwarp(gm);
+    __syncwarp(gmask());
     return base;
   }
 
@@ -241,16 +251,16 @@ struct SolveCtx {
     T p = 0;
 #pragma unroll
     for (int k = 0; k < DPL; ++k) p += a.v[k] * b.v[k];
-    return group_sum<T, G>(p, gm);
+    return group_sum<T, G>(p, gmask());
   }
   __device__ __forceinline__ void to_smem(const Vec<T, DPL>& a, T* dst) const {
-    __syncwarp(gm);
+    __syncwarp(gmask());
 #pragma unroll
     for (int k = 0; k < DPL; ++k) {
       const int i = lane + G * k;
       if (i < nv) dst[i] = a.v[k];
     }
-    __syncwarp(gm);
+    __syncwarp(gmask());
   }
   // y = A x for a symmetric matrix stored as a packed lower triangle
   __device__ __forceinline__ Vec<T, DPL> symv(const T* A, const Vec<T, DPL>& x) const {
@@ -288,7 +298,7 @@ struct SolveCtx {
       acc += acc2;
       out[vi(idx, r)] = sub ? acc - sub[vi(idx, r)] : acc;
     }
-    __syncwarp(gm);
+    __syncwarp(gmask());
   }
   // y = J^T f as a per-dof gather: lane i walks the (source, support position) pairs of dof i; rows of a source are
   // stored back to back (ns entries each).  f must be exactly zero on rows that carry no force.
@@ -313,7 +323,7 @@ struct SolveCtx {
     }
     return out;
   }
-  __device__ __forceinline__ void cholesky_rows(T* A) const { cholesky_rows_fn<T, G>(A, dinv(), nv, lane, gm); }
+  __device__ __forceinline__ void cholesky_rows(T* A) const { cholesky_rows_fn<T, G>(A, dinv(), nv, lane, gmask()); }
   __device__ __forceinline__ void cholesky(T* A) const {
     if (DPL == 1 && MJT_CHOL_ROWS) { cholesky_rows(A); return; }
     const int n = nv;
@@ -334,26 +344,51 @@ struct SolveCtx {
           t[p] = acc;
         }
       }
-      T sdiag = __shfl_sync(gm, t[0], 0, G);
+      T sdiag = __shfl_sync(gmask(), t[0], 0, G);
       if (big) sdiag += T(1e-10); else sdiag = t_max(sdiag, T(1e-12));
       const T inv = t_rsqrt(sdiag);
       const T ljj = sdiag * inv;
-      __syncwarp(gm);
+      __syncwarp(gmask());
 #pragma unroll
       for (int p = 0; p < DPL; ++p) {
         const int i = j + lane + G * p;
         if (i < n) A[tri(i) + j] = (i == j) ? ljj : t[p] * inv;
       }
       if (lane == 0) di[j] = inv;
-      __syncwarp(gm);
+      __syncwarp(gmask());
     }
   }
   // x <- (L L^T)^-1 x with x distributed one element per lane (reference small_cholesky_solve :132-168)
   __device__ __forceinline__ Vec<T, DPL> cho_solve(const T* Lm, Vec<T, DPL> x) const {
     const int n = nv;
     const T* di = dinv();
+    if constexpr (DPL == 1) {
+      // One dof per lane.  Lane j keeps its entry UNSCALED while the sweep passes over it: step i broadcasts the owner's
+      // product x_i * dinv_i, and the owner applies the same product to itself after the sweep -- the same arithmetic as
+      // scaling in place at step i, without the per-step "am I the owner" select.  The update is one predicated load + FMA.
+      const int j = lane;
+      const bool mine = j < n;
+      const T dl = mine ? di[j] : T(0);
+      T xv = x.v[0];
+      const T* rowp = Lm + tri(mine ? j : 0);   // row j of L
+#pragma unroll 4
+      for (int i = 0; i < n; ++i) {             // forward: L y = b
+        const T yi = __shfl_sync(gmask(), xv * dl, i, G);
+        if (mine && j > i) xv -= rowp[i] * yi;
+      }
+      xv *= dl;
+      const T* colp = Lm + (mine ? j : 0);
+#pragma unroll 4
+      for (int i = n - 1; i >= 0; --i) {        // backward: L^T z = y
+        const T zi = __shfl_sync(gmask(), xv * dl, i, G);
+        if (j < i) xv -= colp[tri(i)] * zi;
+      }
+      xv *= dl;
+      x.v[0] = xv;
+      return x;
+    } else {
     for (int i = 0; i < n; ++i) {
-      const T xi = vec_bcast<T, G>(x, i, gm) * di[i];
+      const T xi = vec_bcast<T, G>(x, i, gmask()) * di[i];
 #pragma unroll
       for (int k = 0; k < DPL; ++k) {
         const int j = lane + G * k;
@@ -362,7 +397,7 @@ struct SolveCtx {
       }
     }
     for (int i = n - 1; i >= 0; --i) {
-      const T xi = vec_bcast<T, G>(x, i, gm) * di[i];
+      const T xi = vec_bcast<T, G>(x, i, gmask()) * di[i];
       const T* rowi = Lm + tri(i);
 #pragma unroll
       for (int k = 0; k < DPL; ++k) {
@@ -372,6 +407,7 @@ struct SolveCtx {
       }
     }
     return x;
+    }
   }
   // bits k0 .. k0+nr-1 (nr <= 32) of the active-slot mask (one mask word per G slots)
   __device__ __forceinline__ unsigned active_bits(int k0, int nr) const {
@@ -390,9 +426,9 @@ struct SolveCtx {
   __device__ __forceinline__ void hessian(const T* D) const {
     T* H = Lp();
     const T* M0 = Mp();
-    __syncwarp(gm);   // the previous factor may still be read by lagging lanes
+    __syncwarp(gmask());   // the previous factor may still be read by lagging lanes
     for (int p = lane; p < L.nP; p += G) H[p] = M0[p];
-    __syncwarp(gm);
+    __syncwarp(gmask());
     // sources that touch a single dof (joint limits, dof friction): one lane per dof adds their diagonal terms
     for (int i = lane; i < nv; i += G) {
       T acc = T(0);
@@ -409,7 +445,7 @@ struct SolveCtx {
       }
       H[tri(i) + i] += acc;
     }
-    __syncwarp(gm);
+    __syncwarp(gmask());
     const int nsrc = m.h(H_nsrc);
     for (int sidx = 0; sidx < nsrc; ++sidx) {
       if (src_nsup[sidx] == 1) continue;
@@ -419,6 +455,7 @@ struct SolveCtx {
       unsigned act = 0;
       if (nr <= 32) act = active_bits(cs, nr);
       else for (int e = 0; e < nr; ++e) act |= slot_active(cs + e) ? 1u : 0u;
+      act = (unsigned)uni<G>((int)act);
       if (!act) continue;
       const int ns = src_nsup[sidx];
       const int* col = sup_col + src_cadr[sidx];
@@ -445,7 +482,7 @@ struct SolveCtx {
         }
         H[tri(col[a]) + col[b]] += acc;  // support columns are sorted ascending: col[a] >= col[b]
       }
-      __syncwarp(gm);
+      __syncwarp(gmask());
     }
   }
 };
@@ -455,7 +492,7 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
                           const SolveCtx<T, DPL, COMPACT, G, TILE>& c, const Vec<T, DPL>& qfrc_smooth, const Vec<T, DPL>& qacc_smooth, int mode) {
   typedef Vec<T, DPL> V;
   const int lane = c.lane;
-  const unsigned gm = c.gm;
+  const unsigned gm = c.gmask();
   const int nv = c.nv, nefc = c.nefc, flags = m.h(H_disableflags);
   const SolveLayout& Lo = c.L;
   T* const sm = c.s;
@@ -520,7 +557,7 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
     if (c.compact && !TILE)   // dead rows are never visited again: give them their final zeros now
       for (int r = lane; r < nefc; r += G) { Jaref[r] = T(0); jv[r] = T(0); force[r] = T(0); }
     // rows that can carry force this step; the rest are exactly-zero rows
-    const int nlive = TILE ? c.build_tile(d, D, aref, m.h(H_nf) > 0 ? floss : nullptr) : c.build_live(aref);
+    const int nlive = uni<G>(TILE ? c.build_tile(d, D, aref, m.h(H_nf) > 0 ? floss : nullptr) : c.build_live(aref));
     if (TILE) {
       if (lane == 0) d.set(m.D(D_scr_ovf), nlive < 0 ? T(1) : T(0));
       if (nlive < 0) return;   // does not fit the live tile: the full-tile launch that follows solves this env
@@ -574,6 +611,7 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
       if (newton) {
         unsigned any = 0;
         for (int ch = 0; (ch * G) < nlive; ++ch) any |= c.amask()[ch];
+        any = (unsigned)uni<G>((int)any);
         // no active row: H = M exactly, and chol(M) is already in Lm -- skip the assembly and the factorisation
         if (any || !lm_is_m) {
           c.hessian(D);
@@ -651,7 +689,7 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
           done = done || (lo.d0 < T(0) && lo.d0 > -gtol);
           done = done || (hi.d0 > T(0) && hi.d0 < gtol);
         }
-        if (done) break;
+        if (unib<G>(done)) break;
         Pt cand[3];
         al[0] = lo.alpha - lo.d0 / lo.d1;
         al[1] = hi.alpha - hi.d0 / hi.d1;
@@ -672,7 +710,7 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
         swap = s1 || s2 || s3 || s4 || s5 || s6;
         ++it;
       }
-      const bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
+      const bool improved = unib<G>((lo.cost < p0.cost) || (hi.cost < p0.cost));
       const T alpha = lo.cost < hi.cost ? lo.alpha : hi.alpha;
       if (improved) {
         qacc = axpy(qacc, alpha, search);
@@ -720,7 +758,7 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
         if (act) cpart += T(0.5) * dr * ja * ja;
       }
       const T cost_s = group_sum<T, G>(cpart, gm);  // gauss term is exactly zero at qacc_smooth
-      take_warm = cost_w < cost_s;
+      take_warm = unib<G>(cost_w < cost_s);
       if (take_warm) {
         qacc = warm;
         Ma = Ma_w;
@@ -744,7 +782,7 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
     if (iterations != 1 && !fixed) {
       const T improvement = (prev_cost - cost) / scale;
       const T gradient = t_sqrt(c.dotv(grad, grad)) / scale;
-      run = !(niter >= iterations || improvement < tolerance || gradient < tolerance);
+      run = unib<G>(!(niter >= iterations || improvement < tolerance || gradient < tolerance));
     }
     while (run) {
       linesearch();
@@ -758,7 +796,7 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
       } else {
         const T improvement = (prev_cost - cost) / scale;
         const T gradient = t_sqrt(c.dotv(grad, grad)) / scale;
-        if (niter >= iterations || improvement < tolerance || gradient < tolerance) break;
+        if (unib<G>(niter >= iterations || improvement < tolerance || gradient < tolerance)) break;
       }
       compute_mgrad();
       if (newton) {
@@ -958,7 +996,9 @@ __global__ void __launch_bounds__((sizeof(T) == 4 ? 512 : MJT_SOLVE_F64_THREADS)
   stage_blob(smem_blob, &bar, gblob, blob_words);
   const ModelView<T> m = make_view<T>(smem_blob);
   const int E = blockDim.x / G;                                   // envs per CTA, G lanes each
-  const int warp = threadIdx.x / G, lane = threadIdx.x & (G - 1);   // "warp" = env slot inside the CTA
+  // "warp" = env slot inside the CTA; for full-warp envs the broadcast tells the compiler the slot (hence `valid`, the region
+  // pointer and every branch on per-env data below) is warp-uniform
+  const int warp = uni<G>(threadIdx.x / G), lane = threadIdx.x & (G - 1);
   const unsigned gm = group_mask<G>();
   const int env0 = blockIdx.x * E;
   const int nv = m.h(H_nv), nefc = m.h(H_nefc);

@@ -7,9 +7,14 @@ top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "mujoco_torch_b200", "csrc", "libmjt_b200.so")
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, capture_output=True)
-sass = subprocess.run(["nvdisasm", "-g", "-c", glob.glob(tmp + "/*.cubin")[0]], capture_output=True, text=True).stdout.splitlines()
-# locate function section
-start = next(i for i, l in enumerate(sass) if l.startswith(".text.") and fn in l and l.rstrip().endswith(":"))
+sass, start = None, None
+for cubin in sorted(glob.glob(tmp + "/*.cubin")):   # one cubin per translation unit: find the one that holds the function
+    cand = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
+    hit = [i for i, l in enumerate(cand) if l.startswith(".text.") and fn in l and l.rstrip().endswith(":")]
+    if hit:
+        sass, start = cand, hit[0]
+        break
+assert sass is not None, f"no function matching {fn!r} in {so}"
 lines, cur = [], None
 for l in sass[start + 1:]:
     if l.startswith("//---------------------") or (l.startswith(".text.") and l.rstrip().endswith(":")):
