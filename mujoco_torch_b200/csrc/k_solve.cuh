@@ -79,7 +79,9 @@ __device__ MJT_CHOL_INLINE void cholesky_rows_fn(T* A, T* di, int n, int lane, u
   for (int j = 0; j < G; ++j) {
     if (j < n) {
       const T* rowj = A + tri(j);
-      T acc = (mine && lane >= j) ? rowi[j] : T(0), acc2 = T(0);
+      // unconditional load (a conditional one compiles to a branch): lanes above the diagonal or beyond n read some other
+      // in-bounds word of the tile; whatever they compute is discarded by the selects below and never stored
+      T acc = rowi[j], acc2 = T(0);
 #pragma unroll
       for (int k = 0; k + 1 < j; k += 2) {
         acc -= r[k] * rowj[k];
@@ -115,6 +117,8 @@ struct SolveCtx {
   const int* tri_ab;
   const int* dof_sadr;
   const int* dof_sent;
+  const int* row_order;
+  const int* dof_ent;   // per (dof, source) entry, two words: J offset of the entry's column | ns << 20, first row | nr << 16
   unsigned gm_;   // shuffle / barrier mask of this env's G lanes (half-warp envs); use gmask()
   // A full warp per env: the mask is the compile-time constant 0xffffffff, which lets the compiler emit plain SHFL / WARPSYNC.ALL
   // instead of the mask-checking collective sequence it needs for a run-time mask.
@@ -268,16 +272,19 @@ struct SolveCtx {
     Vec<T, DPL> y = zero();
 #pragma unroll
     for (int k = 0; k < DPL; ++k) {
-      const int i = lane + G * k;
-      if (i < nv) {
-        const T* row = A + tri(i);
-        const T* x = xs();
-        T acc = 0, acc2 = 0;   // two independent chains: row part (contiguous) and column part (strided)
-        for (int c = 0; c <= i; ++c) acc += row[c] * x[c];
-        const T* colp = A + tri(i + 1) + i;
-        for (int c = i + 1; c < nv; ++c) { acc2 += colp[0] * x[c]; colp += c + 1; }
-        y.v[k] = acc + acc2;
+      // every lane walks all nv columns (same trip count: no divergence, unrollable); entry (i, c) of the symmetric matrix is
+      // word tri(i) + c of the packed triangle for c <= i, else tri(c) + i.  Lanes without a dof compute row 0 and drop it.
+      const int i = lane + G * k, ii = i < nv ? i : 0, ti = tri(ii);
+      const T* x = xs();
+      T acc = 0, acc2 = 0;   // two independent chains (even / odd columns)
+      int c = 0;
+#pragma unroll 2
+      for (; c + 1 < nv; c += 2) {
+        acc += A[c <= ii ? ti + c : tri(c) + ii] * x[c];
+        acc2 += A[c + 1 <= ii ? ti + c + 1 : tri(c + 1) + ii] * x[c + 1];
       }
+      if (c < nv) acc += A[c <= ii ? ti + c : tri(c) + ii] * x[c];
+      y.v[k] = i < nv ? acc + acc2 : T(0);
     }
     return y;
   }
@@ -285,7 +292,9 @@ struct SolveCtx {
   __device__ __forceinline__ void jmul(const Vec<T, DPL>& x, T* out, const T* sub, int nlive) const {
     to_smem(x, xs());
     for (int idx = lane; idx < nlive; idx += G) {
-      const int r = row_at(idx);
+      // rows in place: visited in the order of decreasing support size (model.py row_order), so that the 32 rows of one pass
+      // have (nearly) the same trip count -- Humanoid: its 32 contact rows in one pass, the 21 one-column limit rows in the other
+      const int r = compact ? row_at(idx) : row_order[idx];
       const int sidx = row_src[r];
       const int ns = src_nsup[sidx];
       const int* col = sup_col + src_cadr[sidx];
@@ -310,13 +319,23 @@ struct SolveCtx {
       T acc = T(0);
       if (i < nv) {
         for (int q = dof_sadr[i], qe = dof_sadr[i + 1]; q < qe; ++q) {
-          const int ent = dof_sent[q], sidx = ent & 0xffff, pos = ent >> 16;
-          const int cs = compact ? spos()[sidx] : 0;
-          if (cs < 0) continue;
-          const int r0 = src_row[sidx], nr = src_nrows[sidx], ns = src_nsup[sidx];
-          const T* jp = jsrc(sidx, r0) + pos;
-          const T* fp = f + (TILE ? cs : r0);
-          for (int e = 0; e < nr; ++e) acc += jp[e * ns] * fp[e];
+          if (TILE) {
+            const int ent = dof_sent[q], sidx = ent & 0xffff, pos = ent >> 16;
+            const int cs = spos()[sidx];
+            if (cs < 0) continue;
+            const int r0 = src_row[sidx], nr = src_nrows[sidx], ns = src_nsup[sidx];
+            const T* jp = jsrc(sidx, r0) + pos;
+            const T* fp = f + cs;
+            for (int e = 0; e < nr; ++e) acc += jp[e * ns] * fp[e];
+          } else {
+            // static J layout: everything about the entry comes from two packed words (no dependent table walk)
+            if (compact && spos()[dof_sent[q] & 0xffff] < 0) continue;
+            const int w0 = dof_ent[2 * q], w1 = dof_ent[2 * q + 1];
+            const int ns = w0 >> 20, nr = w1 >> 16;
+            const T* jp = Jc() + (w0 & 0xfffff);
+            const T* fp = f + (w1 & 0xffff);
+            for (int e = 0; e < nr; ++e) acc += jp[e * ns] * fp[e];
+          }
         }
       }
       out.v[k] = acc;
@@ -1051,7 +1070,7 @@ __global__ void __launch_bounds__((sizeof(T) == 4 ? 512 : MJT_SOLVE_F64_THREADS)
   EnvBuf<T> d{out + (valid ? env : 0), Bs};
   EnvBuf<T> pub{pubbuf + (valid ? env : 0), Bs};   // the caller's buffer (same as `out` in the full layout)
   SolveCtx<T, DPL, COMPACT, G, TILE> c{m, region + (size_t)warp * Lo.words, Lo, nv, nefc, lane,
-                     m.I(I_row_src), m.I(I_row_jadr), m.I(I_src_nsup), m.I(I_src_cadr), m.I(I_src_row), m.I(I_src_nrows), m.I(I_sup_col), m.I(I_tri_ab), m.I(I_dof_sadr), m.I(I_dof_sent), group_mask<G>()};
+                     m.I(I_row_src), m.I(I_row_jadr), m.I(I_src_nsup), m.I(I_src_cadr), m.I(I_src_row), m.I(I_src_nrows), m.I(I_sup_col), m.I(I_tri_ab), m.I(I_dof_sadr), m.I(I_dof_sent), m.I(I_row_order), m.I(I_dof_ent), group_mask<G>()};
   Vec<T, DPL> qfrc_smooth = c.zero(), qacc_smooth = c.zero();
   if (valid) {
     // ---- factor_m + qacc_smooth

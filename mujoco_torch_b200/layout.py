@@ -44,7 +44,7 @@ sens_type sens_objid sens_adr sens_dim sens_datatype sens_stage sens_objtype sen
 rf_geom
 body_geomadr body_geomnum body_geom body_siteadr body_sitenum body_site
 cvx_geom cvx_nvert cvx_nface cvx_nfv cvx_nedge cvx_vertadr cvx_faceadr cvx_edgeadr cvx_normadr geom_cvx cvx_face cvx_edge
-m_nz geom_need
+m_nz geom_need row_order dof_ent
 """.split()
 
 # ---- float arrays -------------------------------------------------------------------------

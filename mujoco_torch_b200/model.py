@@ -466,6 +466,17 @@ class Model:
             jc_src += [r * self.nv + cc for cc in sp["cols"][ca: ca + ns]]
         I["jc_src"] = i32(jc_src)
         I["dof_sadr"], I["dof_sent"] = i32(sp["dof_sadr"]), i32(sp["dof_sent"])
+        # rows by decreasing support size (stable): k_solve's J.x passes then see homogeneous trip counts
+        I["row_order"] = i32(sorted(range(len(sp["row_src"])), key=lambda r: -sp["src_nsup"][sp["row_src"][r]]))
+        # per (dof, source) entry of the J^T f gather, packed: [J offset of the column | ns << 20, first row | nr << 16]
+        src_row0 = [s[2] for s in self.src]
+        ent = []
+        for e in sp["dof_sent"]:
+            k, pos = e & 0xffff, e >> 16
+            jofs = sp["row_jadr"][src_row0[k]] + pos if sp["src_nrows"][k] else 0
+            assert jofs < (1 << 20) and sp["src_nsup"][k] < (1 << 11) and src_row0[k] < (1 << 16) and sp["src_nrows"][k] < (1 << 15)
+            ent += [jofs | (sp["src_nsup"][k] << 20), src_row0[k] | (sp["src_nrows"][k] << 16)]
+        I["dof_ent"] = i32(ent)
         I["tri_src"] = i32([i * self.nv + j for i in range(self.nv) for j in range(i + 1)])
         I["triu_src"] = i32([j * self.nv + i for i in range(self.nv) for j in range(i)])
         # packed lower-triangle index p -> (row a, col b) as a | b << 16 (Hessian assembly walks support pairs by p)
@@ -676,7 +687,7 @@ class Model:
 
         # the solver kernel stages a reduced blob (only the tables it reads) so that more envs fit in shared memory
         solve_keep = set("jnt_type jnt_qposadr jnt_dofadr act_trntype act_trnid act_gear act_dyntype act_gaintype act_biastype act_actadr act_actnum act_actlimited "
-                         "src_row src_nrows src_nsup src_cadr sup_col row_src row_jadr tri_ab dof_sadr dof_sent jc_src m_nz "
+                         "src_row src_nrows src_nsup src_cadr sup_col row_src row_jadr tri_ab dof_sadr dof_sent jc_src m_nz row_order dof_ent "
                          "opt dof_damping act_actrange act_gainprm act_biasprm act_dynprm ten_damping".split())
         def both(state):
             solve_blob = assemble(solve_keep, None, state)
