@@ -47,12 +47,14 @@ def algorithmic_flops(mj, mx):
     """Algorithmic flops per env-step from the model dims, SURVEY.md 8(d) formulae (FMA = 2 flops; the symmetric count of
     J^T D J, so that exploiting symmetry / sparsity is not rewarded twice).  Solver work is data dependent: the solver body
     is counted ONCE (exact for Humanoid, iterations = 1; a lower bound for the models that iterate to convergence) and the
-    line search at its configured maximum of ls_iterations."""
+    line search at its configured maximum of ls_iterations.  Returned per kernel (k_solve also factorises M and solves for
+    qacc_smooth, and runs the integrator's re-factorisation) and in total."""
     nv, nbody, ncon, nefc = mj.nv, mj.nbody, mx.ncon, mx.nefc
     integ, newton = int(mj.opt.integrator), int(mj.opt.solver) == 2
     ls_it = int(mj.opt.ls_iterations)
     chol, tri = nv ** 3 / 3.0, 2.0 * nv * nv
-    smooth = 700.0 * nbody + 6.0 * nv * nv + chol + tri            # kinematics..rne, make_m (tree-sparse half), factor_m, qacc_smooth
+    smooth = 700.0 * nbody + 6.0 * nv * nv                          # kinematics..rne, make_m (tree-sparse half)
+    factor = chol + tri                                              # factor_m, qacc_smooth
     constraint = ncon * 2 * nv * 18 + 18 * nv * ncon + 4 * nefc * nv   # contact Jacobians, frame.Jdiff, rows + aref
     solve = 0.0
     if nefc:
@@ -61,8 +63,9 @@ def algorithmic_flops(mj, mx):
         linesearch = 2 * nefc * nv + 2 * nv * nv + (2 + 3 * ls_it) * 10 * nefc
         solve = 3 * ctx + 2 * grad + linesearch + ctx               # warm/smooth contexts, 2 gradients, 1 line search, post-LS update
     refactor = chol + tri if integ == 3 or (integ == 0 and not (int(mj.opt.disableflags) & (1 << 15)) and float(np.abs(mj.dof_damping).sum()) > 0) else 0.0
-    fwd = smooth + constraint + solve
-    return (4 * fwd if integ == 1 else fwd + refactor)
+    nfwd = 4 if integ == 1 else 1
+    by_kernel = {"k_smooth": nfwd * smooth, "k_constraint": nfwd * constraint, "k_solve": nfwd * (factor + solve) + (0.0 if integ == 1 else refactor)}
+    return {"by_kernel": by_kernel, "total": sum(by_kernel.values())}
 
 
 def stock_options(args):
@@ -90,26 +93,14 @@ def initial_state(mj, name, B, rank=0):
     return sharding.initial_state(mj, name, rank * B, (rank + 1) * B, seed=42)
 
 
-def measured_traffic(kernel, model, dtype, B):
-    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/traffic.json), or None."""
+def measured_traffic(kernel, model, dtype, B, outputs="state"):
+    """DRAM bytes per launch of `kernel` (ncu dram__bytes_read.sum + dram__bytes_write.sum of the committed capture,
+    profiles/traffic.json), or None when no capture matches the workload."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        return t.get(f"{kernel}:{model}:{dtype}:{B}")
+        return t.get(f"{kernel}:{model}:{dtype}:{B}:{outputs}")
     except Exception:  # noqa: BLE001
         return None
-
-
-def issue_roofline(kernel, model, dtype, B, kernel_ms, sm_count, sm_mhz):
-    """Issue-slot roofline of the dominant kernel: warp instructions per launch (ncu `smsp__inst_executed.sum` of the committed
-    capture, profiles/traffic.json) over the live launch time, against the SMs' issue peak (4 schedulers x 1 warp instruction
-    per clock).  This is the roof k_solve actually runs under; None when no capture matches the workload."""
-    inst = measured_traffic("inst:" + kernel, model, dtype, B)
-    if not inst or not kernel_ms or not sm_count or not sm_mhz:
-        return None
-    ach = inst / (kernel_ms * 1e-3) / 1e9
-    peak = sm_count * 4 * sm_mhz * 1e6 / 1e9
-    return {"bound": "issue", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "G warp-instr/s", "frac": ach / peak,
-            "warp_instructions_per_launch": inst, "source": "ncu smsp__inst_executed.sum (profiles/) / live CUDA-event launch time"}
 
 
 class ClockSampler:
@@ -230,7 +221,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--gather-obs", action="store_true",
-                    help="also all-gather (qpos, qvel), reward, done over the job every step on a side stream (sharding.ObsGather)")
+                    help="also all-gather (qpos, qvel), reward, done over the job every step on a side stream (sharding.ObsGather); "
+                         "on by default when the job has more than one rank")
+    ap.add_argument("--no-gather-obs", action="store_true")
+    ap.add_argument("--no-other-mode", action="store_true", help="skip the second timed loop with the other --outputs mode")
+    ap.add_argument("--no-variants", action="store_true", help="skip the f32 / ImplicitFast variants of the Humanoid workload")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -276,120 +271,174 @@ def main():
             td.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput
+    from mujoco_torch_b200 import sharding
+
+    def rollout(d, steps, outputs, gather=None, zeros_b=None, fixed=False):
+        """`steps` steps from Data `d` with the resident ctrl sequence; returns (device ms between the two events, last Data)."""
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for i in range(steps):
+            d = mt.step(mx, d.replace(ctrl=ctrls[i % 4]), fixed_iterations=fixed, outputs=outputs)
+            if gather is not None:
+                if i:
+                    gather.wait()
+                gather.launch([d.qpos, d.qvel], zeros_b, zeros_b)
+        if gather is not None:
+            gather.wait()
+        ev1.record()
+        barrier()
+        return ev0.elapsed_time(ev1), d
+
+    # ---- device-resident throughput (the headline): W untimed warm-up steps, then exactly K timed steps
     d = d0
     for i in range(args.warmup):
         d = mt.step(mx, d.replace(ctrl=ctrls[i % 4]), outputs=args.outputs)
     barrier()
+    d_start = d   # the timed region's initial state, replayed below for the kernel split and the other output mode
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    gather = None
-    if args.gather_obs:   # optional collective of SURVEY 8(e): off the physics path, overlapped with the next step
-        from mujoco_torch_b200 import sharding as _sh
-
-        gather = _sh.ObsGather(mj.nq + mj.nv, B, dtype, dev)
-        zeros_b = torch.zeros(B, dtype=dtype, device=dev)
-    ev0.record()
-    for i in range(args.steps):
-        d = mt.step(mx, d.replace(ctrl=ctrls[i % 4]), outputs=args.outputs)
-        if gather is not None:
-            if i:
-                gather.wait()
-            gather.launch([d.qpos, d.qvel], zeros_b, zeros_b)
-    if gather is not None:
-        gather.wait()
-    ev1.record()
-    barrier()
-    ms = ev0.elapsed_time(ev1)
+    ms, d = rollout(d_start, args.steps, args.outputs)
     clocks = sampler.stop() if rank == 0 else None
     finite = bool(torch.isfinite(d.qpos).all())
-    # live-tile models: share of envs the last step handed to the full-tile pass (hidden per-env flag of the output buffer)
+    ms_max = sharding.max_over_ranks(ms, dev)
+    value = world * B * args.steps / (ms_max * 1e-3)
+    step_ms = ms_max / args.steps
+
+    # ---- per-kernel device timing: the SAME steps replayed from the same state with every launch bracketed by CUDA events on
+    # its stream (so that the split adds up to the step also for solvers whose iteration count depends on the state)
+    ops.profile_begin()
+    dd = d_start
+    for i in range(args.steps):
+        dd = mt.step(mx, dd.replace(ctrl=ctrls[i % 4]), outputs=args.outputs)
+    prof = ops.profile_end()
+    per_step = {k: v[0] / args.steps for k, v in prof.items()}
+    top = max(per_step, key=per_step.get)
+    # live-tile models: share of envs the last step handed to the full-tile pass (hidden per-env flag; full layout only)
     tile_overflow = None
-    if getattr(mx, "live_caps", (0, 0))[0] > 0 and os.environ.get("MJT_LIVE_TILE", "1") != "0":
+    if args.outputs == "full" and getattr(mx, "live_caps", (0, 0))[0] > 0 and os.environ.get("MJT_LIVE_TILE", "1") != "0":
         try:
-            root = d.qpos._base if d.qpos._base is not None else d.qpos
+            root = dd.qpos._base if dd.qpos._base is not None else dd.qpos
             off = mx.field_off["scr_ovf"]
             flags = root[:, off] if (root.dim() == 2 and root.shape[0] == B and root.shape[1] == mx.data_words) else root.reshape(-1)[off * B:(off + 1) * B]
             tile_overflow = float((flags != 0).double().mean())
         except Exception:  # noqa: BLE001
             tile_overflow = None
-    from mujoco_torch_b200 import sharding
+    del dd
 
-    ms_max = sharding.max_over_ranks(ms, dev)
-    value = world * B * args.steps / (ms_max * 1e-3)
+    # ---- the other output mode on the same steps (both numbers in one line: outputs=state is the rollout form, outputs=full
+    # materialises every field of Data like the reference does)
+    other = "full" if args.outputs == "state" else "state"
+    other_mode = None
+    if not args.no_other_mode:
+        for i in range(3):
+            mt.step(mx, d_start.replace(ctrl=ctrls[i % 4]), outputs=other)
+        ms_o, _ = rollout(d_start, args.steps, other)
+        ms_o = sharding.max_over_ranks(ms_o, dev)
+        other_mode = {"outputs": other, "value": world * B * args.steps / (ms_o * 1e-3), "unit": "env-steps/s", "ms_per_step": ms_o / args.steps}
 
-    # ---- per-kernel device timing for the roofline (same state, a few extra steps)
-    ops.profile_begin()
-    nprof = min(20, args.steps)
-    for i in range(nprof):
-        d = mt.step(mx, d.replace(ctrl=ctrls[i % 4]), outputs=args.outputs)
-    prof = ops.profile_end()
-    kern = {k: v[0] / v[1] for k, v in prof.items()}
-    per_step = {k: v[0] / nprof for k, v in prof.items()}
-    top = max(per_step, key=per_step.get)
+    # ---- rooflines.  The dominant kernel (k_solve) is bound by FMA-pipe issue, not by HBM: the top-level roofline is the compute
+    # one -- algorithmic flops of that kernel per launch over its measured launch time against the FMA peak measured in this run --
+    # and the HBM figure (minimal state I/O of the whole step over the step time) sits beside it.
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:  # noqa: BLE001
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    abytes = algorithmic_bytes(mj, tsize) * B
-    ach = abytes / (per_step[top] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                "traffic": measured_traffic(top, args.model, args.dtype, B), "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
-                "algorithmic_bytes_per_env_step": algorithmic_bytes(mj, tsize),
-                "kernel_ms_per_step": per_step, "kernel_share": {k: v / sum(per_step.values()) for k, v in per_step.items()}}
-
-    # compute roofline (SURVEY.md 8(d) asks for both): algorithmic flops of the whole step over the measured FMA-pipe peak
+    fl = algorithmic_flops(mj, mx)
+    pipe_name = "fp64" if args.dtype == "f64" else "fp32"
     try:
         fma_peak = ops.fma_peak(args.dtype == "f64")
-        aflops = algorithmic_flops(mj, mx)
-        step_ms = ms_max / args.steps
-        roofline["fma"] = {"achieved": aflops * B / (step_ms * 1e-3) / 1e12, "peak": fma_peak, "unit": "TFLOP/s",
-                           "frac": aflops * B / (step_ms * 1e-3) / 1e12 / fma_peak if fma_peak else None,
-                           "algorithmic_flops_per_env_step": aflops, "pipe": "fp64" if args.dtype == "f64" else "fp32",
-                           "peak_source": "mjt_fma_peak (register-resident FMA chains, measured in this run)",
-                           "scope": "whole step; solver body counted once, line search at ls_iterations"}
-    except Exception as exc:  # noqa: BLE001
-        roofline["fma"] = {"error": str(exc)}
-
-    try:
-        issue = issue_roofline(top, args.model, args.dtype, B, kern[top] if stock_options(args) else None,
-                               torch.cuda.get_device_properties(dev).multi_processor_count, (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz"))
-        if issue:
-            roofline["issue"] = issue
     except Exception:  # noqa: BLE001
-        pass
+        fma_peak = None
+    kflops = fl["by_kernel"].get(top, fl["total"])
+    ach = kflops * B / (per_step[top] * 1e-3) / 1e12
+    traffic = {k: measured_traffic(k, args.model, args.dtype, B, args.outputs) for k in per_step}
+    abytes = algorithmic_bytes(mj, tsize)
+    roofline = {
+        "bound": pipe_name, "kernel": top, "achieved": ach, "peak": fma_peak, "unit": "TFLOP/s", "frac": (ach / fma_peak) if fma_peak else None,
+        "traffic": traffic.get(top), "algorithmic_flops_per_env_launch": kflops,
+        "peak_source": "mjt_fma_peak: register-resident FMA chains timed in this run (MEASURED_PEAKS.json holds no FP64/FP32 vector peak)",
+        "kernel_ms_per_step": per_step, "kernel_share": {k: v / sum(per_step.values()) for k, v in per_step.items()},
+        "kernel_sum_ms": sum(per_step.values()),
+        "whole_step": {"bound": pipe_name, "achieved": fl["total"] * B / (step_ms * 1e-3) / 1e12, "peak": fma_peak, "unit": "TFLOP/s",
+                       "frac": (fl["total"] * B / (step_ms * 1e-3) / 1e12 / fma_peak) if fma_peak else None,
+                       "algorithmic_flops_per_env_step": fl["total"],
+                       "scope": "solver body counted once, line search at ls_iterations (SURVEY.md 8d formulae)"},
+        "hbm": {"bound": "hbm", "achieved": abytes * B / (step_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": abytes * B / (step_ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes_per_env_step": abytes,
+                "traffic": (sum(v for v in traffic.values() if v) if all(traffic.get(k) for k in per_step if per_step[k] > 0.05 * step_ms) else None),
+                "traffic_by_kernel": traffic, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
+                "scope": "whole step: minimal state I/O (SURVEY.md 8d) over ms_per_step; traffic = ncu dram bytes per step summed over the kernels (profiles/traffic.json)"},
+    }
 
     # ---- end to end through the public API from pinned host buffers
     e2e = None
     if not args.no_e2e:
         # public API for host-resident state: HostPipeline keeps qpos/qvel/qacc_warmstart/ctrl in pinned host memory and
-        # runs H2D -> step -> D2H chunk by chunk on separate streams (2 chunks by default) (transfers of one chunk overlap kernels of another)
-        pipe = mt.HostPipeline(mx, d, nchunk=int(os.environ["MJT_E2E_CHUNKS"]) if "MJT_E2E_CHUNKS" in os.environ else None)
+        # runs H2D -> step -> D2H chunk by chunk on separate streams (2 chunks by default; transfers of one chunk overlap kernels of another)
+        pipe = mt.HostPipeline(mx, d, nchunk=int(os.environ["MJT_E2E_CHUNKS"]) if "MJT_E2E_CHUNKS" in os.environ else None,
+                               outputs=args.outputs)
         nb_in, nb_out = pipe.h2d_bytes, pipe.d2h_bytes
-
-        def e2e_step():
-            pipe.step(synchronize=False)   # per-chunk streams keep their own H2D -> step -> D2H order across steps
-
         for _ in range(3):
-            e2e_step()
+            pipe.step(synchronize=False)   # per-chunk streams keep their own H2D -> step -> D2H order across steps
         pipe.synchronize()
         barrier()
         n_e2e = max(5, min(args.steps, 30))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(n_e2e):
-            e2e_step()
+            pipe.step(synchronize=False)
         pipe.synchronize()
         e1.record()
         barrier()
         el = sharding.max_over_ranks(e0.elapsed_time(e1), dev) * 1e-3
         e2e = {"value": world * B * n_e2e / el, "unit": "env-steps/s", "h2d_bytes_per_step": nb_in,
-               "d2h_bytes_per_step": nb_out, "steps": n_e2e}
+               "d2h_bytes_per_step": nb_out, "steps": n_e2e, "chunks": len(pipe.slices)}
+        del pipe
+
+    # ---- the one optional collective (SURVEY 8e): all-gather of (qpos, qvel) + reward + done over the job on a side stream,
+    # overlapped with the next physics step.  Measured whenever the job has more than one rank (or on request).
+    obs_gather = None
+    if args.gather_obs or (dist and not args.no_gather_obs):
+        gather = sharding.ObsGather(mj.nq + mj.nv, B, dtype, dev)
+        zeros_b = torch.zeros(B, dtype=dtype, device=dev)
+        rollout(d_start, 3, args.outputs, gather, zeros_b)
+        ms_g, _ = rollout(d_start, args.steps, args.outputs, gather, zeros_b)
+        ms_g = sharding.max_over_ranks(ms_g, dev)
+        obs_gather = {"value": world * B * args.steps / (ms_g * 1e-3), "unit": "env-steps/s", "ms_per_step": ms_g / args.steps,
+                      "added_ms_per_step": ms_g / args.steps - step_ms, "bytes_gathered_per_rank_per_step": gather.bytes_per_gather,
+                      "message": "per env: qpos, qvel, reward, done", "backend": "nccl all_gather_into_tensor" if dist else "single rank (pack + copy only)"}
+
+    # ---- BASELINE configs[3] in full on one line: the other precision / integrator variants of the Humanoid workload, same batch,
+    # same protocol (3 warm-up + up to 20 timed steps each).  Single-GPU runs only.
+    variants = None
+    if not dist and not args.no_variants and args.model == "humanoid" and stock_options(args):
+        variants = []
+        for vd, vi in (("f64", "implicitfast"), ("f32", None), ("f32", "implicitfast")):
+            if (vd, vi) == (args.dtype, None):
+                continue
+            vmj = load_model(args.model, argparse.Namespace(integrator=vi, solver=None, cone=None))
+            vdt = torch.float64 if vd == "f64" else torch.float32
+            vmx = mt.device_put(vmj, dtype=vdt).to(dev)
+            vdata = mt.make_data(vmx).expand(B).clone().replace(qpos=torch.as_tensor(qpos, device=dev).to(vdt), qvel=torch.as_tensor(qvel, device=dev).to(vdt))
+            vctrl = [c.to(vdt).t().contiguous().t() for c in ctrls]
+            for i in range(3):
+                vdata = mt.step(vmx, vdata.replace(ctrl=vctrl[i % 4]), outputs=args.outputs)
+            nv_steps = max(5, min(args.steps, 20))
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for i in range(nv_steps):
+                vdata = mt.step(vmx, vdata.replace(ctrl=vctrl[i % 4]), outputs=args.outputs)
+            a1.record()
+            torch.cuda.synchronize()
+            vms = a0.elapsed_time(a1) / nv_steps
+            variants.append({"dtype": vd, "integrator": vi or "euler (XML)", "outputs": args.outputs, "value": B / (vms * 1e-3), "unit": "env-steps/s",
+                             "ms_per_step": vms, "steps": nv_steps, "finite": bool(torch.isfinite(vdata.qpos).all())})
+            del vdata, vmx
 
     if rank != 0:
         if dist:
@@ -397,30 +446,41 @@ def main():
         return
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and not dist:
         cores = os.cpu_count() or 1
         v, sec = oracle_rate(mj, args.model, args.cpu_batch, 3, cores)
         cpu = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
                "sample": f"oracle port (float64 batched torch), B={args.cpu_batch} envs x 3 steps, {cores} threads"}
+    # the UNMODIFIED reference's eager CPU step cannot run on the GPU box (its Python sources live under /root/reference, which does
+    # not travel); it was timed in the build container through oracle/refshim (scripts/time_reference_eager.py) and is quoted as context
+    cpu_ref = None
+    try:
+        cpu_ref = json.load(open(os.path.join(ROOT, "profiles", "reference_eager_cpu.json"))).get(args.model)
+    except Exception:  # noqa: BLE001
+        pass
 
-    stock = args.integrator is None and args.solver is None and args.cone is None   # published numbers use the XML's own options
+    stock = stock_options(args)   # published numbers use the XML's own options
     pub = PUBLISHED.get((args.model, args.dtype, B)) if stock else None
-    launches = ops.lib().mjt_step_launches(ops.model_handle(mx)) * args.steps
+    launches = ops.lib().mjt_step_launches(ops.model_handle(mx, args.outputs)) * args.steps
     import ctypes
 
     _e, _s = ctypes.c_int(), ctypes.c_int()
-    ops.lib().mjt_solve_config(ops.model_handle(mx), ctypes.byref(_e), ctypes.byref(_s))
+    ops.lib().mjt_solve_config(ops.model_handle(mx, args.outputs), ctypes.byref(_e), ctypes.byref(_s))
+    words = (mx.state_layout["pub_words"] + mx.state_layout["ws_words"]) if args.outputs == "state" else mx.data_words
     line = {
         "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": (value / pub) if pub else None, "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": workload_name(args, mj), "batch_per_gpu": B, "parallelism": f"dp{world} (envs sharded, no collective)",
-                   "l2": f"per-step working set {mx.data_words * B * tsize / 1e6:.0f} MB > 126 MB L2 (inputs larger than L2)",
-                   "nv": mj.nv, "ncon": mx.ncon, "nefc": mx.nefc,
-                   **({"obs_gather_bytes_per_step": gather.bytes_per_gather} if gather is not None else {}), "solve_envs_per_cta": _e.value, "solve_smem_bytes": _s.value,
+                   "outputs": ("state: every step returns qpos, qvel, act, time, qacc, qacc_warmstart, act_dot, sensordata (bit-identical to the "
+                               "full-Data step, tests/test_gpu_api.py); the full-Data number is in other_output_mode") if args.outputs == "state"
+                   else "full: every field of Data materialised each step, like the reference",
+                   "l2": f"per-step working set {words * B * tsize / 1e6:.0f} MB > 126 MB L2 (inputs larger than L2)",
+                   "nv": mj.nv, "ncon": mx.ncon, "nefc": mx.nefc, "solve_envs_per_cta": _e.value, "solve_smem_bytes": _s.value,
                    **({"solve_live_tile": {"rows": mx.live_caps[0], "j_words": mx.live_caps[1], "overflow_frac_last_step": tile_overflow}}
                       if tile_overflow is not None else {})},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "finite": finite,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+        "other_output_mode": other_mode, "variants": variants, "obs_gather": obs_gather, "cpu_baseline_ref": cpu_ref, "finite": finite,
         "published_baseline": {"value": pub, "hardware": "H200 f64 torch.compile(vmap) tuned, reference README.md:178-247"} if pub else None,
     }
     print(json.dumps(line))

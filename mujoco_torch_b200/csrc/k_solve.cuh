@@ -571,7 +571,7 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
     const T tolerance = m.opt(OPT_tolerance), ls_tolerance = m.opt(OPT_ls_tolerance);
     const int iterations = m.h(H_iterations), ls_iterations = m.h(H_ls_iterations);
 
-    V Ma, grad, Mgrad, search;
+    V Ma, grad, Mgrad = c.zero(), search = c.zero();
     T gauss = 0, cost = t_inf<T>(), prev_cost = 0;
     if (c.compact && !TILE)   // dead rows are never visited again: give them their final zeros now
       for (int r = lane; r < nefc; r += G) { Jaref[r] = T(0); jv[r] = T(0); force[r] = T(0); }
@@ -791,17 +791,19 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
     prev_cost = 0;
     update_constraint(true);
     compute_grad();
-    compute_mgrad();
-    search = neg(Mgrad);
 
-    // ---- main loop (:501-539).  The gradient solve at the end of body() is only needed if another iteration
-    // follows, so the termination test is evaluated first (identical outputs, one factorisation less per solve).
+    // ---- main loop (:501-539).  The gradient solve is only needed if an iteration follows, so the termination test is
+    // evaluated first, here and at the end of body() (identical outputs, one factorisation less per solve).
     int niter = 0;
     bool run = true;
     if (iterations != 1 && !fixed) {
       const T improvement = (prev_cost - cost) / scale;
       const T gradient = t_sqrt(c.dotv(grad, grad)) / scale;
       run = unib<G>(!(niter >= iterations || improvement < tolerance || gradient < tolerance));
+    }
+    if (run) {
+      compute_mgrad();
+      search = neg(Mgrad);
     }
     while (run) {
       linesearch();

@@ -204,7 +204,8 @@ extern "C" int mjt_model_field(const mjtModel* m, const char* name, int* offset,
       int off = m->hv(MJT_OFF_D + k);
       if (m->state_layout()) {
         off = -1;
-        static const int pd[NUM_P] = {D_qpos, D_qvel, D_act, D_time, D_qacc, D_qacc_warmstart, D_act_dot, D_sensordata, D_qfrc_constraint};
+        static const int pd[NUM_P] = {D_qpos, D_qvel, D_act, D_time, D_qacc_warmstart, D_qacc, D_act_dot, D_sensordata, D_qfrc_constraint};
+        static_assert(P_qacc_warmstart == 4 && P_qacc == 5 && P_qfrc_constraint == 8, "pd[] must follow layout.py P_FIELDS");
         for (int q = 0; q < NUM_P; ++q)
           if (pd[q] == k) off = m->hv(MJT_OFF_P + q);
         if (off < 0) return -1;

@@ -15,30 +15,52 @@ from . import api
 from .data import Data
 from .model import Model
 
-IN_FIELDS = ("qpos", "qvel", "qacc_warmstart", "ctrl")
-OUT_FIELDS = ("qpos", "qvel", "qacc_warmstart")
-# State that does not travel by default (activations, time) is carried on the device from step to step.
-CARRIED_FIELDS = ("act", "time")
+# The state a step advances, in the order the state layout stores it (layout.py STATE_PUBLIC), then the per-step input.
+STATE_FIELDS = ("qpos", "qvel", "act", "time", "qacc_warmstart")
+IN_FIELDS = STATE_FIELDS + ("ctrl",)
+OUT_FIELDS = STATE_FIELDS
+
+
+def _row_blocks(tensors, B):
+    """Group consecutive ``(B, n)`` env-minor views that sit back to back in one buffer into single ``(rows, B)`` blocks, so that
+    they travel with one copy.  Yields (block tensor, first row, rows); a tensor that is not an env-minor view is its own block
+    (copied through a transposed view)."""
+    out, row = [], 0
+    for t in tensors:
+        n = t.shape[1]
+        minor = t.numel() == 0 or (t.stride(0) == 1 and (n == 1 or t.stride(1) == B))
+        if out and minor and out[-1][3] and t.numel() and t.data_ptr() == out[-1][0].data_ptr() + out[-1][2] * B * t.element_size():
+            first, r0, rows, _ = out[-1]
+            out[-1] = (first, r0, rows + n, True)
+        elif t.numel():
+            out.append((t, row, n, minor))
+        row += n
+    blocks = []
+    for first, r0, rows, minor in out:
+        blk = torch.as_strided(first, (rows, B), (B, 1), first.storage_offset()) if minor else first.t()
+        blocks.append((blk, r0, rows))
+    return blocks
 
 
 class HostPipeline:
-    """``pipe = HostPipeline(mx, d0)`` (``nchunk`` defaults to 2 for batches of 16 384 envs and more, else 1); ``pipe.step()`` advances the host-resident state by one timestep.
+    """``pipe = HostPipeline(mx, d0)`` (``nchunk`` defaults to 2 for batches of 16 384 envs and more, else 1); ``pipe.step()``
+    advances the host-resident state by one timestep.
 
-    * ``pipe.host[c][name]`` -- pinned ``(n, B_c)`` tensors (env-minor, the layout the kernels read) per chunk ``c``;
-      the caller writes ``ctrl`` (and may rewrite any state field) there between steps.
-    * ``step()`` copies the inputs of every chunk to the device, steps it (``outputs="state"`` by default: nothing but the
-      state is materialised), and copies ``qpos, qvel, qacc_warmstart`` back into the same pinned buffers.  It returns after
-      all streams have drained.  Activations and time stay on the device and are carried from step to step.
+    * Per chunk ``c`` one pinned ``(rows, B_c)`` array (env-minor, the layout the kernels read) holds
+      ``qpos | qvel | act | time | qacc_warmstart | ctrl``; ``pipe.host[c][name]`` are its row views -- the caller writes ``ctrl``
+      (and may rewrite any state field) there between steps.
+    * ``step()`` sends the whole array to the device with ONE copy, steps the chunk (``outputs="state"`` by default: nothing
+      but the state is materialised; the state fields of the result are contiguous) and brings the new state back into the same
+      rows with ONE copy.  It returns after all streams have drained (``synchronize=False``: only enqueues).
     """
 
-    def __init__(self, m: Model, d: Data, nchunk: int | None = None, in_fields=IN_FIELDS, out_fields=OUT_FIELDS, outputs: str = "state"):
+    def __init__(self, m: Model, d: Data, nchunk: int | None = None, outputs: str = "state"):
         if d.qpos.dim() != 2:
             raise ValueError("HostPipeline expects a batched Data with one leading batch dim")
         if not d.qpos.is_cuda:
             raise RuntimeError("HostPipeline needs the template Data on the model's CUDA device (there is no CPU path)")
-        self.m, self.in_fields, self.out_fields, self.outputs = m, tuple(in_fields), tuple(out_fields), outputs
-        # every state field the step advances is either sent from the host each step or kept current on the device
-        self.carried = tuple(k for k in CARRIED_FIELDS if k not in self.in_fields and getattr(d, k).numel() > 0)
+        self.m, self.outputs = m, outputs
+        self.in_fields, self.out_fields = IN_FIELDS, OUT_FIELDS
         B = d.qpos.shape[0]
         if nchunk is None:   # measured (profiles/README.md): two chunks overlap PCIe with kernels once a chunk still fills the GPU
             nchunk = 2 if B >= 16384 else 1
@@ -47,16 +69,30 @@ class HostPipeline:
         self.slices = [slice(bounds[c], bounds[c + 1]) for c in range(nchunk)]
         self.streams = [torch.cuda.Stream(device=d.qpos.device) for _ in range(nchunk)]
         self.base = [d[s] for s in self.slices]       # per-chunk template (fields that never travel stay on the device)
-        self.host = []
+        widths = {k: (getattr(d, k).numel() // B) for k in IN_FIELDS}
+        self.rows, r = {}, 0
+        for k in IN_FIELDS:
+            self.rows[k] = (r, r + widths[k])
+            r += widths[k]
+        self.in_rows = r
+        self.out_rows = self.rows[OUT_FIELDS[-1]][1]
+        self.host_buf, self.host, self.dev_in = [], [], []
         for s in self.slices:
-            bufs = {}
-            for k in set(self.in_fields) | set(self.out_fields):
+            n = s.stop - s.start
+            buf = torch.empty((self.in_rows, n), dtype=m.dtype).pin_memory()
+            views = {}
+            for k in IN_FIELDS:
+                a, b = self.rows[k]
                 v = getattr(d, k)[s]
-                bufs[k] = v.reshape(v.shape[0], -1).t().contiguous().cpu().pin_memory()   # (n, B_c)
-            self.host.append(bufs)
+                buf[a:b].copy_(v.reshape(n, -1).t())
+                views[k] = buf[a:b]                    # (n_k, B_c)
+            self.host_buf.append(buf)
+            self.host.append(views)
+            self.dev_in.append(torch.empty((self.in_rows, n), dtype=m.dtype, device=d.qpos.device))
         self._primed = False
-        self.h2d_bytes = sum(b[k].numel() * b[k].element_size() for b in self.host for k in self.in_fields)
-        self.d2h_bytes = sum(b[k].numel() * b[k].element_size() for b in self.host for k in self.out_fields)
+        item = torch.empty((), dtype=m.dtype).element_size()
+        self.h2d_bytes = self.in_rows * B * item
+        self.d2h_bytes = self.out_rows * B * item
 
     def step(self, synchronize: bool = True):
         """One timestep for every chunk.  With ``synchronize=False`` the call only enqueues: each chunk's stream carries
@@ -69,13 +105,17 @@ class HostPipeline:
             self._primed = True
         for c, st in enumerate(self.streams):
             with torch.cuda.stream(st):
-                dev = {k: self.host[c][k].to(self.base[c].qpos.device, non_blocking=True).t() for k in self.in_fields}
-                out = api.step(self.m, self.base[c].replace(**dev), outputs=self.outputs)
-                if self.carried:
-                    self.base[c] = self.base[c].replace(**{k: getattr(out, k) for k in self.carried})
-                for k in self.out_fields:
-                    v = getattr(out, k)
-                    self.host[c][k].copy_(v.reshape(v.shape[0], -1).t(), non_blocking=True)
+                din, n = self.dev_in[c], self.dev_in[c].shape[1]
+                din.copy_(self.host_buf[c], non_blocking=True)                      # one H2D: state + ctrl
+                tmpl = self.base[c]
+                dev = {}
+                for k in IN_FIELDS:
+                    a, b = self.rows[k]
+                    dev[k] = din[a:b].t().reshape(getattr(tmpl, k).shape)           # env-minor views: no transposes before the launch
+                out = api.step(self.m, tmpl.replace(**dev), outputs=self.outputs)
+                outs = [getattr(out, k).reshape(n, -1) for k in OUT_FIELDS]
+                for blk, r0, rows in _row_blocks(outs, n):                          # state layout: ONE block -> one D2H
+                    self.host_buf[c][r0:r0 + rows].copy_(blk, non_blocking=True)
         if synchronize:
             self.synchronize()
 

@@ -112,7 +112,9 @@ HIDDEN_FIELDS = {"scr_cacc", "scr_cfrc", "scr_live", "scr_ovf"}
 # lends to the step (scratch, reused from step to step).  Fields nothing downstream reads (xmat, cinert, cdof_dot, dense qM /
 # qLD / efc_J / actuator_moment, qacc_smooth, efc_force ...) get offset -1 and are never written; qM is stored as a packed
 # lower triangle and efc_J compacted to each row's column support (the form k_solve keeps in shared memory anyway).
-STATE_PUBLIC = ("qpos", "qvel", "act", "time", "qacc", "qacc_warmstart", "act_dot", "sensordata", "qfrc_constraint")
+# (the state a rollout feeds back in -- qpos, qvel, act, time, qacc_warmstart -- comes first and is contiguous, so a host pipeline
+# moves it with one copy per direction)
+STATE_PUBLIC = ("qpos", "qvel", "act", "time", "qacc_warmstart", "qacc", "act_dot", "sensordata", "qfrc_constraint")
 # P table of the blob header: word offsets of the public fields inside the buffer handed back to the caller.  Full layout:
 # the same buffer and offsets as the D table.  State layout: offsets inside the small public buffer (-1 = absent); the D
 # table then addresses the workspace, which keeps its own pre-integration working copies of qpos / qvel / act / time.

@@ -690,7 +690,8 @@ class Model:
                          "src_row src_nrows src_nsup src_cadr sup_col row_src row_jadr tri_ab dof_sadr dof_sent jc_src m_nz row_order dof_ent "
                          "opt dof_damping act_actrange act_gainprm act_biasprm act_dynprm ten_damping".split())
         def both(state):
-            solve_blob = assemble(solve_keep, None, state)
+            # the state layout stores efc_J already compacted: its solver needs no dense-word table (2 KB of shared memory)
+            solve_blob = assemble(solve_keep - ({"jc_src"} if state else set()), None, state)
             full = assemble(None, {"solve_blob_words": int(solve_blob.size)}, state)
             return np.concatenate([full, solve_blob])
 

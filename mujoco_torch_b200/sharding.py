@@ -102,11 +102,12 @@ class ObsGather:
     def _pack_and_gather(self, parts, reward, done):
         import torch.distributed as td
 
-        o = 0
-        for part in parts:   # (B, k) logical; env-minor sources (views of a step's output buffer) copy row by row, coalesced
-            part = part.reshape(self.B, -1)
-            self.send[o:o + part.shape[1]].copy_(part.t())
-            o += part.shape[1]
+        from .hostio import _row_blocks
+
+        # (B, k) logical pieces; env-minor sources (views of a step's output buffer) are contiguous row blocks, and pieces that sit
+        # back to back in that buffer (qpos, qvel of a state-layout step) travel as ONE copy
+        for blk, r0, rows in _row_blocks([p.reshape(self.B, -1) for p in parts], self.B):
+            self.send[r0:r0 + rows].copy_(blk)
         self.send[self.obs_dim].copy_(reward.reshape(self.B))
         self.send[self.obs_dim + 1].copy_(done.reshape(self.B))
         if self.dist:

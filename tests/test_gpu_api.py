@@ -107,7 +107,35 @@ def test_host_pipeline_equals_direct_step():
     for _ in range(2):
         ref = mt.step(mx, ref.replace(ctrl=d.ctrl))
     assert torch.equal(pipe.gather("qpos"), ref.qpos.cpu())
-    assert pipe.h2d_bytes == 48 * (mj.nq + 2 * mj.nv + mj.nu) * 8 and pipe.d2h_bytes == 48 * (mj.nq + 2 * mj.nv) * 8
+    assert pipe.h2d_bytes == 48 * (mj.nq + 2 * mj.nv + mj.na + 1 + mj.nu) * 8 and pipe.d2h_bytes == 48 * (mj.nq + 2 * mj.nv + mj.na + 1) * 8
+
+
+@pytest.mark.parametrize("outputs", ["state", "full"])
+def test_host_pipeline_carries_activations_and_time(outputs):
+    """A model with activation states (sink.xml: filter / integrator / muscle dynamics, na > 0): act and time travel with the
+    state, so N pipeline steps equal N direct steps (they used to be reset to the template's values every step)."""
+    import mujoco_torch_b200 as mt
+
+    mj = util.load_model("sink")
+    B = 24
+    qpos, qvel, ctrl, act = util.sink_state(mj, B)
+    mx = mt.device_put(mj, dtype=torch.float64).to("cuda:0")
+    T = lambda a: torch.as_tensor(a, device="cuda:0")
+    d = mt.make_data(mx).expand(B).clone().replace(qpos=T(qpos), qvel=T(qvel), ctrl=T(ctrl), act=T(act))
+    assert mj.na > 0
+    pipe = mt.HostPipeline(mx, d, nchunk=3, outputs=outputs)
+    ref = d
+    for _ in range(4):
+        pipe.step()
+        ref = mt.step(mx, ref)
+    for k in ("qpos", "qvel", "act", "qacc_warmstart"):
+        assert torch.equal(pipe.gather(k), getattr(ref, k).cpu().reshape(B, -1)), k
+    assert torch.equal(pipe.gather("time")[:, 0], ref.time.cpu()) and float(ref.time[0]) > 0
+    # the state layout's state fields are contiguous: one block per direction
+    from mujoco_torch_b200.hostio import _row_blocks, OUT_FIELDS
+    out = mt.step(mx, d, outputs=outputs)
+    nblk = len(_row_blocks([getattr(out, k).reshape(B, -1) for k in OUT_FIELDS], B))
+    assert nblk == (1 if outputs == "state" else 2)
 
 
 def test_cpu_tensors_fail_loudly():
