@@ -8,8 +8,18 @@
 Workload (config.workload): Humanoid (the reference's humanoid.xml: Newton, 1 iteration / 4 line-search iterations,
 Euler, eulerdamp disabled -- the configuration the reference's README numbers are quoted on), batch 65 536 per GPU,
 float64 like every published reference number.  A step = one `step(mx, d)` over the whole batch.
-`value` is measured with the state resident in HBM; `e2e` runs the same step through the public API from pinned
-host buffers (H2D of the state + ctrl, step, D2H of qpos/qvel/qacc_warmstart) inside the timed region.
+
+  value               device-resident stepping, `--outputs state` (default): the step returns the state fields only; the same
+                      steps with `outputs="full"` (every field of Data, like the reference) are timed too -> other_output_mode
+  e2e                 the same through mujoco_torch_b200.HostPipeline with the per-step input (ctrl) copied from pinned host memory
+                      and the observation (qpos, qvel) read back, every step; e2e_host_state = round 1's protocol (whole state
+                      travels both ways)
+  roofline            the binding roof of the dominant kernel (FMA pipe), the whole-step HBM figure beside it, per-kernel split
+                      measured on the SAME steps (replayed from the timed region's initial state)
+  variants            BASELINE configs[3]: f32 and ImplicitFast variants of the workload (single-GPU runs)
+  obs_gather          multi-rank runs: the optional NCCL all-gather of (qpos, qvel, reward, done) on a side stream
+  cpu_baseline        the oracle port timed on this box's host cores; cpu_baseline_ref quotes the unmodified reference's eager
+                      step timed in the build container (profiles/reference_eager_cpu.json)
 """
 
 from __future__ import annotations
@@ -240,6 +250,11 @@ def main():
     dist = world > 1
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = None
+    if dist and os.environ.get("MJT_NO_CPU_BIND", "0") != "1":
+        from mujoco_torch_b200 import sharding as _sh0
+
+        numa = _sh0.bind_to_local_cpus(local)   # before any pinned allocation: first touch places the staging buffers
     if dist:
         import torch.distributed as td
 
@@ -374,14 +389,16 @@ def main():
                 "scope": "whole step: minimal state I/O (SURVEY.md 8d) over ms_per_step; traffic = ncu dram bytes per step summed over the kernels (profiles/traffic.json)"},
     }
 
-    # ---- end to end through the public API from pinned host buffers
-    e2e = None
-    if not args.no_e2e:
-        # public API for host-resident state: HostPipeline keeps qpos/qvel/qacc_warmstart/ctrl in pinned host memory and
-        # runs H2D -> step -> D2H chunk by chunk on separate streams (2 chunks by default; transfers of one chunk overlap kernels of another)
+    # ---- end to end through the public API from pinned host buffers (mujoco_torch_b200.HostPipeline: H2D -> step -> D2H per chunk
+    # on its own stream, one copy per direction).  Two protocols, both timed every run:
+    #   e2e            : the simulation state stays on the GPU (where step() returns it); every step the step's input -- ctrl -- comes
+    #                    from pinned host memory and its result -- the observation qpos, qvel -- is read back to the host.  This is
+    #                    the traffic of a host-side policy driving the simulator, the call pattern of the reference's own users.
+    #   e2e_host_state : round 1's protocol, kept for continuity: the WHOLE state (qpos, qvel, act, time, qacc_warmstart) + ctrl
+    #                    travels to the device and the whole new state travels back, every step (2.4x the bytes).
+    def measure_e2e(resident):
         pipe = mt.HostPipeline(mx, d, nchunk=int(os.environ["MJT_E2E_CHUNKS"]) if "MJT_E2E_CHUNKS" in os.environ else None,
-                               outputs=args.outputs)
-        nb_in, nb_out = pipe.h2d_bytes, pipe.d2h_bytes
+                               outputs=args.outputs, resident=resident)
         for _ in range(3):
             pipe.step(synchronize=False)   # per-chunk streams keep their own H2D -> step -> D2H order across steps
         pipe.synchronize()
@@ -395,9 +412,17 @@ def main():
         e1.record()
         barrier()
         el = sharding.max_over_ranks(e0.elapsed_time(e1), dev) * 1e-3
-        e2e = {"value": world * B * n_e2e / el, "unit": "env-steps/s", "h2d_bytes_per_step": nb_in,
-               "d2h_bytes_per_step": nb_out, "steps": n_e2e, "chunks": len(pipe.slices)}
-        del pipe
+        ok = all(bool(torch.isfinite(b["qpos"]).all()) for b in pipe.host)
+        return {"value": world * B * n_e2e / el, "unit": "env-steps/s", "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
+                "steps": n_e2e, "chunks": len(pipe.slices), "finite": ok,
+                "protocol": ("state resident on the device; per step H2D ctrl from pinned host memory, D2H qpos + qvel" if resident == "device"
+                             else "state resident on the host; per step H2D qpos, qvel, act, time, qacc_warmstart, ctrl and D2H of the new state"),
+                **({"cpu_binding": numa} if numa is not None else {})}
+
+    e2e = e2e_host = None
+    if not args.no_e2e:
+        e2e = measure_e2e("device")
+        e2e_host = measure_e2e("host")
 
     # ---- the one optional collective: all-gather of (qpos, qvel) + reward + done over the job on a side stream,
     # overlapped with the next physics step.  Measured whenever the job has more than one rank (or on request).
@@ -436,8 +461,12 @@ def main():
             a1.record()
             torch.cuda.synchronize()
             vms = a0.elapsed_time(a1) / nv_steps
+            bad = float((~torch.isfinite(vdata.qpos).all(1)).double().mean())
             variants.append({"dtype": vd, "integrator": vi or "euler (XML)", "outputs": args.outputs, "value": B / (vms * 1e-3), "unit": "env-steps/s",
-                             "ms_per_step": vms, "steps": nv_steps, "finite": bool(torch.isfinite(vdata.qpos).all())})
+                             "ms_per_step": vms, "steps": nv_steps, "nonfinite_env_frac": bad,
+                             **({"note": "Humanoid's XML stops the solver after 1 iteration; ImplicitFast re-solves qacc from that unconverged constraint "
+                                         "force, and a few % of the randomly actuated envs diverge within ~10 steps -- in the CPU oracle as well "
+                                         "(DESIGN.md 4); _check_state resets a coordinate once it passes 1e10"} if vi == "implicitfast" else {})})
             del vdata, vmx
 
     if rank != 0:
@@ -480,7 +509,7 @@ def main():
                    **({"solve_live_tile": {"rows": mx.live_caps[0], "j_words": mx.live_caps[1], "overflow_frac_last_step": tile_overflow}}
                       if tile_overflow is not None else {})},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-        "other_output_mode": other_mode, "variants": variants, "obs_gather": obs_gather, "cpu_baseline_ref": cpu_ref, "finite": finite,
+        "e2e_host_state": e2e_host, "other_output_mode": other_mode, "variants": variants, "obs_gather": obs_gather, "cpu_baseline_ref": cpu_ref, "finite": finite,
         "published_baseline": {"value": pub, "hardware": "H200 f64 torch.compile(vmap) tuned, reference README.md:178-247"} if pub else None,
     }
     print(json.dumps(line))

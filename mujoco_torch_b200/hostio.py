@@ -49,18 +49,26 @@ class HostPipeline:
     * Per chunk ``c`` one pinned ``(rows, B_c)`` array (env-minor, the layout the kernels read) holds
       ``qpos | qvel | act | time | qacc_warmstart | ctrl``; ``pipe.host[c][name]`` are its row views -- the caller writes ``ctrl``
       (and may rewrite any state field) there between steps.
+    * ``resident="device"`` keeps the state on the GPU (carried from step to step): only ``ctrl`` comes from the host array and only
+      ``qpos | qvel`` go back to it -- what a host-side policy driving a device-resident simulation moves.
     * ``step()`` sends the whole array to the device with ONE copy, steps the chunk (``outputs="state"`` by default: nothing
       but the state is materialised; the state fields of the result are contiguous) and brings the new state back into the same
       rows with ONE copy.  It returns after all streams have drained (``synchronize=False``: only enqueues).
     """
 
-    def __init__(self, m: Model, d: Data, nchunk: int | None = None, outputs: str = "state"):
+    def __init__(self, m: Model, d: Data, nchunk: int | None = None, outputs: str = "state", resident: str = "host"):
         if d.qpos.dim() != 2:
             raise ValueError("HostPipeline expects a batched Data with one leading batch dim")
         if not d.qpos.is_cuda:
             raise RuntimeError("HostPipeline needs the template Data on the model's CUDA device (there is no CPU path)")
-        self.m, self.outputs = m, outputs
-        self.in_fields, self.out_fields = IN_FIELDS, OUT_FIELDS
+        if resident not in ("host", "device"):
+            raise ValueError("resident must be 'host' or 'device'")
+        self.m, self.outputs, self.resident = m, outputs, resident
+        # resident="host": the whole state travels both ways every step.  resident="device": the state stays on the GPU and is
+        # carried from step to step; only the per-step input (ctrl) comes from the host and only the observation (qpos, qvel)
+        # goes back -- the traffic of a host-side policy driving a device-resident simulation.
+        self.in_fields = IN_FIELDS if resident == "host" else ("ctrl",)
+        self.out_fields = OUT_FIELDS if resident == "host" else ("qpos", "qvel")
         B = d.qpos.shape[0]
         if nchunk is None:   # measured (profiles/README.md): two chunks overlap PCIe with kernels once a chunk still fills the GPU
             nchunk = 2 if B >= 16384 else 1
@@ -69,19 +77,22 @@ class HostPipeline:
         self.slices = [slice(bounds[c], bounds[c + 1]) for c in range(nchunk)]
         self.streams = [torch.cuda.Stream(device=d.qpos.device) for _ in range(nchunk)]
         self.base = [d[s] for s in self.slices]       # per-chunk template (fields that never travel stay on the device)
-        widths = {k: (getattr(d, k).numel() // B) for k in IN_FIELDS}
+        # host array rows: the fields that come back first (so that a field travelling both ways uses the same rows), then the rest
+        order = list(self.out_fields) + [k for k in self.in_fields if k not in self.out_fields]
+        widths = {k: (getattr(d, k).numel() // B) for k in order}
         self.rows, r = {}, 0
-        for k in IN_FIELDS:
+        for k in order:
             self.rows[k] = (r, r + widths[k])
             r += widths[k]
-        self.in_rows = r
-        self.out_rows = self.rows[OUT_FIELDS[-1]][1]
+        self.out_rows = self.rows[self.out_fields[-1]][1]
+        self.in_lo = min(self.rows[k][0] for k in self.in_fields)   # the H2D copy covers rows [in_lo, end)
+        self.in_rows = r - self.in_lo
         self.host_buf, self.host, self.dev_in = [], [], []
         for s in self.slices:
             n = s.stop - s.start
-            buf = torch.empty((self.in_rows, n), dtype=m.dtype).pin_memory()
+            buf = torch.empty((r, n), dtype=m.dtype).pin_memory()
             views = {}
-            for k in IN_FIELDS:
+            for k in order:
                 a, b = self.rows[k]
                 v = getattr(d, k)[s]
                 buf[a:b].copy_(v.reshape(n, -1).t())
@@ -106,14 +117,16 @@ class HostPipeline:
         for c, st in enumerate(self.streams):
             with torch.cuda.stream(st):
                 din, n = self.dev_in[c], self.dev_in[c].shape[1]
-                din.copy_(self.host_buf[c], non_blocking=True)                      # one H2D: state + ctrl
+                din.copy_(self.host_buf[c][self.in_lo:], non_blocking=True)         # one H2D: state + ctrl (or ctrl alone)
                 tmpl = self.base[c]
                 dev = {}
-                for k in IN_FIELDS:
+                for k in self.in_fields:
                     a, b = self.rows[k]
-                    dev[k] = din[a:b].t().reshape(getattr(tmpl, k).shape)           # env-minor views: no transposes before the launch
+                    dev[k] = din[a - self.in_lo:b - self.in_lo].t().reshape(getattr(tmpl, k).shape)   # env-minor views: no transposes before the launch
                 out = api.step(self.m, tmpl.replace(**dev), outputs=self.outputs)
-                outs = [getattr(out, k).reshape(n, -1) for k in OUT_FIELDS]
+                if self.resident == "device":   # the advanced state is the next step's template (views of the step's small output buffer)
+                    self.base[c] = tmpl.replace(**{k: getattr(out, k) for k in STATE_FIELDS})
+                outs = [getattr(out, k).reshape(n, -1) for k in self.out_fields]
                 for blk, r0, rows in _row_blocks(outs, n):                          # state layout: ONE block -> one D2H
                     self.host_buf[c][r0:r0 + rows].copy_(blk, non_blocking=True)
         if synchronize:

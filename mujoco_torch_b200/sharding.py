@@ -68,6 +68,34 @@ def job_rate(envs_per_rank: int, steps: int, ms_per_rank: float, device=None) ->
     return world * envs_per_rank * steps / (max_over_ranks(ms_per_rank, device) * 1e-3)
 
 
+def bind_to_local_cpus(device_index: int) -> dict:
+    """One process per GPU on a multi-socket host: run this rank's Python thread -- and, by first touch, place its pinned
+    staging buffers -- on the CPU cores NVML reports as local to the GPU (same socket / PCIe root).  Without it the eight ranks
+    of a box land wherever the launcher put them and host<->device copies cross the socket interconnect.  Returns what was done
+    (for the bench line); never raises."""
+    import os
+
+    info = {"bound": False}
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        local = sorted(cpus & allowed)
+        if local:
+            os.sched_setaffinity(0, local)
+            info = {"bound": True, "cpus": len(local), "first_cpu": local[0], "last_cpu": local[-1], "allowed_before": len(allowed)}
+        else:
+            info = {"bound": False, "reason": "no overlap between the GPU's local cpus and this process's allowed set", "allowed": len(allowed)}
+    except Exception as exc:  # noqa: BLE001
+        info = {"bound": False, "reason": f"{type(exc).__name__}: {exc}"}
+    return info
+
+
 class ObsGather:
     """Optional per-agent-step all-gather of observation + reward + done over the job: the only collective a
     sharded rollout may want, and it is off the physics path.

@@ -110,6 +110,23 @@ def test_host_pipeline_equals_direct_step():
     assert pipe.h2d_bytes == 48 * (mj.nq + 2 * mj.nv + mj.na + 1 + mj.nu) * 8 and pipe.d2h_bytes == 48 * (mj.nq + 2 * mj.nv + mj.na + 1) * 8
 
 
+def test_host_pipeline_device_resident_state():
+    """resident="device": the state is carried on the GPU, ctrl is the only H2D traffic and (qpos, qvel) the only D2H traffic;
+    the trajectory equals direct stepping with the same per-step ctrl."""
+    mt, mj, mx, d = _batch(B=40)
+    pipe = mt.HostPipeline(mx, d, nchunk=2, resident="device")
+    assert pipe.h2d_bytes == 40 * mj.nu * 8 and pipe.d2h_bytes == 40 * (mj.nq + mj.nv) * 8
+    ref = d
+    rng = np.random.RandomState(3)
+    for it in range(4):
+        ctrl = rng.uniform(-1, 1, size=(40, mj.nu))
+        for c, sl in enumerate(pipe.slices):
+            pipe.host[c]["ctrl"].copy_(torch.as_tensor(ctrl[sl]).t())
+        pipe.step()
+        ref = mt.step(mx, ref.replace(ctrl=torch.as_tensor(ctrl, device="cuda:0")))
+        assert torch.equal(pipe.gather("qpos"), ref.qpos.cpu()) and torch.equal(pipe.gather("qvel"), ref.qvel.cpu()), it
+
+
 @pytest.mark.parametrize("outputs", ["state", "full"])
 def test_host_pipeline_carries_activations_and_time(outputs):
     """A model with activation states (sink.xml: filter / integrator / muscle dynamics, na > 0): act and time travel with the
