@@ -19,19 +19,104 @@ from . import layout as L
 from . import ops
 from .data import Contact, Data
 from .mjmodel import ConeType, MjModelLite
-from .model import Model, device_put_model
+from .model import Model, Option, Statistic, device_put_model
 
 _OUT_FIELDS = tuple(n for n, _ in L.D_FIELDS if n not in L.HIDDEN_FIELDS and not n.startswith("contact_"))
 
 
 def device_put(value, *, dtype: torch.dtype | None = None):
-    """Place a compiled model (``mujoco.MjModel`` or ``MjModelLite``: any object with MjModel attribute names) on
-    the device-side representation.  Mirrors reference ``device_put`` (device.py:1029-1112) for models."""
-    if isinstance(value, Model):
+    """Place a MuJoCo struct on the device-side representation.  Mirrors reference ``device_put`` (device.py:1029-1112), duck-typed
+    on MuJoCo's attribute names because the ``mujoco`` package may be absent:
+
+      * a compiled model (``mujoco.MjModel`` or ``MjModelLite``: has ``nq`` and ``opt``)  -> :class:`Model` (all static precompute);
+      * simulation data (``mujoco.MjData`` or any object with ``qpos, qvel, ctrl ...``)    -> :class:`Data` with batch size ``[]``;
+        like the reference (`_data_derived`) contact / efc arrays keep the struct's CURRENT sizes -- ``step`` accepts any incoming
+        sizes and always returns the model's static ones; rotation matrices come back as ``(n, 3, 3)``;
+      * options (``mujoco.MjOption``: has ``timestep`` and ``gravity``)                   -> :class:`Option`;
+      * statistics (``mujoco.MjStatistic``: has ``meaninertia``)                          -> :class:`Statistic`.
+    """
+    if isinstance(value, (Model, Data, Option, Statistic)):
         return value
-    if not hasattr(value, "nq") or not hasattr(value, "opt"):
-        raise NotImplementedError(f"{type(value)} is not supported for device_put.")
-    return device_put_model(value, dtype)
+    if hasattr(value, "nq") and hasattr(value, "opt"):
+        return device_put_model(value, dtype)
+    if hasattr(value, "qpos") and hasattr(value, "qvel"):
+        return _data_from_struct(value, torch.get_default_dtype() if dtype is None else dtype)
+    if hasattr(value, "timestep") and hasattr(value, "gravity"):
+        return Option(value)
+    if hasattr(value, "meaninertia"):
+        return Statistic(value)
+    raise NotImplementedError(f"{type(value)} is not supported for device_put.")
+
+
+_DATA_33 = ("xmat", "ximat", "geom_xmat", "site_xmat", "cam_xmat")   # MuJoCo stores rotation matrices flattened to 9
+_DATA_STATE = ("qpos", "qvel", "act", "time", "qacc", "qacc_warmstart", "ctrl", "qfrc_applied", "xfrc_applied", "mocap_pos", "mocap_quat",
+               "eq_active", "sensordata", "qfrc_constraint")
+_CONTACT_FIELDS = ("dist", "pos", "frame", "includemargin", "friction", "solref", "solreffriction", "solimp", "dim", "geom1", "geom2", "geom",
+                   "efc_address")
+
+
+def _data_from_struct(value, dtype) -> Data:
+    """reference device_put(MjData): every Data field the struct carries becomes a tensor (floats in ``dtype``, indices integer)."""
+    def t(x, want_int=False):
+        a = np.ascontiguousarray(np.asarray(x))
+        out = torch.as_tensor(a)
+        if want_int or not out.is_floating_point():
+            return out.to(torch.int32) if a.dtype.kind in "iub" else out
+        return out.to(dtype)
+
+    f = {}
+    names = [n for n, _ in L.D_FIELDS if n not in L.HIDDEN_FIELDS and not n.startswith("contact_")]
+    names += [n for n in _DATA_STATE if n not in names]
+    names += ["userdata", "qLDiagInv", "qfrc_fluid", "qfrc_inverse", "cacc", "cfrc_int", "cfrc_ext", "subtree_linvel", "subtree_angmom",
+              "efc_pos", "efc_margin", "efc_type", "solver_niter"]
+    for name in names:
+        if not hasattr(value, name):
+            continue
+        v = t(getattr(value, name), want_int=name in ("eq_active", "efc_type", "solver_niter"))
+        if name == "time":
+            v = v.reshape(())
+        if name in _DATA_33 and v.dim() >= 1 and v.shape[-1] == 9:
+            v = v.reshape(*v.shape[:-1], 3, 3)
+        if name == "efc_J" and v.dim() == 1 and hasattr(value, "qvel"):
+            nv = int(np.asarray(value.qvel).size)
+            v = v.reshape(-1, nv) if nv and v.numel() % nv == 0 else v
+        f[name] = v
+    for req in ("qpos", "qvel"):
+        if req not in f:
+            raise ValueError(f"device_put: the data struct has no {req}")
+    nv = f["qvel"].shape[-1]
+    f.setdefault("time", torch.zeros((), dtype=dtype))
+    f.setdefault("act", torch.zeros(0, dtype=dtype))
+    f.setdefault("ctrl", torch.zeros(0, dtype=dtype))
+    f.setdefault("qacc_warmstart", torch.zeros(nv, dtype=dtype))
+    f.setdefault("qfrc_applied", torch.zeros(nv, dtype=dtype))
+    f.setdefault("qfrc_constraint", torch.zeros(nv, dtype=dtype))
+    f.setdefault("xfrc_applied", torch.zeros((0, 6), dtype=dtype))
+    f.setdefault("mocap_pos", torch.zeros((0, 3), dtype=dtype))
+    f.setdefault("mocap_quat", torch.zeros((0, 4), dtype=dtype))
+    f.setdefault("sensordata", torch.zeros(0, dtype=dtype))
+    f.setdefault("eq_active", torch.zeros(0, dtype=torch.int32))
+    # contacts: the struct's current ones (0 after a reset), MuJoCo names (`dim`) mapped to the reference's (`contact_dim`)
+    c = getattr(value, "contact", None)
+    cf = {}
+    for name in _CONTACT_FIELDS:
+        if c is not None and hasattr(c, name):
+            v = t(getattr(c, name), want_int=name in ("dim", "geom1", "geom2", "geom", "efc_address"))
+            if name == "frame" and v.dim() >= 1 and v.shape[-1] == 9:
+                v = v.reshape(*v.shape[:-1], 3, 3)
+            cf["contact_dim" if name == "dim" else name] = v
+    ncon = int(cf["dist"].shape[0]) if "dist" in cf else 0
+    z = lambda *sh: torch.zeros(sh, dtype=dtype)
+    zi = lambda *sh: torch.zeros(sh, dtype=torch.int64)
+    for name, default in (("dist", z(ncon)), ("pos", z(ncon, 3)), ("frame", z(ncon, 3, 3)), ("includemargin", z(ncon)), ("friction", z(ncon, 5)),
+                          ("solref", z(ncon, 2)), ("solreffriction", z(ncon, 2)), ("solimp", z(ncon, 5)),
+                          ("contact_dim", torch.zeros(ncon, dtype=torch.int32)), ("geom1", zi(ncon)), ("geom2", zi(ncon)), ("geom", zi(ncon, 2)),
+                          ("efc_address", zi(ncon))):
+        cf.setdefault(name, default)
+    f["contact"] = Contact(cf)
+    nefc = int(f["efc_D"].shape[0]) if "efc_D" in f else int(getattr(value, "nefc", 0) or 0)
+    return Data(f, dict(ne=int(getattr(value, "ne", 0) or 0), nf=int(getattr(value, "nf", 0) or 0), nl=int(getattr(value, "nl", 0) or 0),
+                        ncon=ncon, nefc=nefc))
 
 
 def _contact_static(m: Model, lead, device):

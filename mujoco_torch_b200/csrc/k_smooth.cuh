@@ -691,8 +691,44 @@ __device__ void smooth_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<
       const T* bp = m.F(F_act_biasprm) + 10 * u;
       T gain = gp[0], bias = 0;
       if (gt == GAIN_AFFINE) gain = gp[0] + gp[1] * len + gp[2] * vel;
-      // TODO(muscle gain/bias): refused at device_put
       if (bt == BIAS_AFFINE) bias = bp[0] + bp[1] * len + bp[2] * vel;
+      if (gt == GAIN_MUSCLE || bt == BIAS_MUSCLE) {
+        // support.muscle_gain / muscle_bias :231-296: prm = [range0 range1 force scale lmin lmax vmax fpmax fvmax]
+        const T* lr = m.F(F_act_lengthrange) + 2 * u;
+        const T acc0 = m.F(F_act_acc0)[u];
+        const T mn = T(MJT_MINVAL);
+        if (gt == GAIN_MUSCLE) {
+          T force0 = gp[2];
+          if (force0 < T(0)) force0 = gp[3] / t_max(acc0, mn);
+          const T L0 = (lr[1] - lr[0]) / t_max(gp[1] - gp[0], mn);
+          const T L = gp[0] + (len - lr[0]) / t_max(L0, mn);
+          const T V = vel / t_max(L0 * gp[6], mn);
+          const T lmin = gp[4], lmax = gp[5], fvmax = gp[8];
+          const T a = T(0.5) * (lmin + T(1)), b = T(0.5) * (T(1) + lmax);
+          const T x0 = (L - lmin) / t_max(a - lmin, mn), x1 = (T(1) - L) / t_max(T(1) - a, mn);
+          const T x2 = (L - T(1)) / t_max(b - T(1), mn), x3 = (lmax - L) / t_max(lmax - b, mn);
+          T FL = L <= b ? T(1) - T(0.5) * x2 * x2 : T(0.5) * x3 * x3;
+          if (L <= T(1)) FL = T(1) - T(0.5) * x1 * x1;
+          if (L <= a) FL = T(0.5) * x0 * x0;
+          if (!(lmin <= L && L <= lmax)) FL = T(0);
+          const T y = fvmax - T(1);
+          T FV = V <= y ? fvmax - (y - V) * (y - V) / t_max(y, mn) : fvmax;
+          if (V <= T(0)) FV = (V + T(1)) * (V + T(1));
+          if (V <= T(-1)) FV = T(0);
+          gain = -force0 * FL * FV;
+        }
+        if (bt == BIAS_MUSCLE) {
+          T force0 = bp[2];
+          if (force0 < T(0)) force0 = bp[3] / t_max(acc0, mn);
+          const T L0 = (lr[1] - lr[0]) / t_max(bp[1] - bp[0], mn);
+          const T L = bp[0] + (len - lr[0]) / t_max(L0, mn);
+          const T lmax = bp[5], fpmax = bp[7];
+          const T b = T(0.5) * (T(1) + lmax);
+          const T x = (L - T(1)) / t_max(b - T(1), mn);
+          bias = L <= b ? -force0 * fpmax * T(0.5) * x * x : -force0 * fpmax * (T(0.5) + (L - b) / t_max(b - T(1), mn));
+          if (L <= T(1)) bias = T(0);
+        }
+      }
       T force = gain * ctrl_act + bias;
       if (m.I(I_act_forcelimited)[u]) force = t_min(t_max(force, m.F(F_act_forcerange)[2 * u]), m.F(F_act_forcerange)[2 * u + 1]);
       if (oForce >= 0) d.set(oForce + u, force);

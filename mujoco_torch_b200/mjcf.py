@@ -965,8 +965,25 @@ class Compiler:
                     act["gainprm"][0] = kv
                     act["biastype"] = 1
                     act["biasprm"][2] = -kv
+                elif ae.tag == "muscle":
+                    # MuJoCo's <muscle> shortcut: muscle dynamics, gain and bias sharing one parameter vector
+                    # [range0 range1 force scale lmin lmax vmax fpmax fvmax]; dynprm = [tau_act tau_deact tausmooth]
+                    tc = _f(a.get("timeconst"), 2, np.array([0.01, 0.04]))
+                    act["dyntype"], act["gaintype"], act["biastype"] = 4, 2, 2
+                    act["dynprm"][:] = 0
+                    act["dynprm"][:3] = [tc[0], tc[1], float(a.get("tausmooth", 0))]
+                    rg = _f(a.get("range"), 2, np.array([0.75, 1.05]))
+                    prm = [rg[0], rg[1], float(a.get("force", -1)), float(a.get("scale", 200)), float(a.get("lmin", 0.5)),
+                           float(a.get("lmax", 1.6)), float(a.get("vmax", 1.5)), float(a.get("fpmax", 1.3)), float(a.get("fvmax", 1.2))]
+                    for key in ("gainprm", "biasprm"):
+                        act[key][:] = 0
+                        act[key][:9] = prm
                 elif ae.tag != "motor":
                     raise NotImplementedError(f"actuator {ae.tag}")
+                # MuJoCo computes missing length ranges of muscles by simulation (mj_setLengthRange); only explicit ones here
+                act["lengthrange"] = _f(a.get("lengthrange"), 2, np.zeros(2))
+                if (act["gaintype"] == 2 or act["biastype"] == 2) and "lengthrange" not in a:
+                    raise NotImplementedError("muscle actuators need an explicit lengthrange (automatic length-range computation is not implemented)")
                 for key, rk in (("ctrl", "ctrlrange"), ("force", "forcerange"), ("act", "actrange")):
                     rng = _f(a.get(rk), 2, np.zeros(2))
                     lim = _bool(a.get(key + "limited"), None)
@@ -1192,7 +1209,7 @@ class Compiler:
         m.actuator_ctrlrange, m.actuator_forcerange = arr([a["ctrlrange"] for a in acts], (2,)), arr([a["forcerange"] for a in acts], (2,))
         m.actuator_actrange, m.actuator_gear = arr([a["actrange"] for a in acts], (2,)), arr([a["gear"] for a in acts], (6,))
         m.actuator_cranklength = np.zeros(nu)
-        m.actuator_lengthrange = np.zeros((nu, 2))
+        m.actuator_lengthrange = arr([a["lengthrange"] for a in acts], (2,))
         # sensors
         for key, dt in (("type", np.int32), ("datatype", np.int32), ("needstage", np.int32), ("objtype", np.int32),
                         ("objid", np.int32), ("dim", np.int32), ("adr", np.int32), ("cutoff", np.float64)):

@@ -103,6 +103,10 @@ CASES = [
     # CG run past convergence: the early-exit path stops at `tolerance` (2e-7 relative away in qacc), the fixed path keeps going.
     # (A short unconverged CG run is not usable as a pin: the oracle's own answer moves by 3e-3 under 2e-16 input perturbations.)
     ("ant_zoo_cg_fixed_iterations", "ant_zoo", {"cone": 1, "solver": 1, "iterations": 60, "ls_iterations": 20, "fixed_iterations": 1}, 4, 0.2, 1),
+    # muscle actuators: dynamics, length / velocity gain curves and passive bias (support.py:196-296), on a joint, on a tendon,
+    # and as a gain-only general actuator (drop -4 = tests/util.muscle_state), Euler and ImplicitFast
+    ("muscle", "muscle", {}, 32, -4.0, 3),
+    ("muscle_implicitfast", "muscle", {"integrator": 3}, 32, -4.0, 2),
 ]
 
 
@@ -117,7 +121,9 @@ def run_case(name, model, opt, B, drop, nsteps):
     lite = util.load_model(model, **{k: v for k, v in opt.items() if k != "fixed_iterations"})
     qpos, qvel, ctrl = util.seeded_state(lite, B, drop=drop)
     act = None
-    if drop < -2.5:
+    if drop < -3.5:
+        qpos, qvel, ctrl, act = util.muscle_state(lite, B)
+    elif drop < -2.5:
         qpos, qvel, ctrl, act = util.sink_state(lite, B)
     elif drop < 0:  # pile-up state: every free body lowered and tilted so that convex pairs interpenetrate
         qpos, qvel, ctrl = util.pile_state(lite, B) if drop > -1.5 else util.stack_state(lite, B)

@@ -330,6 +330,7 @@ STATE_CASES = [
     ("frictionloss_dof", {"integrator": 3}, "seed", 0.0), ("equality_bodies", {}, "seed", 0.0), ("equality", {}, "seed", 0.0),
     ("sink", {}, "sink", 0.0), ("sink", {"cone": 1}, "sink", 0.0), ("sink", {"integrator": 3}, "sink", 0.0), ("sink", {"integrator": 1}, "sink", 0.0),
     ("convex", {}, "pile", 0.0), ("stack", {}, "stack", 0.0), ("cartpole", {}, "seed", 0.0),
+    ("muscle", {}, "muscle", 0.0), ("muscle", {"integrator": 3}, "muscle", 0.0),
 ]
 
 
@@ -346,6 +347,8 @@ def test_state_outputs_bit_identical_to_full(name, opt, kind, drop, dtype):
     act = None
     if kind == "sink":
         qpos, qvel, ctrl, act = util.sink_state(mj, B)
+    elif kind == "muscle":
+        qpos, qvel, ctrl, act = util.muscle_state(mj, B)
     elif kind == "pile":
         qpos, qvel, ctrl = util.pile_state(mj, B)
     elif kind == "stack":
@@ -483,3 +486,23 @@ def test_stage_functions_stop_early_and_match_forward():
         for k in keys:
             assert torch.equal(getattr(out, k), getattr(full, k)), f"{stage}: {k}"
     assert torch.equal(mt.collision(mx, d).contact.dist, full.contact.dist)
+
+
+def test_device_put_data_struct_steps_like_make_data():
+    """reference call form `dx = device_put(mujoco.MjData(m))` (benchmarks/_helpers.py:28-33): contact / efc arrays of the incoming
+    Data have the struct's current sizes (0 after a reset); step accepts them and returns the model's static sizes."""
+    import types as pytypes
+
+    mt, mj, mx, d = _batch(B=4)
+    md = pytypes.SimpleNamespace(qpos=d.qpos[1].cpu().numpy(), qvel=d.qvel[1].cpu().numpy(), act=np.zeros(0), time=0.0, ctrl=d.ctrl[1].cpu().numpy(),
+                                 qacc_warmstart=np.zeros(mj.nv), qfrc_applied=np.zeros(mj.nv), xfrc_applied=np.zeros((mj.nbody, 6)),
+                                 mocap_pos=np.zeros((0, 3)), mocap_quat=np.zeros((0, 4)), eq_active=np.zeros(0, np.uint8), sensordata=np.zeros(0),
+                                 contact=pytypes.SimpleNamespace(dist=np.zeros(0), pos=np.zeros((0, 3)), frame=np.zeros((0, 9)), dim=np.zeros(0, np.int32)),
+                                 efc_J=np.zeros(0), efc_D=np.zeros(0), ncon=0, nefc=0)
+    dx = mt.device_put(md).to("cuda:0")
+    assert dx.contact.dist.shape == (0,) and dx.nefc == 0
+    out = mt.step(mx, dx)
+    ref = mt.step(mx, d)
+    assert out.contact.dist.shape == (mx.ncon,) and out.efc_J.shape == (mx.nefc, mj.nv) and out.nefc == mx.nefc
+    for k in ("qpos", "qvel", "qacc"):
+        assert torch.equal(getattr(out, k), getattr(ref, k)[1]), k

@@ -51,6 +51,10 @@ CASES = [
     ("sink", {"cone": 1}, -3.0),
     ("sink", {"integrator": 3}, -3.0),     # ImplicitFast with na != nu: the reference crashes here, oracle only
     ("sink", {"integrator": 1}, -3.0),
+    # drop -4: assets/xml/muscle.xml -- muscle dynamics / gain / bias on a joint, a tendon and a gain-only general actuator
+    ("muscle", {}, -4.0),
+    ("muscle", {"integrator": 3}, -4.0),
+    ("muscle", {"integrator": 1}, -4.0),
     # convex narrowphase (drop -1: loose pile of free bodies, drop -2: the model's own stack, squeezed)
     ("convex", {}, -1.0),
     ("shapes", {}, -1.0),
@@ -121,6 +125,8 @@ def _compare(mj, B, dtype, tol, drop, label=""):
     act = None
     if drop >= 0:
         qpos, qvel, ctrl = util.seeded_state(mj, B, drop=drop)
+    elif drop < -3.5:
+        qpos, qvel, ctrl, act = util.muscle_state(mj, B)
     elif drop < -2.5:
         qpos, qvel, ctrl, act = util.sink_state(mj, B)
     else:

@@ -3,6 +3,7 @@
 import ctypes
 import os
 import re
+import types as pytypes
 
 import numpy as np
 import pytest
@@ -215,6 +216,41 @@ def test_device_get_into_follows_the_reference_rules():
         mt.device_get_into(many[:2], d)
     with pytest.raises(ValueError, match="unrecognizable batch dimension"):
         mt.device_get_into([blank(())], mt.make_data(mx))
+
+
+def test_device_put_accepts_data_option_and_statistic_structs():
+    """reference device.device_put :1029-1112 maps MjModel / MjData / MjOption / MjStatistic; ours is duck-typed on MuJoCo's
+    attribute names.  An MjData-like struct (flattened rotation matrices, `contact.dim`, current ncon = 0 after a reset, like
+    benchmarks/_helpers.py:28-33) becomes a Data whose state feeds `step`; options and statistics become Option / Statistic."""
+    mj = util.load_model("humanoid")
+    mx = mt.device_put(mj)
+    rng = np.random.RandomState(1)
+    md = pytypes.SimpleNamespace(qpos=np.asarray(mj.qpos0) + 0.01 * rng.randn(mj.nq), qvel=0.1 * rng.randn(mj.nv), act=np.zeros(0), time=0.25,
+                                 ctrl=rng.uniform(-1, 1, mj.nu), qacc_warmstart=np.zeros(mj.nv), qfrc_applied=np.zeros(mj.nv),
+                                 xfrc_applied=np.zeros((mj.nbody, 6)), mocap_pos=np.zeros((0, 3)), mocap_quat=np.zeros((0, 4)),
+                                 eq_active=np.zeros(0, np.uint8), sensordata=np.zeros(0), xmat=np.tile(np.eye(3).reshape(9), (mj.nbody, 1)),
+                                 xpos=np.zeros((mj.nbody, 3)), ncon=0, nefc=0,
+                                 contact=pytypes.SimpleNamespace(dist=np.zeros(0), pos=np.zeros((0, 3)), frame=np.zeros((0, 9)), dim=np.zeros(0, np.int32),
+                                                                 geom1=np.zeros(0, np.int32), geom2=np.zeros(0, np.int32)))
+    for dtype in (None, torch.float32):
+        d = mt.device_put(md, dtype=dtype)
+        want = torch.get_default_dtype() if dtype is None else dtype
+        assert isinstance(d, mt.Data) and d.batch_size == torch.Size([]) and d.qpos.dtype == want
+        assert d.xmat.shape == (mj.nbody, 3, 3) and d.contact.dist.shape == (0,) and d.contact.frame.shape == (0, 3, 3)
+        assert d.contact.contact_dim.dtype == torch.int32 and float(d.time) == 0.25 and d.ncon == 0
+        assert torch.allclose(d.ctrl, torch.as_tensor(md.ctrl).to(want))
+    # every input of the step op is there, with the shapes make_data gives
+    ref = mt.make_data(mx)
+    from mujoco_torch_b200 import ops
+    for name in ops._STATE_ARGS:
+        assert getattr(d, name).shape == getattr(ref, name).shape, name
+    batch = torch.stack([d, d])
+    assert batch.qpos.shape == (2, mj.nq) and batch.contact.dist.shape == (2, 0)
+    opt = mt.device_put(mj.opt)
+    assert isinstance(opt, mt.Option) and opt.timestep == float(mj.opt.timestep) and opt.iterations == int(mj.opt.iterations)
+    assert isinstance(mt.device_put(mj.stat), mt.Statistic) and mt.device_put(mj.stat).meaninertia == float(mj.stat.meaninertia)
+    with pytest.raises(NotImplementedError):
+        mt.device_put(object())
 
 
 def test_env_minor_inputs_need_no_copy():

@@ -95,6 +95,18 @@ def sink_state(mj, B, seed=9):
     return qpos, qvel, rng.uniform(-1.5, 1.5, size=(B, mj.nu)), rng.uniform(-0.6, 0.6, size=(B, mj.na))
 
 
+def muscle_state(mj, B, seed=21):
+    """assets/xml/muscle.xml: joint angles over their ranges (so the muscles sweep their length-gain curve), activations in [0, 1],
+    controls a little beyond [0, 1] (muscle dynamics clamp them)."""
+    rng = np.random.RandomState(seed)
+    qpos = np.tile(np.asarray(mj.qpos0), (B, 1))
+    for j in range(mj.njnt):
+        lo, hi = mj.jnt_range[j]
+        qpos[:, int(mj.jnt_qposadr[j])] = rng.uniform(0.9 * lo, 0.9 * hi, size=B)
+    qvel = 2.0 * rng.randn(B, mj.nv)
+    return qpos, qvel, rng.uniform(-0.2, 1.2, size=(B, mj.nu)), rng.uniform(0.0, 1.0, size=(B, mj.na))
+
+
 def run_oracle(mj, qpos, qvel, ctrl, dtype=torch.float64, nsteps=1, warm=None, act=None, fixed_iterations=False):
     from oracle import forward as of
     from oracle import model as om
