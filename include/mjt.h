@@ -111,6 +111,33 @@ int mjt_solve_config(const mjtModel* m, int* envs_per_cta, int* smem_bytes);
  * (SURVEY.md 8(d)); the reference has no counterpart. */
 int mjt_fma_peak(int is_f64, double* tflops, void* stream);
 
+/* ---- RL environment layer (reference mujoco_torch/zoo/base.py `_step` :300-340 and the per-environment classes of zoo/):
+ * the per-agent-step epilogue after the FRAME_SKIP physics steps, fused into one launch.  Everything is env-minor. */
+typedef struct mjtEnvSpec {
+  int nq, nv, nu, na;
+  int qpos_skip, qvel_skip;       /* observation = qpos[qpos_skip:] ++ clip(qvel[qvel_skip:]) (zoo/*.py _make_obs) */
+  double qvel_clip;               /* <= 0: no clipping */
+  double dt;                      /* agent step = opt.timestep * FRAME_SKIP */
+  double forward_weight, healthy_reward, ctrl_cost_weight, reward_const;   /* reward = fw*(x - x_prev)/dt + hr*healthy - cw*|a|^2 + const */
+  int z_index;                    /* healthy needs z_low <= qpos[z_index] <= z_high; -1: no height rule */
+  double z_low, z_high;
+  int angle_index;                /* healthy needs |qpos[angle_index]| <= angle_max; -1: no angle rule */
+  double angle_max;
+  int terminate_when_unhealthy;   /* terminated = !healthy */
+  int max_episode_steps;          /* truncation: done = terminated | step_count >= max_episode_steps */
+  int auto_reset;                 /* finished envs restart from reset_state (+ noise) inside the same launch */
+} mjtEnvSpec;
+
+int mjt_env_obs_dim(const mjtEnvSpec* spec);
+
+/* qpos (nq), qvel (nv), act (na), time (1), qacc_warmstart (nv): the state rows the last physics step wrote (updated in place for
+ * envs that are reset); action (nu); xprev (1): qpos[0] at the start of the agent step, in/out; step_count (1, int32), in/out;
+ * reset_state: DENSE vector [qpos | qvel | act | time | qacc_warmstart] of the template state (same for every env);
+ * noise: (nq + nv, nenv) uniform reset noise or NULL; message: (obs_dim + 3, nenv) = observation | reward | done | terminated. */
+int mjt_env_post(const mjtEnvSpec* spec, int is_f64, void* qpos, void* qvel, void* act, void* time, void* qacc_warmstart,
+                 const void* action, void* xprev, int* step_count, const void* reset_state, const void* noise, void* message,
+                 int nenv, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

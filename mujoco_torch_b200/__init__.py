@@ -7,6 +7,7 @@
 """
 
 from . import mjcf  # noqa: F401
+from . import zoo  # noqa: F401
 from .api import (  # noqa: F401
     collision, com_pos, com_vel, constraint_sizes, crb, device_put, factor_m, forward, fwd_acceleration, fwd_actuation,
     fwd_position, fwd_velocity, kinematics, make_constraint, make_data, passive, rne, sensor_acc, sensor_pos, sensor_vel,

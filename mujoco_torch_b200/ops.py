@@ -92,7 +92,7 @@ def profile_end() -> dict:
 
 EXPORTS = ("mjt_version", "mjt_last_error", "mjt_model_create", "mjt_model_destroy", "mjt_model_layout", "mjt_model_data_words",
            "mjt_model_scratch_words", "mjt_model_dtype_size", "mjt_model_field", "mjt_step", "mjt_forward", "mjt_step_launches",
-           "mjt_profile_begin", "mjt_profile_end", "mjt_solve_config", "mjt_fma_peak")
+           "mjt_profile_begin", "mjt_profile_end", "mjt_solve_config", "mjt_fma_peak", "mjt_env_obs_dim", "mjt_env_post")
 
 
 def _check(rc):

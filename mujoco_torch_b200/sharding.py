@@ -160,6 +160,44 @@ class ObsGather:
         else:
             self._pack_and_gather(parts, reward, done)
 
+    def launch_packed(self, message: torch.Tensor):
+        """All-gather a message that is ALREADY packed env-minor, ``(rows, B)`` contiguous -- e.g. ``zoo.BatchedEnv.message``,
+        written by the fused env epilogue kernel: no pack step at all, the collective reads the kernel's output.  ``rows`` may
+        exceed ``obs_dim + 2`` (extra rows such as ``terminated`` travel too); use :meth:`wait_packed` for the result."""
+        import torch.distributed as td
+
+        if message.dim() != 2 or message.shape[1] != self.B or not message.is_contiguous():
+            raise ValueError(f"ObsGather.launch_packed: expected a contiguous (rows, {self.B}) message, got {tuple(message.shape)}")
+        rows = message.shape[0]
+        if getattr(self, "_recv_packed", None) is None or self._recv_packed.shape[1] != rows:
+            self._recv_packed = torch.empty((self.world, rows, self.B), dtype=message.dtype, device=self.device)
+
+        def run():
+            if self.dist:
+                self._work = td.all_gather_into_tensor(self._recv_packed.view(self.world * rows, self.B), message, async_op=True)
+            else:
+                self._recv_packed[0].copy_(message)
+
+        if self.stream is not None:
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self.stream):
+                run()
+            try:
+                message.record_stream(self.stream)
+            except RuntimeError:
+                pass
+        else:
+            run()
+
+    def wait_packed(self) -> torch.Tensor:
+        """``(world, rows, B)`` messages of the whole job in rank order (= global env order), after :meth:`launch_packed`."""
+        if self._work is not None:
+            self._work.wait()
+            self._work = None
+        if self.stream is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self.stream)
+        return self._recv_packed
+
     def wait(self):
         """``(obs (world, B, obs_dim), reward (world, B), done (world, B) bool)`` of the whole job; rank-major = global env order."""
         if self._work is not None:

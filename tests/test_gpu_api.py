@@ -506,3 +506,80 @@ def test_device_put_data_struct_steps_like_make_data():
     assert out.contact.dist.shape == (mx.ncon,) and out.efc_J.shape == (mx.nefc, mj.nv) and out.nefc == mx.nefc
     for k in ("qpos", "qvel", "qacc"):
         assert torch.equal(getattr(out, k), getattr(ref, k)[1]), k
+
+
+@pytest.mark.parametrize("name", ["humanoid", "ant", "halfcheetah", "hopper", "walker2d", "cartpole"])
+def test_env_layer_fused_epilogue_matches_the_reference_formulas(name):
+    """zoo.BatchedEnv (reference mujoco_torch/zoo: base.py `_step` :300-340 + the per-env classes): FRAME_SKIP state-only physics
+    steps, then ONE kernel for observation / reward / terminated / truncated / step counting.  Held against the same agent step
+    evaluated with torch ops written after the reference's formulas (fused=False): identical physics, observation and flags
+    bit for bit, reward to rounding (the kernel contracts the sum into FMAs)."""
+    import mujoco_torch_b200 as mt
+
+    B = 96
+    envs = [mt.zoo.BatchedEnv(name, num_envs=B, device="cuda:0", max_episode_steps=7, auto_reset=False, seed=11, fused=f) for f in (True, False)]
+    nu = envs[0]._m_mj.nu
+    outs = [e.reset() for e in envs]
+    assert torch.equal(outs[0]["observation"], outs[1]["observation"]) and outs[0]["observation"].shape == (B, envs[0].obs_dim)
+    g = torch.Generator(device="cuda:0").manual_seed(5)
+    seen_done = False
+    for it in range(9):
+        action = torch.empty(B, nu, dtype=torch.float64, device="cuda:0").uniform_(-1, 1, generator=g)
+        a, b = envs[0].step(action), envs[1].step(action)
+        assert torch.equal(a["observation"], b["observation"]), f"{name} step {it}: observation"
+        assert torch.equal(a["done"], b["done"]) and torch.equal(a["terminated"], b["terminated"]), f"{name} step {it}: flags"
+        assert a["reward"].shape == (B, 1) and a["done"].shape == (B, 1) and a["done"].dtype == torch.bool
+        assert float((a["reward"] - b["reward"]).abs().max()) <= 1e-12 * max(1.0, float(b["reward"].abs().max())), f"{name} step {it}: reward"
+        assert torch.equal(envs[0]._step_count.long(), envs[1]._step_count.long())
+        seen_done |= bool(a["done"].any())
+    assert seen_done, "max_episode_steps=7 must have truncated every env by step 7"
+    assert bool(a["done"].all())
+
+
+def test_env_layer_auto_reset_restarts_finished_envs_in_the_same_launch():
+    """auto_reset=True (zoo/base.py:322-329): an env that finishes returns the observation of its terminal state, and its state
+    is the template plus uniform noise of +-RESET_NOISE_SCALE when the call returns; the others are untouched."""
+    import mujoco_torch_b200 as mt
+
+    B = 128
+    env = mt.zoo.BatchedEnv("hopper", num_envs=B, device="cuda:0", max_episode_steps=1000, auto_reset=True, seed=3)
+    ref = mt.zoo.BatchedEnv("hopper", num_envs=B, device="cuda:0", max_episode_steps=1000, auto_reset=False, seed=3)
+    env.reset(); ref.reset()
+    g = torch.Generator(device="cuda:0").manual_seed(9)
+    tmpl = env._dx0
+    for it in range(60):
+        action = torch.empty(B, 3, dtype=torch.float64, device="cuda:0").uniform_(-1, 1, generator=g)
+        # bring the non-resetting twin to the same pre-step state, so that one agent step can be compared env by env
+        for k in ("qpos", "qvel", "act", "time", "qacc_warmstart"):
+            getattr(ref._dx, k).copy_(getattr(env._dx, k))
+        ref._xprev.copy_(env._xprev); ref._step_count.copy_(env._step_count)
+        out, twin = env.step(action), ref.step(action)
+        assert torch.equal(out["observation"], twin["observation"]) and torch.equal(out["done"], twin["done"])
+        done = out["done"].squeeze(-1)
+        if done.any():
+            q, v = env._dx.qpos[done], env._dx.qvel[done]
+            assert float((q - tmpl.qpos).abs().max()) <= env.RESET_NOISE_SCALE and float((v - tmpl.qvel).abs().max()) <= env.RESET_NOISE_SCALE
+            assert float((q - tmpl.qpos).abs().max()) > 0 and int(env._step_count[done].max()) == 0
+            assert torch.equal(env._dx.time[done], tmpl.time.expand(int(done.sum())))
+            assert torch.equal(env._xprev[done], q[:, 0])
+        keep = ~done
+        assert torch.equal(env._dx.qpos[keep], ref._dx.qpos[keep]) and torch.equal(env._step_count[keep], ref._step_count[keep])
+    assert int(env._step_count.max()) < 60, "hopper under random actions must have fallen (and been reset) within 60 agent steps"
+
+
+def test_env_layer_message_feeds_the_gather_without_a_pack_step():
+    from mujoco_torch_b200 import sharding
+    import mujoco_torch_b200 as mt
+
+    env = mt.zoo.BatchedEnv("halfcheetah", num_envs=64, device="cuda:0", seed=1)
+    env.reset()
+    out = env.step(torch.zeros(64, 6, dtype=torch.float64, device="cuda:0"))
+    gth = sharding.ObsGather(env.obs_dim, 64, torch.float64, "cuda:0")
+    gth.launch_packed(env.message)
+    first = {k: v.clone() for k, v in out.items()}
+    env.step(torch.ones(64, 6, dtype=torch.float64, device="cuda:0"))       # overlaps the gather; it writes the OTHER message buffer
+    allmsg = gth.wait_packed()
+    assert allmsg.shape == (1, env.obs_dim + 3, 64)
+    got = env.unpack(allmsg[0])
+    for k in ("observation", "reward", "done", "terminated"):
+        assert torch.equal(got[k], first[k]), k

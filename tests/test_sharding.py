@@ -48,6 +48,13 @@ def _worker(rank, world, port, out):
                      and np.array_equal(obs_all.reshape(world * B, od).numpy(), np.concatenate(obs_parts))
                      and rew_all.reshape(-1).tolist() == [1.0] * B + [2.0] * B
                      and done_all.reshape(-1).tolist() == [i % 2 == 0 for i in range(B)] + [i % 2 == 1 for i in range(B)])
+        # the same collective fed by an already packed env-minor message (what the fused env epilogue kernel writes): no pack step
+        msg = torch.cat([obs.t(), torch.full((1, B), float(rank + 1), dtype=torch.float64), torch.zeros(2, B, dtype=torch.float64)]).contiguous()
+        g.launch_packed(msg)
+        packed = g.wait_packed()
+        msgs = [None] * world
+        td.all_gather_object(msgs, msg.numpy())
+        gather_ok = gather_ok and tuple(packed.shape) == (world, od + 3, B) and np.array_equal(packed.numpy(), np.stack(msgs))
         slow = sharding.max_over_ranks(10.0 + rank)          # rank 1 is the slow one
         rate = sharding.job_rate(100, 10, 10.0 + rank)       # 2 ranks x 100 envs x 10 steps / 11 ms
         if rank == 0:
