@@ -499,7 +499,7 @@ def test_device_put_data_struct_steps_like_make_data():
                                  mocap_pos=np.zeros((0, 3)), mocap_quat=np.zeros((0, 4)), eq_active=np.zeros(0, np.uint8), sensordata=np.zeros(0),
                                  contact=pytypes.SimpleNamespace(dist=np.zeros(0), pos=np.zeros((0, 3)), frame=np.zeros((0, 9)), dim=np.zeros(0, np.int32)),
                                  efc_J=np.zeros(0), efc_D=np.zeros(0), ncon=0, nefc=0)
-    dx = mt.device_put(md).to("cuda:0")
+    dx = mt.device_put(md, dtype=torch.float64).to("cuda:0")   # (without dtype: torch's default dtype, like the reference)
     assert dx.contact.dist.shape == (0,) and dx.nefc == 0
     out = mt.step(mx, dx)
     ref = mt.step(mx, d)
