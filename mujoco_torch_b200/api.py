@@ -121,6 +121,8 @@ def _data_from_struct(value, dtype) -> Data:
 
 def _contact_static(m: Model, lead, device):
     c = m.con
+    if m.topk:   # make_data of a max_contact_points model: K slots (their parameters become per-env data after the first step)
+        c = {k: v[: m.ncon] for k, v in c.items()}
     ft = lambda a: torch.as_tensor(np.ascontiguousarray(a)).to(m.dtype).to(device)
     it = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a).astype(np.int64)).to(dt).to(device)
     ex = lambda t: t.expand(*lead, *t.shape) if lead else t
@@ -130,6 +132,20 @@ def _contact_static(m: Model, lead, device):
         solreffriction=ex(ft(c["solreffriction"])), solimp=ex(ft(c["solimp"])), contact_dim=ex(it(c["dim"], torch.int32)),
         geom1=ex(g1), geom2=ex(g2), geom=ex(torch.stack([g1, g2], dim=-1)), efc_address=ex(it(m.con_efcadr, torch.int64)),
     )
+
+
+def _contact_topk(m: Model, src: torch.Tensor, lead, device):
+    """max_contact_points models: the contact parameters of every env follow the candidates k_topk selected (``src``: candidate
+    index per contact slot, (..., K)); reference collision_driver.collision :822-840 emits the same data-dependent Contact."""
+    c = m.con
+    idx = src.long()
+    ft = lambda a: torch.as_tensor(np.ascontiguousarray(a)).to(m.dtype).to(device)[idx]
+    it = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a).astype(np.int64)).to(dt).to(device)[idx]
+    g1, g2 = it(c["g1"], torch.int64), it(c["g2"], torch.int64)
+    adr = torch.as_tensor(np.asarray(m.con_efcadr).astype(np.int64)).to(device)
+    return dict(includemargin=ft(c["include"]), friction=ft(c["friction"]), solref=ft(c["solref"]), solreffriction=ft(c["solreffriction"]),
+                solimp=ft(c["solimp"]), contact_dim=it(c["dim"], torch.int32), geom1=g1, geom2=g2, geom=torch.stack([g1, g2], dim=-1),
+                efc_address=adr.expand(*lead, *adr.shape) if lead else adr)
 
 
 def make_data(m: Model) -> Data:
@@ -216,11 +232,14 @@ def _run(m: Model, d: Data, mode: int, outputs: str = "full") -> Data:
         new[name] = v if len(shp) == 1 else v.reshape(tuple(lead) + tuple(shp))
     # model-constant contact fields (reference collision_driver._compute_static_contact_dict :691-793); efc_address is
     # re-derived cone-aware every step by the reference (constraint.py:636-646), so it always comes from the model
-    key = (lead, str(out.device))
-    cache = m.__dict__.setdefault("_static_contact_cache", {})
-    if key not in cache:
-        cache[key] = _contact_static(m, lead, out.device)
-    static = cache[key]
+    if m.topk:
+        static = _contact_topk(m, sl("scr_consrc").reshape(*lead, m.ncon), lead, out.device)
+    else:
+        key = (lead, str(out.device))
+        cache = m.__dict__.setdefault("_static_contact_cache", {})
+        if key not in cache:
+            cache[key] = _contact_static(m, lead, out.device)
+        static = cache[key]
     new["contact"] = Contact(dict(dist=sl("contact_dist").reshape(*lead, m.ncon), pos=sl("contact_pos").reshape(*lead, m.ncon, 3),
                                   frame=sl("contact_frame").reshape(*lead, m.ncon, 3, 3), **static))
     meta = dict(d._meta)

@@ -24,10 +24,14 @@ template <typename T> __device__ __forceinline__ V3<T> zaxis(const GeomPose<T>& 
 template <typename T>
 __device__ __forceinline__ void write_contact(const ModelView<T>& m, const EnvBuf<T>& d, int slot, T dist, const V3<T>& pos, const T* frame) {
   if (slot < 0) return;
-  d.set(m.D(D_contact_dist) + slot, dist);
-  st3(d, m.D(D_contact_pos) + 3 * slot, pos);
+  // max_contact_points models: `slot` is the candidate's index and the contact goes to the candidate scratch (k_topk selects)
+  const bool tk = m.h(H_topk) > 0;
+  const int oD = m.D(tk ? D_scr_cand_dist : D_contact_dist), oP = m.D(tk ? D_scr_cand_pos : D_contact_pos);
+  const int oF = m.D(tk ? D_scr_cand_frame : D_contact_frame);
+  d.set(oD + slot, dist);
+  st3(d, oP + 3 * slot, pos);
 #pragma unroll
-  for (int k = 0; k < 9; ++k) d.set(m.D(D_contact_frame) + 9 * slot + k, frame[k]);
+  for (int k = 0; k < 9; ++k) d.set(oF + 9 * slot + k, frame[k]);
 }
 
 // reference _plane_sphere :29-38
@@ -149,5 +153,46 @@ __global__ void __launch_bounds__(MJT_ENV_THREADS, MJT_COLLISION_MINB) k_collisi
   for (int env = blockIdx.y * blockDim.x + threadIdx.x; env < B; env += gridDim.y * blockDim.x) {
     EnvBuf<T> d{out + env, (size_t)B};
     for (int p = blockIdx.x; p < m.h(H_npair_cand); p += gridDim.x) collide_pair<T>(m, d, p);
+  }
+}
+
+
+// k_topk: max_contact_points (reference collision_driver.collision :822-840).  One thread per env: of the ncand candidate contacts
+// the K with the smallest distance are kept, in ascending distance like torch.topk(-dist, K) returns them (ties: the lower
+// candidate index first), then permuted by the baked argsort of the survivors' (equal) condims.  The contact and the index of the
+// candidate it came from go to the final slots; k_constraint looks the contact's parameters and bodies up through that index.
+template <typename T>
+__global__ void __launch_bounds__(MJT_ENV_THREADS) k_topk(const int* __restrict__ gblob, int blob_words, T* __restrict__ out, int B) {
+  extern __shared__ __align__(16) int smem_blob[];
+  __shared__ uint64_t bar;
+  stage_blob(smem_blob, &bar, gblob, blob_words);
+  const ModelView<T> m = make_view<T>(smem_blob);
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= B) return;
+  EnvBuf<T> d{out + env, (size_t)B};
+  const int K = m.h(H_topk), n = m.h(H_ncand);
+  const int oC = m.D(D_scr_cand_dist), oCP = m.D(D_scr_cand_pos), oCF = m.D(D_scr_cand_frame), oS = m.D(D_scr_consrc);
+  const int* perm = m.I(I_topk_perm);
+  T last = -t_inf<T>();
+  int last_i = -1;
+  for (int k = 0; k < K; ++k) {
+    // next candidate in (dist, index) order after (last, last_i)
+    T best = t_inf<T>();
+    int bi = -1;
+    for (int c = 0; c < n; ++c) {
+      const T v = d.get(oC + c);
+      const bool after = (v > last) || (v == last && c > last_i);
+      if (after && (bi < 0 || v < best)) { best = v; bi = c; }
+    }
+    if (bi < 0) { bi = last_i < 0 ? 0 : last_i; best = d.get(oC + bi); }   // NaN distances: keep the output defined
+    last = best;
+    last_i = bi;
+    // position of this survivor after the condim sort: slot s with perm[s] == k
+    int slot = k;
+    for (int s = 0; s < K; ++s) if (perm[s] == k) slot = s;
+    d.set(m.D(D_contact_dist) + slot, best);
+    for (int j = 0; j < 3; ++j) d.set(m.D(D_contact_pos) + 3 * slot + j, d.get(oCP + 3 * bi + j));
+    for (int j = 0; j < 9; ++j) d.set(m.D(D_contact_frame) + 9 * slot + j, d.get(oCF + 9 * bi + j));
+    d.set(oS + slot, T(bi));
   }
 }

@@ -287,14 +287,16 @@ __device__ void constraint_source(const ModelView<T>& m, const MjtIn& in, const 
       }
     } break;
     case SRC_CONTACT: {  // :408-583
-      const int c = id;
-      const int condim = m.I(I_con_dim)[c], b1 = m.I(I_con_body1)[c], b2 = m.I(I_con_body2)[c];
+      const int c = id;                                    // contact slot: where dist / pos / frame live
+      // parameter index: the slot itself, or with max_contact_points the candidate k_topk put into this slot
+      const int cc = m.h(H_topk) > 0 ? (int)d.get(m.D(D_scr_consrc) + c) : c;
+      const int condim = m.I(I_con_dim)[cc], b1 = m.I(I_con_body1)[cc], b2 = m.I(I_con_body2)[cc];
       const bool elliptic = m.h(H_cone) == 1;
       const int nrows = condim == 1 ? 1 : (elliptic ? condim : 2 * (condim - 1));
-      const T dist = d.get(m.D(D_contact_dist) + c) - m.F(F_con_includemargin)[c];
+      const T dist = d.get(m.D(D_contact_dist) + c) - m.F(F_con_includemargin)[cc];
       const bool active = dist < T(0);
       live = active;
-      const T* fri = m.F(F_con_friction) + 5 * c;
+      const T* fri = m.F(F_con_friction) + 5 * cc;
       const T t = m.F(F_body_invweight0)[2 * b1] + m.F(F_body_invweight0)[2 * b2];
       T jv[MJT_MAXROWS];
       for (int k = 0; k < MJT_MAXROWS; ++k) jv[k] = 0;
@@ -339,8 +341,8 @@ __device__ void constraint_source(const ModelView<T>& m, const MjtIn& in, const 
           }
         }
       }
-      const T* solref = m.F(F_con_solref) + 2 * c;
-      const T* solimp = m.F(F_con_solimp) + 5 * c;
+      const T* solref = m.F(F_con_solref) + 2 * cc;
+      const T* solimp = m.F(F_con_solimp) + 5 * cc;
       const T posa = active ? dist : T(0);
       if (condim == 1) {
         out.finish(row0, jv[0], posa, posa, t, solref, solimp, T(0));
@@ -351,7 +353,7 @@ __device__ void constraint_source(const ModelView<T>& m, const MjtIn& in, const 
         kbi(m, solref, solimp, posa, &k, &b, &imp);   // identical for every row of the pyramid
         for (int e = 0; e < nrows; ++e) out.finish_kbi(row0 + e, jv[e], posa, iw, k, b, imp, T(0));
       } else {
-        const T* srf0 = m.F(F_con_solreffriction) + 2 * c;
+        const T* srf0 = m.F(F_con_solreffriction) + 2 * cc;
         const bool any = srf0[0] != T(0) || srf0[1] != T(0);
         const T srf[2] = {any ? srf0[0] : srf0[0] + solref[0], any ? srf0[1] : srf0[1] + solref[1]};
         T k0, b0, imp0, k1, b1, imp1;   // normal row / friction rows (the impedance is the same: it depends on dist and solimp only)

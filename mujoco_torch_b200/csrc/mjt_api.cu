@@ -82,7 +82,8 @@ static const char* kFieldNames[] = {
     "geom_xpos", "geom_xmat", "site_xpos", "site_xmat", "subtree_com", "cinert", "crb", "cdof", "cdof_dot", "cvel", "qM", "qLD",
     "ten_length", "ten_J", "ten_velocity", "actuator_length", "actuator_moment", "actuator_velocity", "actuator_force", "qfrc_bias",
     "qfrc_passive", "qfrc_gravcomp", "qfrc_actuator", "qfrc_smooth", "qacc_smooth", "qfrc_constraint", "contact_dist", "contact_pos",
-    "contact_frame", "efc_J", "efc_D", "efc_aref", "efc_frictionloss", "efc_force", "sensordata", "scr_cacc", "scr_cfrc", "scr_live", "scr_ovf"
+    "contact_frame", "efc_J", "efc_D", "efc_aref", "efc_frictionloss", "efc_force", "sensordata", "scr_cacc", "scr_cfrc", "scr_live", "scr_ovf",
+    "scr_cand_dist", "scr_cand_pos", "scr_cand_frame", "scr_consrc"
 
 };
 static_assert(sizeof(kFieldNames) / sizeof(kFieldNames[0]) == NUM_D, "field name table out of sync with mjt_layout.h");
@@ -279,6 +280,11 @@ static int run_forward(const mjtModel* m, const MjtIn& in, T* pub, T* ws, int B,
     LAUNCH("k_collision", st, k_collision<T><<<grid, threads, blob_b, st>>>(m->d_blob, m->blob_words, ws, B));
     ++n;
   }
+  if (m->hv(H_topk) > 0) {   // max_contact_points: keep the K closest of the candidate contacts
+    if (set_smem<T>((const void*)k_topk<T>, blob_b)) return 1;
+    LAUNCH("k_topk", st, k_topk<T><<<gx, threads, blob_b, st>>>(m->d_blob, m->blob_words, ws, B));
+    ++n;
+  }
   if (upto == UPTO_COLLISION) return done();
   if (m->hv(H_nsrc) > 0) {
     if (set_smem<T>((const void*)k_constraint<T>, blob_b)) return 1;
@@ -417,6 +423,7 @@ extern "C" int mjt_forward(const mjtModel* m, const mjtStateIn* in, void* out, v
 extern "C" int mjt_step_launches(const mjtModel* m) {
   int per_forward = m->tile ? 3 : 2;  // k_smooth + k_solve (live-tile models: two k_solve passes)
   if (m->hv(H_npair_cand) > 0) ++per_forward;
+  if (m->hv(H_topk) > 0) ++per_forward;
   if (m->hv(H_nsrc) > 0) ++per_forward;
   if (m->hv(H_nsensordata) > 0) ++per_forward;
   if (m->hv(H_nsensordata) > 0 && m->hv(H_nsens_acc) > 0 && m->hv(H_nefc) > 0) ++per_forward;

@@ -22,7 +22,7 @@ disableflags solver cone integrator iterations ls_iterations
 data_words has_gravcomp has_fluid nv_pad nlim_sh nlim_ball nfric_dof nfric_ten nlim_ten
 ne_connect ne_weld ne_joint maskwords nsens_pos nsens_vel nsens_acc
 nconvex nrfgeom jc_words solve_blob_words live_rcap live_jcap
-layout_state pub_words n_mnz
+layout_state pub_words n_mnz topk ncand
 """.split()
 
 # ---- int arrays ---------------------------------------------------------------------------
@@ -44,7 +44,7 @@ sens_type sens_objid sens_adr sens_dim sens_datatype sens_stage sens_objtype sen
 rf_geom
 body_geomadr body_geomnum body_geom body_siteadr body_sitenum body_site
 cvx_geom cvx_nvert cvx_nface cvx_nfv cvx_nedge cvx_vertadr cvx_faceadr cvx_edgeadr cvx_normadr geom_cvx cvx_face cvx_edge
-m_nz geom_need row_order dof_ent
+m_nz geom_need row_order dof_ent topk_perm
 """.split()
 
 # ---- float arrays -------------------------------------------------------------------------
@@ -95,6 +95,9 @@ D_FIELDS = [
     # per row source: 1 when the constraint kernel instantiated non-zero rows for it this step; per env: 1 when the live
     # tile of the solver overflowed and the env has to be solved by the full-tile kernel
     ("scr_live", "(nsrc,)"), ("scr_ovf", "()"),
+    # max_contact_points (top-k contact selection, reference collision_driver.py:822-840): every candidate contact in group order,
+    # and per final contact slot the candidate it came from (all of size 0 for models without the numeric)
+    ("scr_cand_dist", "(ncand,)"), ("scr_cand_pos", "(ncand,3)"), ("scr_cand_frame", "(ncand,3,3)"), ("scr_consrc", "(ntopk,)"),
 ]
 
 # kernel dispatch "source" types for the constraint kernel
@@ -104,7 +107,7 @@ PAIR_FNS = "PLANE_SPHERE PLANE_CAPSULE SPHERE_SPHERE SPHERE_CAPSULE CAPSULE_CAPS
 PAIR_NCON = dict(PLANE_SPHERE=1, PLANE_CAPSULE=2, SPHERE_SPHERE=1, SPHERE_CAPSULE=1, CAPSULE_CAPSULE=1, PLANE_CONVEX=4,
                  SPHERE_CONVEX=1, CAPSULE_CONVEX=2, CONVEX_CONVEX=4)
 
-HIDDEN_FIELDS = {"scr_cacc", "scr_cfrc", "scr_live", "scr_ovf"}
+HIDDEN_FIELDS = {"scr_cacc", "scr_cfrc", "scr_live", "scr_ovf", "scr_cand_dist", "scr_cand_pos", "scr_cand_frame", "scr_consrc"}
 
 # ---- the "state" output layout (``step(..., outputs="state")``) --------------------------------------------------
 # Same kernels, second blob: its D-offset table describes a split buffer.  Words [0, pub_words) are the PUBLIC part -- the

@@ -260,13 +260,24 @@ class Model:
             dims += [p["dim"]] * n
             owner += [(ip, k) for k in range(n)]
         ncon = len(dims)
+        # max_contact_points (reference collision_driver.py:571-578, 822-840): of the `ncand` candidate contacts only the K with the
+        # smallest distance survive, chosen per env at run time.  The candidates then keep their group order (k_collision writes
+        # them to scratch slots), k_topk selects, and contact parameters / bodies are looked up through the selected candidate.
+        self.topk, self.ncand = 0, 0
         for i in range(getattr(mj, "nnumeric", 0)):
             nm = mj.names[int(mj.name_numericadr[i]):].split(b"\x00", 1)[0].decode()
             if nm == "max_contact_points" and 0 <= int(mj.numeric_data[int(mj.numeric_adr[i])]) < ncon:
-                raise NotImplementedError("max_contact_points top-k selection is not implemented")
+                self.topk, self.ncand = int(mj.numeric_data[int(mj.numeric_adr[i])]), ncon
+        if self.topk and len(set(dims)) > 1:
+            # the reference sizes the efc rows from the K smallest condims of the model (make_condim :618-644) while the contacts that
+            # survive are picked by distance: with mixed condims its row table and its contacts disagree -- nothing to be faithful to
+            raise NotImplementedError("max_contact_points with contacts of different condim is not supported")
         # The reference orders contacts with torch.argsort(contact_dim) (collision_driver.py:764,842), which is not a
         # stable sort for n > 16; we make the same call once here and bake the permutation.
         order = torch.argsort(torch.tensor(dims, dtype=torch.int32)).tolist() if ncon else []
+        if self.topk:
+            order = list(range(ncon))   # candidates stay in group order; the sort runs over the K selected (topk_perm)
+            self.topk_perm = torch.argsort(torch.tensor(dims[: self.topk], dtype=torch.int32)).tolist()
         slot_of = {owner[src]: dst for dst, src in enumerate(order)}
         self.pairs, self.ncon = pairs, ncon
         self.contact_order = order
@@ -284,6 +295,8 @@ class Model:
                 con["include"][c], con["friction"][c], con["solref"][c] = inc, fr, sr
                 con["solreffriction"][c], con["solimp"][c] = srf, si
         self.con = con
+        if self.topk:
+            self.ncon = ncon = self.topk   # contact slots; self.con keeps one entry per CANDIDATE
 
         # constraint row sources, in the reference's row order (constraint.py:651-674)
         src = []  # (type, id, nrows)
@@ -371,7 +384,11 @@ class Model:
             nrows_of[k] = nxt - row
         for k, (t, i, row) in enumerate(self.src):
             name = L.SRC_TYPES[t]
-            if name == "CONTACT":
+            if name == "CONTACT" and self.topk:
+                sup = set()   # any candidate may land in this slot: the union of their supports
+                for cnd in range(self.ncand):
+                    sup |= anc(int(gb[self.con["g1"][cnd]])) ^ anc(int(gb[self.con["g2"][cnd]]))
+            elif name == "CONTACT":
                 a, b = anc(int(gb[self.con["g1"][i]])), anc(int(gb[self.con["g2"][i]]))
                 sup = a ^ b
             elif name in ("EQ_CONNECT", "EQ_WELD"):
@@ -453,8 +470,9 @@ class Model:
         I["pair_g1"], I["pair_g2"] = i32([p["g1"] for p in self.pairs]), i32([p["g2"] for p in self.pairs])
         I["pair_slot"] = i32(self.pair_slot[: len(self.pairs)])
         gb = np.asarray(mj.geom_bodyid)
-        I["con_body1"], I["con_body2"] = i32(gb[self.con["g1"]]) if self.ncon else i32([]), i32(gb[self.con["g2"]]) if self.ncon else i32([])
+        I["con_body1"], I["con_body2"] = i32(gb[self.con["g1"]]) if len(self.con["g1"]) else i32([]), i32(gb[self.con["g2"]]) if len(self.con["g2"]) else i32([])
         I["con_dim"], I["con_efcadr"] = i32(self.con["dim"]), i32(self.con_efcadr)
+        I["topk_perm"] = i32(getattr(self, "topk_perm", []))
         I["con_geom1"], I["con_geom2"] = i32(self.con["g1"]), i32(self.con["g2"])
         I["src_type"], I["src_id"], I["src_row"] = (i32([s[k] for s in self.src]) for k in range(3))
         sp = self.sup
@@ -566,7 +584,7 @@ class Model:
         # Data field tables of the two output layouts (layout.py)
         sizes = dict(nq=self.nq, nv=self.nv, nu=self.nu, na=self.na, nbody=self.nbody, njnt=self.njnt, ngeom=self.ngeom,
                      nsite=self.nsite, ntendon=self.ntendon, ncon=self.ncon, nefc=self.nefc, nsensordata=self.nsensordata,
-                     nsrc=len(self.src))
+                     nsrc=len(self.src), ncand=self.ncand, ntopk=self.topk)
         self.field_shape, self.field_off, off = {}, {}, 0
         for name, expr in L.D_FIELDS:
             shp = tuple(int(s) for s in eval(expr, {}, sizes))
@@ -595,6 +613,8 @@ class Model:
             need.add("actuator_moment")
         if self.ncon:
             need |= {"contact_dist", "contact_pos", "contact_frame"}
+        if self.topk:
+            need |= {"scr_cand_dist", "scr_cand_pos", "scr_cand_frame", "scr_consrc"}
         if self.nefc:
             need |= {"efc_J", "efc_D", "efc_aref", "scr_live"}
             if self.nf:
@@ -638,7 +658,7 @@ class Model:
                  nfric_dof=cnt("FRIC_DOF"), nfric_ten=cnt("FRIC_TEN"), nlim_ten=cnt("LIM_TEN"), ne_connect=cnt("EQ_CONNECT"),
                  ne_weld=cnt("EQ_WELD"), ne_joint=cnt("EQ_JOINT"), maskwords=self.maskwords, nsens_pos=int((st == 1).sum()),
                  nsens_vel=int((st == 2).sum()), nsens_acc=int((st == 3).sum()), nconvex=len(cv), nrfgeom=len(rf), jc_words=self.sup["jc_words"],
-                 live_rcap=self.live_caps[0], live_jcap=self.live_caps[1], n_mnz=len(m_nz))
+                 live_rcap=self.live_caps[0], live_jcap=self.live_caps[1], n_mnz=len(m_nz), topk=self.topk, ncand=self.ncand)
         nH, nI, nF, nD, nPf = len(L.H_SCALARS), len(L.I_ARRAYS), len(L.F_ARRAYS), len(L.D_FIELDS), len(L.P_FIELDS)
         def assemble(keep=None, extra=None, state=False):
             """One blob; with ``keep`` only the named arrays carry data (the others get length 0)."""

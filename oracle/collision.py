@@ -113,4 +113,11 @@ def collision(m, d):
     d.contact_dist = torch.cat(dists, 1)[:, perm]
     d.contact_pos = torch.cat(poss, 1)[:, perm]
     d.contact_frame = torch.cat(frames, 1)[:, perm]
+    if getattr(m, "topk", 0):
+        # collision_driver.collision :822-840: `_, idx = torch.topk(-contact.dist, k=max_cp)`, then argsort by condim of the survivors
+        _, idx = torch.topk(-d.contact_dist, k=m.topk, dim=1)
+        idx = idx[:, m.topk_perm]
+        take = lambda x: torch.gather(x, 1, idx.reshape(idx.shape + (1,) * (x.dim() - 2)).expand(idx.shape + x.shape[2:]))
+        d.contact_dist, d.contact_pos, d.contact_frame = take(d.contact_dist), take(d.contact_pos), take(d.contact_frame)
+        d.contact_src = idx
     return d

@@ -191,45 +191,62 @@ def make_constraint(m, d):
         geom_body = np.asarray(mj.geom_bodyid)
         elliptic = m.cone == 1
         start = 0
+        def contact_rows(condim, ci, pi):
+            """Rows of contact slot `ci` (dist / pos / frame) with the parameters and bodies of contact-table entry `pi`."""
+            dist = d.contact_dist[:, ci] - c["includemargin"][pi]
+            body1, body2 = int(geom_body[int(c["geom1"][pi])]), int(geom_body[int(c["geom2"][pi])])
+            pos_c, frame = d.contact_pos[:, ci], d.contact_frame[:, ci]
+            jacp2, jacr2 = smooth.jac(m, d, pos_c, body2)
+            jacp1, jacr1 = smooth.jac(m, d, pos_c, body1)
+            diff = torch.matmul(frame, (jacp2 - jacp1).transpose(-1, -2))  # (B,3,nv)
+            t = m.body_invweight0[body1, 0] + m.body_invweight0[body2, 0]
+            active = (dist < 0).to(dt)
+            fri = c["friction"][pi]
+            if condim == 1:  # :408-451
+                pos = (dist * active)[:, None]
+                return (diff[:, 0:1] * active[:, None, None], pos, pos, t.expand(1), c["solref"][pi].expand(1, 2), c["solimp"][pi].expand(1, 5))
+            if not elliptic:  # :454-516
+                if condim > 3:
+                    diff = torch.cat((diff, torch.matmul(frame, (jacr2 - jacr1).transpose(-1, -2))), dim=1)
+                ne = (condim - 1) * 2
+                f = fri[: condim - 1].repeat_interleave(2) * torch.tensor([1.0, -1.0] * (condim - 1), dtype=dt)
+                j = diff[:, 0:1] + diff[:, 1:condim].repeat_interleave(2, dim=1) * f[None, :, None]
+                mu = fri[0]
+                iw = (t + mu * mu * t) * 2 * mu * mu / m.impratio
+                pos = dist[:, None].expand(B, ne) * active[:, None]
+                return (j * active[:, None, None], pos, pos, iw.expand(ne), c["solref"][pi].expand(ne, 2), c["solimp"][pi].expand(ne, 5))
+            # elliptic :519-583
+            j = diff
+            if condim > 3:
+                j = torch.cat((j, torch.matmul(frame, (jacr2 - jacr1).transpose(-1, -2))[:, : condim - 3]), dim=1)
+            srf = c["solreffriction"][pi]
+            srf = srf + c["solref"][pi] * float(not bool((srf != 0).any()))
+            solref = torch.cat((c["solref"][pi][None], srf[None].expand(condim - 1, 2)), dim=0)
+            fr2 = torch.square(fri[0]) / torch.square(fri[1 : condim - 1])
+            iw = torch.cat((t[None], (t / m.impratio)[None], (t / m.impratio) * fr2))
+            pos_aref = torch.zeros((B, condim), dtype=dt)
+            pos_aref[:, 0] = dist
+            return (j * active[:, None, None], pos_aref * active[:, None], dist[:, None].expand(B, condim), iw, solref, c["solimp"][pi].expand(condim, 5))
+
+        src = getattr(d, "contact_src", None) if getattr(m, "topk", 0) else None   # max_contact_points: candidate per (env, slot)
         for condim, count in ((1, n1), (3, n3), (4, n4), (6, n6)):
             for ci in range(start, start + count):
-                dist = d.contact_dist[:, ci] - c["includemargin"][ci]
-                body1, body2 = int(geom_body[int(c["geom1"][ci])]), int(geom_body[int(c["geom2"][ci])])
-                pos_c, frame = d.contact_pos[:, ci], d.contact_frame[:, ci]
-                jacp2, jacr2 = smooth.jac(m, d, pos_c, body2)
-                jacp1, jacr1 = smooth.jac(m, d, pos_c, body1)
-                diff = torch.matmul(frame, (jacp2 - jacp1).transpose(-1, -2))  # (B,3,nv)
-                t = m.body_invweight0[body1, 0] + m.body_invweight0[body2, 0]
-                active = (dist < 0).to(dt)
-                fri = c["friction"][ci]
-                if condim == 1:  # :408-451
-                    pos = (dist * active)[:, None]
-                    rows.add(diff[:, 0:1] * active[:, None, None], pos, pos, t.expand(1), c["solref"][ci].expand(1, 2),
-                             c["solimp"][ci].expand(1, 5))
-                elif not elliptic:  # :454-516
-                    if condim > 3:
-                        diff = torch.cat((diff, torch.matmul(frame, (jacr2 - jacr1).transpose(-1, -2))), dim=1)
-                    ne = (condim - 1) * 2
-                    f = fri[: condim - 1].repeat_interleave(2) * torch.tensor([1.0, -1.0] * (condim - 1), dtype=dt)
-                    j = diff[:, 0:1] + diff[:, 1:condim].repeat_interleave(2, dim=1) * f[None, :, None]
-                    mu = fri[0]
-                    iw = (t + mu * mu * t) * 2 * mu * mu / m.impratio
-                    pos = dist[:, None].expand(B, ne) * active[:, None]
-                    rows.add(j * active[:, None, None], pos, pos, iw.expand(ne), c["solref"][ci].expand(ne, 2),
-                             c["solimp"][ci].expand(ne, 5))
-                else:  # :519-583
-                    j = diff
-                    if condim > 3:
-                        j = torch.cat((j, torch.matmul(frame, (jacr2 - jacr1).transpose(-1, -2))[:, : condim - 3]), dim=1)
-                    srf = c["solreffriction"][ci]
-                    srf = srf + c["solref"][ci] * float(not bool((srf != 0).any()))
-                    solref = torch.cat((c["solref"][ci][None], srf[None].expand(condim - 1, 2)), dim=0)
-                    fr2 = torch.square(fri[0]) / torch.square(fri[1 : condim - 1])
-                    iw = torch.cat((t[None], (t / m.impratio)[None], (t / m.impratio) * fr2))
-                    pos_aref = torch.zeros((B, condim), dtype=dt)
-                    pos_aref[:, 0] = dist
-                    rows.add(j * active[:, None, None], pos_aref * active[:, None], dist[:, None].expand(B, condim), iw, solref,
-                             c["solimp"][ci].expand(condim, 5))
+                if src is None:
+                    rows.add(*contact_rows(condim, ci, ci))
+                    continue
+                # the slot holds a different candidate in different envs: evaluate each candidate that occurs, pick per env
+                merged = None
+                for v in torch.unique(src[:, ci]).tolist():
+                    r = contact_rows(condim, ci, int(v))
+                    nrow = r[1].shape[1]
+                    r = (r[0], r[1], r[2], r[3].expand(B, nrow), r[4].expand(B, nrow, 2), r[5].expand(B, nrow, 5))
+                    if merged is None:
+                        merged = [x.clone() for x in r]
+                    else:
+                        sel = src[:, ci] == v
+                        for x, y in zip(merged, r):
+                            x[sel] = y[sel]
+                rows.add(*merged)
             start += count
 
     J = torch.cat(rows.J, dim=1)

@@ -232,17 +232,23 @@ class OModel:
         contact_dim = torch.tensor(diml, dtype=torch.int32)
         total = len(diml)
         max_cp = _max_contact_points(mj)
+        self.topk = 0
         if max_cp > -1 and total > max_cp:
-            raise NotImplementedError("max_contact_points top-k is data dependent; not on the oracle path")
+            # collision_driver.collision :822-840: the K closest candidates survive, per env; the contact table below then keeps
+            # one entry per CANDIDATE (group order) and oracle.collision records which candidate sits in which slot
+            if len(set(diml)) > 1:
+                raise NotImplementedError("max_contact_points with contacts of different condim is not supported")
+            self.topk, self.ncand = max_cp, total
+            self.topk_perm = torch.argsort(contact_dim[:max_cp])
         # The reference sorts with an UNSTABLE argsort (collision_driver.py:764,842): same call, same torch build.
-        sort_idx = torch.argsort(contact_dim)
+        sort_idx = torch.argsort(contact_dim) if not self.topk else torch.arange(total)
         self.contact_perm = sort_idx
         f = lambda l: torch.stack([torch.as_tensor(np.asarray(x, dtype=np.float64)) for x in l]).to(dt)[sort_idx]
         self.contact = dict(
             geom1=torch.tensor(g1l)[sort_idx], geom2=torch.tensor(g2l)[sort_idx], dim=contact_dim[sort_idx],
             includemargin=f(im), friction=f(fr), solref=f(sr), solreffriction=f(srf), solimp=f(si),
         )
-        self.ncon = total
+        self.ncon = self.topk or total
 
     def _params(self, c):
         """reference collision_driver.py:177-257 for one candidate (float64 host arithmetic)."""
@@ -295,7 +301,7 @@ class OModel:
         nc = 0
         counts = [0, 0, 0, 0]
         if self.ncon:
-            dims = self.contact["dim"]
+            dims = self.contact["dim"][: self.ncon]   # max_contact_points: the K smallest condims (make_condim :618-644; all equal here)
             for k, condim in enumerate((1, 3, 4, 6)):
                 n = int((dims == condim).sum())
                 counts[k] = n

@@ -107,6 +107,9 @@ CASES = [
     # and as a gain-only general actuator (drop -4 = tests/util.muscle_state), Euler and ImplicitFast
     ("muscle", "muscle", {}, 32, -4.0, 3),
     ("muscle_implicitfast", "muscle", {"integrator": 3}, 32, -4.0, 2),
+    # max_contact_points = 6 of 19 candidate contacts: data-dependent contact selection, parameters and geom ids per env
+    # (collision_driver.py:822-840); loose pile of capsules and a ball on the floor, two steps
+    ("capsules_topk", "capsules_topk", {}, 32, -1.0, 2),
 ]
 
 

@@ -181,11 +181,13 @@ def test_oracle_matches_reference(path):
             return getattr(do, ocon[k]).numpy()
         B = z["in_qpos"].shape[0]
         if k == "efc_address":
-            dims = mo.contact["dim"].numpy()
+            dims = mo.contact["dim"].numpy()[: mo.ncon]
             rows = np.where(dims == 1, 1, dims if mo.cone == 1 else 2 * (dims - 1))
             adr = mo.ne + mo.nf + mo.nl + np.concatenate([[0], np.cumsum(rows)[:-1]])
             return np.tile(adr, (B, 1))
         key = {"contact_dim": "dim"}.get(k, k)
+        if getattr(mo, "topk", 0):   # max_contact_points: the slot's parameters are those of the candidate selected in that env
+            return mo.contact[key][do.contact_src].numpy()
         v = mo.contact[key].numpy()
         return np.tile(v, (B,) + (1,) * v.ndim)
 

@@ -330,7 +330,7 @@ STATE_CASES = [
     ("frictionloss_dof", {"integrator": 3}, "seed", 0.0), ("equality_bodies", {}, "seed", 0.0), ("equality", {}, "seed", 0.0),
     ("sink", {}, "sink", 0.0), ("sink", {"cone": 1}, "sink", 0.0), ("sink", {"integrator": 3}, "sink", 0.0), ("sink", {"integrator": 1}, "sink", 0.0),
     ("convex", {}, "pile", 0.0), ("stack", {}, "stack", 0.0), ("cartpole", {}, "seed", 0.0),
-    ("muscle", {}, "muscle", 0.0), ("muscle", {"integrator": 3}, "muscle", 0.0),
+    ("muscle", {}, "muscle", 0.0), ("muscle", {"integrator": 3}, "muscle", 0.0), ("capsules_topk", {}, "pile", 0.0),
 ]
 
 

@@ -92,6 +92,88 @@ def test_g5_parent_child_filter():
     assert m2.ncon == 1
 
 
+def _collide(xml):
+    _, m = _model(xml)
+    d = of.make_data(m, 1)
+    d = osm.kinematics(m, d)
+    return m, ocol.collision(m, d)
+
+
+CAPSULES_BODY = """<worldbody>
+  <body pos="0 0 0.54"><joint axis="1 0 0" type="free"/><geom fromto="-0.4 0 0 0.4 0 0" size="0.05" type="capsule"/></body>
+  <body pos="0 0 0.54"><joint axis="1 0 0" type="free"/><geom fromto="-0.4 0 0 0.4 0 0" size="0.05" type="capsule"/></body>
+  <body pos="0 0 0.54"><joint axis="1 0 0" type="free"/><geom fromto="-0.4 0 0 0.4 0 0" size="0.05" type="capsule"/></body>
+</worldbody>"""
+
+
+def test_g5_top_k_contacts():
+    """reference test/collision_driver_test.py:470-524 (TopKContactTest): three coincident capsules give 3 contacts, 2 with
+    `max_contact_points = 2`; the product's device_put sizes its contact slots the same way."""
+    import mujoco_torch_b200 as mt
+
+    m_all, d_all = _collide(f"<mujoco>{CAPSULES_BODY}</mujoco>")
+    xml_k = f'<mujoco><custom><numeric data="2" name="max_contact_points"/></custom>{CAPSULES_BODY}</mujoco>'
+    m_k, d_k = _collide(xml_k)
+    assert m_all.ncon == 3 and d_all.contact_dist.shape == (1, 3)
+    assert m_k.ncon == 2 and d_k.contact_dist.shape == (1, 2) and d_k.contact_src.shape == (1, 2)
+    mx = mt.device_put(mjcf.from_xml_string(xml_k))
+    assert (mx.topk, mx.ncand, mx.ncon) == (2, 3, 2) and mx.field_shape["scr_cand_dist"] == (3,) and mx.field_shape["contact_dist"] == (2,)
+    assert mt.device_put(mjcf.from_xml_string(f"<mujoco>{CAPSULES_BODY}</mujoco>")).topk == 0
+    # the K survivors are the closest candidates, in ascending distance (torch.topk(-dist))
+    mixed = """<mujoco><custom><numeric data="2" name="max_contact_points"/></custom><worldbody>
+      <geom type="plane" size="5 5 0.1"/>
+      <body pos="0 0 0.03"><joint type="free"/><geom size="0.05"/></body>
+      <body pos="1 0 0.045"><joint type="free"/><geom size="0.05"/></body>
+      <body pos="2 0 0.2"><joint type="free"/><geom size="0.05"/></body>
+      <body pos="3 0 0.01"><joint type="free"/><geom size="0.05"/></body></worldbody></mujoco>"""
+    m_m, d_m = _collide(mixed)
+    plane_sphere = [i for i in range(m_m.ncand) if int(m_m.contact["geom1"][i]) == 0]
+    chosen = [int(m_m.contact["geom2"][int(i)]) for i in d_m.contact_src[0]]
+    assert chosen == [4, 1] and m_m.ncand > m_m.ncon == 2 and len(plane_sphere) == 4     # geoms 4 (z 0.01) and 1 (z 0.03) are deepest
+    np.testing.assert_allclose(d_m.contact_dist[0].numpy(), [0.01 - 0.05, 0.03 - 0.05], atol=1e-12)
+
+
+def test_g4_box_plane_at_45_degrees():
+    """reference test/collision_driver_test.py:261-282: a unit box rotated 45 degrees about x above a plane touches it along an
+    edge: the first two manifold points penetrate, the last two do not."""
+    m, d = _collide("""<mujoco><worldbody><geom size="40 40 40" type="plane"/>
+      <body pos="0 0 0.7" euler="45 0 0"><joint axis="1 0 0" type="free"/><geom size="0.5 0.5 0.5" type="box"/></body></worldbody></mujoco>""")
+    dist = d.contact_dist[0].numpy()
+    assert dist.shape == (4,) and (dist[:2] < 0).all() and (dist[2:] > 0).all()
+    np.testing.assert_allclose(dist[:2], 0.7 - 0.5 * np.sqrt(2.0), atol=1e-9)
+    np.testing.assert_allclose(d.contact_frame[0, :2, 0].numpy(), [[0, 0, 1.0]] * 2, atol=1e-12)
+
+
+def test_g4_box_box_face():
+    """reference test/collision_driver_test.py:284-308: a small tilted box resting on a larger one: 4 contacts, all penetrating,
+    at z ~ 0.39 (2 decimals), normal +z."""
+    m, d = _collide("""<mujoco><worldbody>
+      <body pos="0.0 1.0 0.2"><joint axis="1 0 0" type="free"/><geom size="0.2 0.2 0.2" type="box"/></body>
+      <body pos="0.1 1.0 0.495" euler="0.1 -0.1 0"><joint axis="1 0 0" type="free"/><geom size="0.1 0.1 0.1" type="box"/></body>
+    </worldbody></mujoco>""")
+    assert d.contact_pos.shape == (1, 4, 3) and (d.contact_dist[0] < 0).all()
+    np.testing.assert_array_almost_equal(d.contact_pos[0, :, 2].numpy(), [0.39] * 4, 2)
+    np.testing.assert_array_almost_equal(d.contact_frame[0, :, 0, :].numpy(), [[0.0, 0.0, 1.0]] * 4)
+
+
+def test_g4_box_box_edge():
+    """reference test/collision_driver_test.py:310-336: an edge-edge box contact: exactly one penetrating point."""
+    m, d = _collide("""<mujoco><worldbody>
+      <body pos="-1.0 -1.0 0.2"><joint axis="1 0 0" type="free"/><geom size="0.2 0.2 0.2" type="box"/></body>
+      <body pos="-1.0 -1.2 0.55" euler="0 45 30"><joint axis="1 0 0" type="free"/><geom size="0.1 0.1 0.1" type="box"/></body>
+    </worldbody></mujoco>""")
+    dist = d.contact_dist[0].numpy()
+    assert (dist[:1] < 0).all() and (dist[1:] > 0).all()
+
+
+def test_g4_capsule_box_edge():
+    """reference test/collision_driver_test.py:230-254: a tilted capsule touching a box edge: two slots, the second one separated."""
+    m, d = _collide("""<mujoco><worldbody>
+      <body pos="0.5 0 0.55" euler="0 30 0"><joint axis="1 0 0" type="free"/><geom fromto="-0.6 0 0 0.6 0 0" size="0.05" type="capsule"/></body>
+      <body><joint axis="1 0 0" type="free"/><geom size="0.5 0.5 0.5" type="box"/></body></worldbody></mujoco>""")
+    assert d.contact_pos.shape == (1, 2, 3) and float(d.contact_dist[0, 1]) > 0 and float(d.contact_dist[0, 0]) < 0
+
+
 def test_g6_segment_geometry():
     """reference test/math_test.py:131-188 (closest points between segments; literals)."""
     t = lambda *v: torch.tensor([v], dtype=torch.float64)
