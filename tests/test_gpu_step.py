@@ -191,9 +191,10 @@ def _compare(mj, B, dtype, tol, drop, label=""):
              for k in ("qpos", "qvel", "qacc")}
     warnings.warn(f"parity {label} {'f32' if f32 else 'f64'} B={B}: oracle-unstable envs {n_unst}, extra outliers {n_extra}, worst error on compared envs "
                   + ", ".join(f"{k} {v:.1e}" for k, v in worst.items()))
-    allowed = n_unst + (2 if n_unst else 0) + (B // 20 if f32 else 0)
-    assert n_unst <= 0.35 * B, f"too many oracle-unstable envs: {n_unst}/{B}"
-    assert n_extra <= allowed, f"{n_extra} envs beyond tol {tol} while the oracle itself is unstable on only {n_unst}/{B}"
+    # Allowances = the worst case observed over every config on the B200 (round 2 GPU test log, profiles/r2_gpu_tests.txt:
+    # 9 oracle-unstable envs of 64 -- convex pile / Humanoid with 1 solver iteration -- and 2 extra outliers) plus 2.
+    assert n_unst <= 11 * B // 64, f"too many oracle-unstable envs: {n_unst}/{B}"
+    assert n_extra <= 4, f"{n_extra} envs beyond tol {tol} while the oracle itself is unstable on only {n_unst}/{B}"
     ok = ~(unstable | outlier)
     bad = {}
 
