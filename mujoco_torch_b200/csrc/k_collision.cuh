@@ -83,11 +83,20 @@ __device__ __forceinline__ void closest_segment_to_segment(const V3<T>& a0, cons
 template <typename T>
 __device__ void convex_pair(const ModelView<T>& m, const EnvBuf<T>& d, int fn, int g1, int g2, const int* slot);
 
+// height fields (k_hfield.cuh): a real call, so that its stack and registers do not weigh on the other pair types
 template <typename T>
+__device__ __noinline__ void hfield_pair(const ModelView<T>& m, const EnvBuf<T>& d, int p, int fn, int g1, int g2, const int* slot);
+
+// HF: the instantiation for models with height-field pairs (its callee costs registers and stack; everything else runs HF = false)
+template <typename T, bool HF>
 __device__ void collide_pair(const ModelView<T>& m, const EnvBuf<T>& d, int p) {
   const int fn = m.I(I_pair_fn)[p], g1 = m.I(I_pair_g1)[p], g2 = m.I(I_pair_g2)[p];
   const int* slot = m.I(I_pair_slot) + 4 * p;
   const T* size = m.F(F_geom_size);
+  if (fn >= FN_HFIELD_SPHERE) {
+    if (HF) hfield_pair<T>(m, d, p, fn, g1, g2, slot);
+    return;
+  }
   if (fn >= FN_PLANE_CONVEX) {
     convex_pair<T>(m, d, fn, g1, g2, slot);
     return;
@@ -143,7 +152,7 @@ __device__ void collide_pair(const ModelView<T>& m, const EnvBuf<T>& d, int p) {
   }
 }
 
-template <typename T>
+template <typename T, bool HF>
 __global__ void __launch_bounds__(MJT_ENV_THREADS, MJT_COLLISION_MINB) k_collision(const int* __restrict__ gblob, int blob_words, T* __restrict__ out, int B) {
   extern __shared__ __align__(16) int smem_blob[];
   __shared__ uint64_t bar;
@@ -152,7 +161,7 @@ __global__ void __launch_bounds__(MJT_ENV_THREADS, MJT_COLLISION_MINB) k_collisi
   // grid.x walks the candidate pairs (fastest), grid.y the env blocks (see k_constraint)
   for (int env = blockIdx.y * blockDim.x + threadIdx.x; env < B; env += gridDim.y * blockDim.x) {
     EnvBuf<T> d{out + env, (size_t)B};
-    for (int p = blockIdx.x; p < m.h(H_npair_cand); p += gridDim.x) collide_pair<T>(m, d, p);
+    for (int p = blockIdx.x; p < m.h(H_npair_cand); p += gridDim.x) collide_pair<T, HF>(m, d, p);
   }
 }
 

@@ -216,14 +216,9 @@ __device__ __forceinline__ int best_face(int nface, S support, bool* all_negativ
   return best;
 }
 
+// sphere against a hull, everything in the hull's frame (sp = sphere centre): distance, contact position, normal (sphere -> hull)
 template <typename T>
-__device__ void sphere_convex(const ModelView<T>& m, const EnvBuf<T>& d, int g1, int g2, const int* slot) {
-  GeomPose<T> s, cx;
-  load_geom(m, d, g1, s);
-  load_geom(m, d, g2, cx);
-  const Hull<T> h = load_hull(m, g2);
-  const T r = m.F(F_geom_size)[3 * g1];
-  const V3<T> sp = mat_tmul(cx.mat, s.pos - cx.pos);
+__device__ void sphere_hull_core(const Hull<T>& h, const V3<T>& sp, T r, T* dist, V3<T>* pos, V3<T>* nrm) {
   const int f = best_face<T>(h.nface, [&](int k) { const V3<T> nk = h.n(k); return dot(sp - nk * r - h.v(h.face[k * h.nfv]), nk); }, nullptr);
   const V3<T> normal = h.n(f), f0 = h.v(h.face[f * h.nfv]);
   V3<T> pt = sp - normal * dot(sp - f0, normal);
@@ -246,20 +241,29 @@ __device__ void sphere_convex(const ModelView<T>& m, const EnvBuf<T>& d, int g1,
   T dd;
   const V3<T> n = normalize3(pt - sp, &dd);
   const V3<T> spt = sp + n * r;
-  T frame[9];
-  make_frame(mat_mul(cx.mat, n), frame);
-  write_contact(m, d, slot[0], dd - r, mat_mul(cx.mat, (pt + spt) * T(0.5)) + cx.pos, frame);
+  *dist = dd - r;
+  *pos = (pt + spt) * T(0.5);
+  *nrm = n;
 }
 
 template <typename T>
-__device__ void capsule_convex(const ModelView<T>& m, const EnvBuf<T>& d, int g1, int g2, const int* slot) {
-  GeomPose<T> cap, cx;
-  load_geom(m, d, g1, cap);
+__device__ void sphere_convex(const ModelView<T>& m, const EnvBuf<T>& d, int g1, int g2, const int* slot) {
+  GeomPose<T> s, cx;
+  load_geom(m, d, g1, s);
   load_geom(m, d, g2, cx);
   const Hull<T> h = load_hull(m, g2);
-  const T r = m.F(F_geom_size)[3 * g1], len = m.F(F_geom_size)[3 * g1 + 1];
-  const V3<T> cpos = mat_tmul(cx.mat, cap.pos - cx.pos), seg = mat_tmul(cx.mat, zaxis(cap)) * len;
-  const V3<T> c0 = cpos - seg, c1 = cpos + seg;
+  T dist;
+  V3<T> pos, n;
+  sphere_hull_core<T>(h, mat_tmul(cx.mat, s.pos - cx.pos), m.F(F_geom_size)[3 * g1], &dist, &pos, &n);
+  T frame[9];
+  make_frame(mat_mul(cx.mat, n), frame);
+  write_contact(m, d, slot[0], dist, mat_mul(cx.mat, pos) + cx.pos, frame);
+}
+
+// capsule (segment c0-c1, radius r) against a hull in the hull's frame: two slots with penetration, position and the face / edge
+// normal `nrm` (hull -> capsule; the contact normal is its negative)
+template <typename T>
+__device__ void capsule_hull_core(const Hull<T>& h, const V3<T>& c0, const V3<T>& c1, T r, T* pen, V3<T>* pos, V3<T>* nrm, bool need_support = true) {
   bool has_support;
   const int f = best_face<T>(h.nface, [&](int k) {
     const V3<T> nk = h.n(k), nr = nk * r, fk = h.v(h.face[k * h.nfv]);
@@ -273,14 +277,13 @@ __device__ void capsule_convex(const ModelView<T>& m, const EnvBuf<T>& d, int g1
     *pp = e0;
     *pn = cross(e1 - e0, normal);
   }, &cl[0], &cl[1]);
-  V3<T> pos[2], nrm[2];
-  T pen[2];
   for (int k = 0; k < 2; ++k) {
     const V3<T> c = cl[k] - normal * r;
     const V3<T> fp = c - normal * dot(c - f0, normal);
     pos[k] = (c + fp) * T(0.5);
     nrm[k] = normal;
-    pen[k] = (mask && has_support) ? dot(fp - c, normal) : T(-1);
+    // capsule_convex :741-747 also requires every face to see the capsule behind it; _capsule_prism (collision_hfield.py:133-141) does not
+    pen[k] = (mask && (has_support || !need_support)) ? dot(fp - c, normal) : T(-1);
   }
   // closest face edge to the capsule axis (:760-784)
   V3<T> ec(0, 0, 0), cc(0, 0, 0);
@@ -299,6 +302,19 @@ __device__ void capsule_convex(const ModelView<T>& m, const EnvBuf<T>& d, int g1
     nrm[0] = eaxis;
     pen[0] = r - edist;
   }
+}
+
+template <typename T>
+__device__ void capsule_convex(const ModelView<T>& m, const EnvBuf<T>& d, int g1, int g2, const int* slot) {
+  GeomPose<T> cap, cx;
+  load_geom(m, d, g1, cap);
+  load_geom(m, d, g2, cx);
+  const Hull<T> h = load_hull(m, g2);
+  const T r = m.F(F_geom_size)[3 * g1], len = m.F(F_geom_size)[3 * g1 + 1];
+  const V3<T> cpos = mat_tmul(cx.mat, cap.pos - cx.pos), seg = mat_tmul(cx.mat, zaxis(cap)) * len;
+  V3<T> pos[2], nrm[2];
+  T pen[2];
+  capsule_hull_core<T>(h, cpos - seg, cpos + seg, r, pen, pos, nrm);
   for (int k = 0; k < 2; ++k) {
     T frame[9];
     make_frame(mat_mul(cx.mat, -nrm[k]), frame);
@@ -306,14 +322,10 @@ __device__ void capsule_convex(const ModelView<T>& m, const EnvBuf<T>& d, int g1
   }
 }
 
+// hull A (pose A) against hull B (pose Bp): four manifold slots (distance, position in B's frame) and the separating axis in B's
+// frame, oriented A -> B like the reference's _sat_hull_hull (the callers order the hulls: fewer vertices first)
 template <typename T>
-__device__ void convex_convex(const ModelView<T>& m, const EnvBuf<T>& d, int g1, int g2, const int* slot) {
-  Hull<T> ha = load_hull(m, g1), hb = load_hull(m, g2);
-  const bool swapped = ha.nvert > hb.nvert;
-  if (swapped) { const Hull<T> t = ha; ha = hb; hb = t; const int g = g1; g1 = g2; g2 = g; }
-  GeomPose<T> A, Bp;
-  load_geom(m, d, g1, A);
-  load_geom(m, d, g2, Bp);
+__device__ void hull_hull_core(const Hull<T>& ha, const GeomPose<T>& A, const Hull<T>& hb, const GeomPose<T>& Bp, T* dist, V3<T>* pos, V3<T>* axis_out) {
   const int P = ha.nfv > hb.nfv ? ha.nfv : hb.nfv;
   // hull A expressed in hull B's frame
   T tm[9];
@@ -416,8 +428,6 @@ __device__ void convex_convex(const ModelView<T>& m, const EnvBuf<T>& d, int g1,
     ref_n = hb.n(b_max);
     inc_n = NA(a_min);
   }
-  T dist[4];
-  V3<T> pos[4];
   contact_manifold<T>(ref, inc, P, ref_n, inc_n, dist, pos);
   if (is_edge) {
     int k0 = 0;
@@ -426,7 +436,21 @@ __device__ void convex_convex(const ModelView<T>& m, const EnvBuf<T>& d, int g1,
     const V3<T> p0 = pos[k0];
     for (int k = 0; k < 4; ++k) { dist[k] = k == 0 ? d0 : T(1); pos[k] = p0; }
   }
-  V3<T> nw = mat_mul(Bp.mat, best_axis * T(best_sign));
+  *axis_out = best_axis * T(best_sign);
+}
+
+template <typename T>
+__device__ void convex_convex(const ModelView<T>& m, const EnvBuf<T>& d, int g1, int g2, const int* slot) {
+  Hull<T> ha = load_hull(m, g1), hb = load_hull(m, g2);
+  const bool swapped = ha.nvert > hb.nvert;
+  if (swapped) { const Hull<T> t = ha; ha = hb; hb = t; const int g = g1; g1 = g2; g2 = g; }
+  GeomPose<T> A, Bp;
+  load_geom(m, d, g1, A);
+  load_geom(m, d, g2, Bp);
+  T dist[4];
+  V3<T> pos[4], axis;
+  hull_hull_core<T>(ha, A, hb, Bp, dist, pos, &axis);
+  V3<T> nw = mat_mul(Bp.mat, axis);
   if (swapped) nw = -nw;
   T frame[9];
   make_frame(nw, frame);

@@ -10,6 +10,7 @@
 #include "k_collision.cuh"
 #include "k_constraint.cuh"
 #include "k_convex.cuh"
+#include "k_hfield.cuh"
 #include "k_sensor.cuh"
 #include "k_smooth.cuh"
 #include "mjt_solve_layout.h"
@@ -70,6 +71,7 @@ struct mjtModel {
   int tile_envs;
   size_t tile_smem, tile_region_bytes;
   // tuning knobs, read from the environment once at mjt_model_create (never on the launch path)
+  bool has_hfield;        // some candidate pair is a height-field pair (selects the k_collision instantiation)
   int constraint_split;   // CTAs per env block in k_constraint
   int ovf_envs;           // envs per CTA of the live-tile overflow pass
   int hv(int k) const { return h[k]; }
@@ -173,6 +175,8 @@ extern "C" int mjt_model_create(const void* blob_host, size_t nbytes, int device
     delete m;
     return fail("mjt_model_create: model blob exceeds shared memory");
   }
+  m->has_hfield = false;
+  for (int p = 0; p < w[H_npair_cand]; ++p) m->has_hfield = m->has_hfield || (w[w[MJT_OFF_I + I_pair_fn] + p] >= FN_HFIELD_SPHERE);
   m->constraint_split = w[H_nsrc] < MJT_CONSTRAINT_SPLIT ? w[H_nsrc] : MJT_CONSTRAINT_SPLIT;
   if (const char* fs = getenv("MJT_CONSTRAINT_SPLIT")) { const int v = atoi(fs); if (v >= 1) m->constraint_split = v < w[H_nsrc] ? v : w[H_nsrc]; }
   m->ovf_envs = 32 / G;   // one warp per CTA: CTAs without a flagged env leave at once, flagged envs pack the SMs
@@ -275,9 +279,14 @@ static int run_forward(const mjtModel* m, const MjtIn& in, T* pub, T* ws, int B,
   ++n;
   if (upto == UPTO_SMOOTH) return done();
   if (m->hv(H_npair_cand) > 0) {
-    if (set_smem<T>((const void*)k_collision<T>, blob_b)) return 1;
     dim3 grid(m->hv(H_npair_cand), gx < 65535 ? gx : 65535);
-    LAUNCH("k_collision", st, k_collision<T><<<grid, threads, blob_b, st>>>(m->d_blob, m->blob_words, ws, B));
+    if (m->has_hfield) {
+      if (set_smem<T>((const void*)k_collision<T, true>, blob_b)) return 1;
+      LAUNCH("k_collision", st, k_collision<T, true><<<grid, threads, blob_b, st>>>(m->d_blob, m->blob_words, ws, B));
+    } else {
+      if (set_smem<T>((const void*)k_collision<T, false>, blob_b)) return 1;
+      LAUNCH("k_collision", st, k_collision<T, false><<<grid, threads, blob_b, st>>>(m->d_blob, m->blob_words, ws, B));
+    }
     ++n;
   }
   if (m->hv(H_topk) > 0) {   // max_contact_points: keep the K closest of the candidate contacts

@@ -45,6 +45,7 @@ rf_geom
 body_geomadr body_geomnum body_geom body_siteadr body_sitenum body_site
 cvx_geom cvx_nvert cvx_nface cvx_nfv cvx_nedge cvx_vertadr cvx_faceadr cvx_edgeadr cvx_normadr geom_cvx cvx_face cvx_edge
 m_nz geom_need row_order dof_ent topk_perm
+hf_nrow hf_ncol hf_adr pair_hf
 """.split()
 
 # ---- float arrays -------------------------------------------------------------------------
@@ -62,6 +63,7 @@ con_includemargin con_friction con_solref con_solreffriction con_solimp
 eq_data eq_solref eq_solimp
 sens_cutoff
 cvx_vert cvx_norm
+hf_size hf_data pair_rbound
 """.split()
 
 # slots inside the ``opt`` float array
@@ -103,9 +105,10 @@ D_FIELDS = [
 # kernel dispatch "source" types for the constraint kernel
 SRC_TYPES = "EQ_CONNECT EQ_WELD EQ_JOINT FRIC_DOF FRIC_TEN LIM_BALL LIM_SH LIM_TEN CONTACT".split()
 # narrowphase function ids
-PAIR_FNS = "PLANE_SPHERE PLANE_CAPSULE SPHERE_SPHERE SPHERE_CAPSULE CAPSULE_CAPSULE PLANE_CONVEX SPHERE_CONVEX CAPSULE_CONVEX CONVEX_CONVEX".split()
+PAIR_FNS = ("PLANE_SPHERE PLANE_CAPSULE SPHERE_SPHERE SPHERE_CAPSULE CAPSULE_CAPSULE PLANE_CONVEX SPHERE_CONVEX CAPSULE_CONVEX CONVEX_CONVEX "
+            "HFIELD_SPHERE HFIELD_CAPSULE HFIELD_CONVEX").split()
 PAIR_NCON = dict(PLANE_SPHERE=1, PLANE_CAPSULE=2, SPHERE_SPHERE=1, SPHERE_CAPSULE=1, CAPSULE_CAPSULE=1, PLANE_CONVEX=4,
-                 SPHERE_CONVEX=1, CAPSULE_CONVEX=2, CONVEX_CONVEX=4)
+                 SPHERE_CONVEX=1, CAPSULE_CONVEX=2, CONVEX_CONVEX=4, HFIELD_SPHERE=4, HFIELD_CAPSULE=4, HFIELD_CONVEX=4)
 
 HIDDEN_FIELDS = {"scr_cacc", "scr_cfrc", "scr_live", "scr_ovf", "scr_cand_dist", "scr_cand_pos", "scr_cand_frame", "scr_consrc"}
 

@@ -414,6 +414,11 @@ class Compiler:
         g["rgba"] = rgba
         g["matid"] = self._materials["index"].get(a.get("material"), -1) if a.get("material") else -1
         g["dataid"] = -1
+        if gtype == GeomType.HFIELD:
+            hid = meshes["hfield_index"][a["hfield"]]
+            g["dataid"] = hid
+            hs = meshes["hfields"][hid]["size"]
+            g["size"] = size = np.array([hs[0], hs[1], 0.25 * hs[2] + 0.5 * hs[3]])   # MuJoCo: geom size of a height field (x, y, z half sizes)
         if gtype == GeomType.MESH:
             mid = meshes["index"][a["mesh"]]
             mm = meshes["list"][mid]
@@ -434,6 +439,9 @@ class Compiler:
             g["rbound"] = np.linalg.norm(size) if gtype == GeomType.BOX else np.max(size)
         elif gtype == GeomType.MESH:
             g["rbound"] = float(np.max(np.linalg.norm(meshes["list"][g["dataid"]]["vert"], axis=1)))
+        elif gtype == GeomType.HFIELD:
+            hs = meshes["hfields"][g["dataid"]]["size"]
+            g["rbound"] = float(np.sqrt(hs[0] ** 2 + hs[1] ** 2 + max(hs[2], hs[3]) ** 2))
         else:
             g["rbound"] = 0.0
         return g
@@ -478,9 +486,23 @@ class Compiler:
         root = self.root
         m = MjModelLite()
         # meshes
-        meshes = {"index": {}, "list": [], "names": []}
+        meshes = {"index": {}, "list": [], "names": [], "hfield_index": {}, "hfields": []}
         asset = root.find("asset")
         if asset is not None:
+            # height fields: <hfield name nrow ncol size="rx ry elevation_z base_z" elevation="nrow*ncol values, row-major"/>; like
+            # MuJoCo's compiler the data are shifted / scaled into [0, 1] (file-based height fields are not supported)
+            for he in asset.findall("hfield"):
+                a = dict(he.attrib)
+                if "file" in a:
+                    raise NotImplementedError("hfield from file is not supported; give nrow / ncol / elevation")
+                nrow, ncol = int(a["nrow"]), int(a["ncol"])
+                data = _f(a.get("elevation"), None, np.zeros(nrow * ncol))
+                if data.size != nrow * ncol:
+                    raise ValueError(f"hfield {a.get('name')}: elevation has {data.size} values, expected nrow * ncol = {nrow * ncol}")
+                lo, hi = float(data.min()), float(data.max())
+                data = (data - lo) / (hi - lo) if hi > lo else np.zeros_like(data)
+                meshes["hfield_index"][a.get("name")] = len(meshes["hfields"])
+                meshes["hfields"].append(dict(name=a.get("name"), nrow=nrow, ncol=ncol, size=_f(a["size"], 4), data=data))
             for me in asset.findall("mesh"):
                 a = self.defaults.resolve("mesh", me, None)
                 path = os.path.join(self.basedir, self.meshdir, a["file"])
@@ -1084,7 +1106,13 @@ class Compiler:
         m.nsite, m.ncam, m.nlight, m.nmesh, m.npair, m.nexclude = nsite, ncam, nlight, len(meshes["list"]), npair, len(excludes)
         m.neq, m.ntendon, m.nwrap, m.nsensor, m.nnumeric, m.nmocap, m.nM = neq, ntendon, nwrap, nsensor, len(numerics), nmocap, nM
         m.nsensordata = nsensordata
-        m.nhfield, m.ntex, m.ntexdata, m.nkey = 0, 0, 0, 0
+        m.nhfield, m.ntex, m.ntexdata, m.nkey = len(meshes["hfields"]), 0, 0, 0
+        hfs = meshes["hfields"]
+        m.hfield_size = np.array([h["size"] for h in hfs], dtype=np.float64).reshape(len(hfs), 4)
+        m.hfield_nrow = np.array([h["nrow"] for h in hfs], dtype=np.int32)
+        m.hfield_ncol = np.array([h["ncol"] for h in hfs], dtype=np.int32)
+        m.hfield_adr = np.array(np.concatenate([[0], np.cumsum([h["nrow"] * h["ncol"] for h in hfs])[:-1]]) if hfs else [], dtype=np.int32)
+        m.hfield_data = np.concatenate([h["data"] for h in hfs]) if hfs else np.zeros(0)
         m.opt = opt
         m.qpos0 = arr(qpos0)
         m.qpos_spring = arr(qpos_spring)

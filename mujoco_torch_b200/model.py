@@ -25,7 +25,11 @@ _FN_TABLE = {
     (_G.SPHERE, _G.BOX): "SPHERE_CONVEX", (_G.SPHERE, _G.MESH): "SPHERE_CONVEX", (_G.CAPSULE, _G.CAPSULE): "CAPSULE_CAPSULE",
     (_G.CAPSULE, _G.BOX): "CAPSULE_CONVEX", (_G.CAPSULE, _G.MESH): "CAPSULE_CONVEX", (_G.BOX, _G.BOX): "CONVEX_CONVEX",
     (_G.BOX, _G.MESH): "CONVEX_CONVEX", (_G.MESH, _G.MESH): "CONVEX_CONVEX",
+    # height fields (reference collision_driver.py:111-114, collision_hfield.py)
+    (_G.HFIELD, _G.SPHERE): "HFIELD_SPHERE", (_G.HFIELD, _G.CAPSULE): "HFIELD_CAPSULE", (_G.HFIELD, _G.BOX): "HFIELD_CONVEX",
+    (_G.HFIELD, _G.MESH): "HFIELD_CONVEX",
 }
+HFIELD_MAX_PRISMS = 32   # sub-grid prisms one (pair, env) thread walks; larger objects / finer grids are refused at device_put
 # Solver live tile: room for LIVE_FRAC of the constraint rows, at least LIVE_MIN_ROWS.  Measured on the bench states the live
 # share is far below that (box stack: <= 112 of 336 rows for 99 % of the envs, Ant: <= 36 of 284); envs that need more take
 # the full-tile pass.  Models solved by half warps (nv <= 16) are occupancy-limited by the row vectors rather than by M / L, so
@@ -469,6 +473,29 @@ class Model:
         I["pair_fn"] = i32([fn_id[p["fn"]] for p in self.pairs])
         I["pair_g1"], I["pair_g2"] = i32([p["g1"] for p in self.pairs]), i32([p["g2"] for p in self.pairs])
         I["pair_slot"] = i32(self.pair_slot[: len(self.pairs)])
+        # height-field pairs (reference collision_driver._hfield_subgrid_size :318-329): the sub-grid of cells around the object,
+        # from its bounding radius and the grid pitch -- static; which cells it covers is decided per env in the kernel
+        nhf = int(getattr(mj, "nhfield", 0))
+        I["hf_nrow"], I["hf_ncol"], I["hf_adr"] = i32(getattr(mj, "hfield_nrow", [])), i32(getattr(mj, "hfield_ncol", [])), i32(getattr(mj, "hfield_adr", []))
+        pair_hf, pair_rb = [], []
+        for p_ in self.pairs:
+            if not p_["fn"].startswith("HFIELD"):
+                pair_hf += [-1, 0, 0]
+                pair_rb.append(0.0)
+                continue
+            hid = int(mj.geom_dataid[p_["g1"]])
+            hs, nrow, ncol = np.asarray(mj.hfield_size[hid], dtype=np.float64), int(mj.hfield_nrow[hid]), int(mj.hfield_ncol[hid])
+            rb = float(mj.geom_rbound[p_["g2"]])
+            xtick, ytick = 2.0 * hs[0] / (ncol - 1), 2.0 * hs[1] / (nrow - 1)
+            xb, yb = min(int(np.ceil(2 * rb / xtick)) + 1, ncol), min(int(np.ceil(2 * rb / ytick)) + 1, nrow)
+            if 2 * xb * yb > HFIELD_MAX_PRISMS:
+                raise NotImplementedError(f"hfield pair ({p_['g1']}, {p_['g2']}): sub-grid {xb} x {yb} needs {2 * xb * yb} prisms, more than {HFIELD_MAX_PRISMS}")
+            pair_hf += [hid, xb, yb]
+            # the radius that places the sub-grid around the object is NOT geom_rbound: hfield_sphere / hfield_convex use
+            # max(geom_size) (collision_hfield.py:355,381), hfield_capsule radius + half length (:368)
+            gs = np.asarray(mj.geom_size[p_["g2"]], dtype=np.float64)
+            pair_rb.append(float(gs[0] + gs[1]) if p_["fn"] == "HFIELD_CAPSULE" else float(gs.max()))
+        I["pair_hf"] = i32(pair_hf)
         gb = np.asarray(mj.geom_bodyid)
         I["con_body1"], I["con_body2"] = i32(gb[self.con["g1"]]) if len(self.con["g1"]) else i32([]), i32(gb[self.con["g2"]]) if len(self.con["g2"]) else i32([])
         I["con_dim"], I["con_efcadr"] = i32(self.con["dim"]), i32(self.con_efcadr)
@@ -565,6 +592,7 @@ class Model:
         F["sens_cutoff"] = f(mj.sensor_cutoff)
         F["cvx_vert"] = np.concatenate(vert_all) if vert_all else f([])
         F["cvx_norm"] = np.concatenate(norm_all) if norm_all else f([])
+        F["hf_size"], F["hf_data"], F["pair_rbound"] = f(getattr(mj, "hfield_size", [])), f(getattr(mj, "hfield_data", [])), f(pair_rb)
 
         # structurally non-zero entries of the packed lower triangle of M: (a, b) with dof b an ancestor-or-self of dof a
         # (support.make_m :50-80); a tendon armature couples arbitrary dofs, so then every entry counts

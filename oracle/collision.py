@@ -8,7 +8,7 @@ Each narrowphase returns (dist (B,n), pos (B,n,3), frame (B,n,3,3)).
 import torch
 
 from . import omath as M
-from .model import BOX, CAPSULE, MESH, PLANE, SPHERE
+from .model import BOX, CAPSULE, HFIELD, MESH, PLANE, SPHERE
 
 
 def _plane_sphere(n, ppos, spos, r):
@@ -83,6 +83,10 @@ def _fn(t):
     }
     if t in table:
         return table[t]
+    if t[0] == HFIELD:
+        from . import hfield
+
+        return hfield.hfield_pair
     from . import convex
 
     return {

@@ -110,6 +110,9 @@ CASES = [
     # max_contact_points = 6 of 19 candidate contacts: data-dependent contact selection, parameters and geom ids per env
     # (collision_driver.py:822-840); loose pile of capsules and a ball on the floor, two steps
     ("capsules_topk", "capsules_topk", {}, 32, -1.0, 2),
+    # height-field narrowphase: sphere, capsule and box scattered over a bumpy 9 x 11 terrain (drop -5 = tests/util.terrain_state);
+    # the reference walks the sub-grid in Python per env (collision_hfield.py), which is exactly how it is recorded here
+    ("terrain", "terrain", {}, 32, -5.0, 1),
 ]
 
 
@@ -124,7 +127,9 @@ def run_case(name, model, opt, B, drop, nsteps):
     lite = util.load_model(model, **{k: v for k, v in opt.items() if k != "fixed_iterations"})
     qpos, qvel, ctrl = util.seeded_state(lite, B, drop=drop)
     act = None
-    if drop < -3.5:
+    if drop < -4.5:
+        qpos, qvel, ctrl = util.terrain_state(lite, B)
+    elif drop < -3.5:
         qpos, qvel, ctrl, act = util.muscle_state(lite, B)
     elif drop < -2.5:
         qpos, qvel, ctrl, act = util.sink_state(lite, B)

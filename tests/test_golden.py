@@ -59,7 +59,8 @@ def _check(z, get, get_contact, label):
                 bad["contact." + k] = e
         # positions: an inactive slot of a convex (box / mesh) pair holds an arbitrary tie-broken manifold point -- skip those
         gtype = np.asarray(util.load_model(str(z["model"])).geom_type)
-        skip = (gtype[z["contact_geom2"].astype(np.int64)] >= 6) & (z["contact_dist"] - z["contact_includemargin"] >= 0)
+        manifold = (gtype[z["contact_geom2"].astype(np.int64)] >= 6) | (gtype[z["contact_geom1"].astype(np.int64)] == 1)   # convex / hfield pairs
+        skip = manifold & (z["contact_dist"] - z["contact_includemargin"] >= 0)
         pe = np.abs(np.asarray(get_contact("pos"), dtype=np.float64) - z["contact_pos"]).max(-1) / max(np.abs(z["contact_pos"]).max(), 1e-6)
         if np.where(skip, 0.0, pe).max() > TOL:
             bad["contact.pos"] = float(np.where(skip, 0.0, pe).max())

@@ -331,6 +331,7 @@ STATE_CASES = [
     ("sink", {}, "sink", 0.0), ("sink", {"cone": 1}, "sink", 0.0), ("sink", {"integrator": 3}, "sink", 0.0), ("sink", {"integrator": 1}, "sink", 0.0),
     ("convex", {}, "pile", 0.0), ("stack", {}, "stack", 0.0), ("cartpole", {}, "seed", 0.0),
     ("muscle", {}, "muscle", 0.0), ("muscle", {"integrator": 3}, "muscle", 0.0), ("capsules_topk", {}, "pile", 0.0),
+    ("terrain", {}, "terrain", 0.0),
 ]
 
 
@@ -349,6 +350,8 @@ def test_state_outputs_bit_identical_to_full(name, opt, kind, drop, dtype):
         qpos, qvel, ctrl, act = util.sink_state(mj, B)
     elif kind == "muscle":
         qpos, qvel, ctrl, act = util.muscle_state(mj, B)
+    elif kind == "terrain":
+        qpos, qvel, ctrl = util.terrain_state(mj, B)
     elif kind == "pile":
         qpos, qvel, ctrl = util.pile_state(mj, B)
     elif kind == "stack":

@@ -55,6 +55,8 @@ CASES = [
     ("muscle", {}, -4.0),
     ("muscle", {"integrator": 3}, -4.0),
     ("muscle", {"integrator": 1}, -4.0),
+    # drop -5: assets/xml/terrain.xml -- sphere, capsule and box on a height field
+    ("terrain", {}, -5.0),
     # convex narrowphase (drop -1: loose pile of free bodies, drop -2: the model's own stack, squeezed)
     ("convex", {}, -1.0),
     ("shapes", {}, -1.0),
@@ -125,6 +127,8 @@ def _compare(mj, B, dtype, tol, drop, label=""):
     act = None
     if drop >= 0:
         qpos, qvel, ctrl = util.seeded_state(mj, B, drop=drop)
+    elif drop < -4.5:
+        qpos, qvel, ctrl = util.terrain_state(mj, B)
     elif drop < -3.5:
         qpos, qvel, ctrl, act = util.muscle_state(mj, B)
     elif drop < -2.5:
@@ -232,7 +236,7 @@ def _compare(mj, B, dtype, tol, drop, label=""):
         round_pair = (gt[mo.contact["geom1"]] >= 2) & (gt[mo.contact["geom1"]] <= 3) & (gt[mo.contact["geom2"]] >= 2) & (gt[mo.contact["geom2"]] <= 3)
         degen = round_pair[None, :] & ((do.contact_dist.double() + rsum[None, :]).abs() < 1e-5)
         # slots of convex pairs that are inactive carry an arbitrary (tie-broken) manifold point: compare active ones only
-        convex_slot = gt[mo.contact["geom2"]] >= 6
+        convex_slot = (gt[mo.contact["geom2"]] >= 6) | (gt[mo.contact["geom1"]] == 1)   # height-field pairs select a manifold too
         pe = (dc.contact.pos.cpu().double() - do.contact_pos.double()).abs().amax(-1) / max(float(do.contact_pos.abs().max()), 1e-6)
         # f32: the closest-point formulas are ill-conditioned for (near-)parallel segments (1e-6 regulariser vs f32 rounding of
         # 1 - cos^2); a far-apart inactive pair may place its witness point anywhere along the segment -- it is never used

@@ -107,6 +107,23 @@ def muscle_state(mj, B, seed=21):
     return qpos, qvel, rng.uniform(-0.2, 1.2, size=(B, mj.nu)), rng.uniform(0.0, 1.0, size=(B, mj.na))
 
 
+def terrain_state(mj, B, seed=31):
+    """assets/xml/terrain.xml: free bodies scattered over the height field, at heights around its surface (some resting in it, some
+    above it), random orientations."""
+    rng = np.random.RandomState(seed)
+    qpos = np.tile(np.asarray(mj.qpos0), (B, 1))
+    for j in range(mj.njnt):
+        if int(mj.jnt_type[j]) != 0:
+            continue
+        a = int(mj.jnt_qposadr[j])
+        qpos[:, a] = rng.uniform(-0.9, 0.9, size=B)
+        qpos[:, a + 1] = rng.uniform(-0.7, 0.7, size=B)
+        qpos[:, a + 2] = rng.uniform(0.1, 0.45, size=B)
+        q = rng.randn(B, 4)
+        qpos[:, a + 3:a + 7] = q / np.linalg.norm(q, axis=1, keepdims=True)
+    return qpos, 0.3 * rng.randn(B, mj.nv), np.zeros((B, mj.nu))
+
+
 def run_oracle(mj, qpos, qvel, ctrl, dtype=torch.float64, nsteps=1, warm=None, act=None, fixed_iterations=False):
     from oracle import forward as of
     from oracle import model as om
