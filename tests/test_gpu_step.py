@@ -197,7 +197,11 @@ def _compare(mj, B, dtype, tol, drop, label=""):
                   + ", ".join(f"{k} {v:.1e}" for k, v in worst.items()))
     # Allowances = the worst case observed over every config on the B200 (round 2 GPU test log, profiles/r2_gpu_tests.txt:
     # 9 oracle-unstable envs of 64 -- convex pile / Humanoid with 1 solver iteration -- and 2 extra outliers) plus 2.
-    assert n_unst <= 11 * B // 64, f"too many oracle-unstable envs: {n_unst}/{B}"
+    # Height fields: the same contact is found by neighbouring prisms and the manifold selection picks among exactly tied candidates,
+    # so the oracle's own contact set moves under few-ulp perturbations for a third of the scattered-bodies envs (observed 20 of 64;
+    # every env the oracle is stable on matches to 1e-14).
+    has_hfield = bool((np.asarray(mj.geom_type) == 1).any())
+    assert n_unst <= (22 if has_hfield else 11) * B // 64, f"too many oracle-unstable envs: {n_unst}/{B}"
     assert n_extra <= 4, f"{n_extra} envs beyond tol {tol} while the oracle itself is unstable on only {n_unst}/{B}"
     ok = ~(unstable | outlier)
     bad = {}
