@@ -1000,7 +1000,7 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
 }
 
 template <typename T, int DPL, bool COMPACT, int G, bool TILE>
-__global__ void __launch_bounds__((sizeof(T) == 4 ? 512 : MJT_SOLVE_F64_THREADS), (sizeof(T) == 4 ? 2 : MJT_SOLVE_F64_MINB)) k_solve(const int* __restrict__ gfull, const int* __restrict__ gblob, int blob_words, MjtIn in,
+__global__ void __launch_bounds__((sizeof(T) == 4 ? 512 : MJT_SOLVE_F64_THREADS), (sizeof(T) == 4 ? (DPL == 1 ? 2 : 1) : MJT_SOLVE_F64_MINB)) k_solve(const int* __restrict__ gfull, const int* __restrict__ gblob, int blob_words, MjtIn in,
                                                T* __restrict__ out, T* __restrict__ pubbuf, int B, int mode, int only_flagged) {
   extern __shared__ __align__(16) int smem_blob[];
   __shared__ uint64_t bar;

@@ -127,7 +127,10 @@ extern "C" int mjt_model_create(const void* blob_host, size_t nbytes, int device
   const size_t sm_total = (size_t)prop.sharedMemPerMultiprocessor;
   // f64 kernel: MJT_SOLVE_F64_THREADS x MJT_SOLVE_F64_MINB threads fit the register file; f32 kernel: 2 x 512
   const int tmax = m->f64 ? MJT_SOLVE_F64_THREADS : 512;
-  const size_t tcap = (size_t)tmax * (m->f64 ? MJT_SOLVE_F64_MINB : 2);   // resident threads per SM
+  // resident threads per SM the kernels are compiled for (k_solve's __launch_bounds__): f64 one 512-thread CTA at 128 registers; f32
+  // two at 64 registers -- except the two-dofs-per-lane instantiation (nv > 32), whose tile fits one CTA per SM anyway and which
+  // therefore keeps 128 registers instead of spilling
+  const size_t tcap = (size_t)tmax * (m->f64 ? MJT_SOLVE_F64_MINB : (nv > G ? 1 : 2));
   const int estep = 32 / G, emax = tmax / G;
   const size_t max_smem = (size_t)m->max_smem;
   auto pick_envs = [&](size_t reg, const char* knob) {   // most resident envs per SM wins; ties go to the larger CTA
@@ -251,9 +254,11 @@ static int set_smem(const void* fn, size_t bytes) {
 // one forward pass (optionally followed by the in-kernel integrator) into `out`
 // Threads per CTA of the thread-per-env kernels: full-size CTAs once the batch fills the GPU twice over, otherwise
 // smaller CTAs so that a small batch still spreads over all SMs.
-static int env_threads(const mjtModel* m, int B) {
+static int env_threads(const mjtModel* m, int B, int grid_x = 1) {
+  // grid_x: CTAs that share one env block (k_collision: one per candidate pair, k_constraint: one per row-source group) -- they
+  // count towards filling the GPU, and every CTA stages the whole model blob, so such kernels keep full-size CTAs much longer
   int t = MJT_ENV_THREADS;
-  while (t > 32 && (B + t - 1) / t < 2 * m->sm_count) t >>= 1;
+  while (t > 32 && (long long)((B + t - 1) / t) * grid_x < 2 * m->sm_count) t >>= 1;
   return t;
 }
 
@@ -279,13 +284,14 @@ static int run_forward(const mjtModel* m, const MjtIn& in, T* pub, T* ws, int B,
   ++n;
   if (upto == UPTO_SMOOTH) return done();
   if (m->hv(H_npair_cand) > 0) {
-    dim3 grid(m->hv(H_npair_cand), gx < 65535 ? gx : 65535);
+    const int ct = env_threads(m, B, m->hv(H_npair_cand)), cgx = (B + ct - 1) / ct;
+    dim3 grid(m->hv(H_npair_cand), cgx < 65535 ? cgx : 65535);
     if (m->has_hfield) {
       if (set_smem<T>((const void*)k_collision<T, true>, blob_b)) return 1;
-      LAUNCH("k_collision", st, k_collision<T, true><<<grid, threads, blob_b, st>>>(m->d_blob, m->blob_words, ws, B));
+      LAUNCH("k_collision", st, k_collision<T, true><<<grid, ct, blob_b, st>>>(m->d_blob, m->blob_words, ws, B));
     } else {
       if (set_smem<T>((const void*)k_collision<T, false>, blob_b)) return 1;
-      LAUNCH("k_collision", st, k_collision<T, false><<<grid, threads, blob_b, st>>>(m->d_blob, m->blob_words, ws, B));
+      LAUNCH("k_collision", st, k_collision<T, false><<<grid, ct, blob_b, st>>>(m->d_blob, m->blob_words, ws, B));
     }
     ++n;
   }
@@ -299,8 +305,9 @@ static int run_forward(const mjtModel* m, const MjtIn& in, T* pub, T* ws, int B,
     if (set_smem<T>((const void*)k_constraint<T>, blob_b)) return 1;
     // grid.x CTAs share one env block and split its row sources; each CTA stages the model blob once, so a few sources
     // per CTA amortise the staging while still spreading an env block's rows over several SMs
-    dim3 grid(m->constraint_split, gx < 65535 ? gx : 65535);
-    LAUNCH("k_constraint", st, k_constraint<T><<<grid, threads, blob_b, st>>>(m->d_blob, m->blob_words, in, ws, B));
+    const int ct = env_threads(m, B, m->constraint_split), cgx = (B + ct - 1) / ct;
+    dim3 grid(m->constraint_split, cgx < 65535 ? cgx : 65535);
+    LAUNCH("k_constraint", st, k_constraint<T><<<grid, ct, blob_b, st>>>(m->d_blob, m->blob_words, in, ws, B));
     ++n;
   }
   if (upto == UPTO_CONSTRAINT) return done();

@@ -187,6 +187,7 @@ def _compare(mj, B, dtype, tol, drop, label=""):
         e_c = (dc.qfrc_constraint.cpu().double() - ref).abs().amax(1) / fscale
         e_o = (do.qfrc_constraint.double() - ref).abs().amax(1) / fscale
         outlier |= e_c > torch.maximum(torch.clamp(4 * e_o, min=10 * tol), 100 * spread)
+    has_hfield = bool((np.asarray(mj.geom_type) == 1).any())
     n_unst, n_extra = int(unstable.sum()), int((outlier & ~unstable).sum())
     # the exclusion counts and the worst error on the envs that ARE compared go to pytest's warnings summary (the GPU test log)
     import warnings
@@ -200,7 +201,6 @@ def _compare(mj, B, dtype, tol, drop, label=""):
     # Height fields: the same contact is found by neighbouring prisms and the manifold selection picks among exactly tied candidates,
     # so the oracle's own contact set moves under few-ulp perturbations for a third of the scattered-bodies envs (observed 20 of 64;
     # every env the oracle is stable on matches to 1e-14).
-    has_hfield = bool((np.asarray(mj.geom_type) == 1).any())
     assert n_unst <= (22 if has_hfield else 11) * B // 64, f"too many oracle-unstable envs: {n_unst}/{B}"
     assert n_extra <= 4, f"{n_extra} envs beyond tol {tol} while the oracle itself is unstable on only {n_unst}/{B}"
     ok = ~(unstable | outlier)
@@ -232,7 +232,10 @@ def _compare(mj, B, dtype, tol, drop, label=""):
         act_c = (dc.contact.dist.cpu() - dc.contact.includemargin.cpu()) < 0
         # active set: exact, except where the oracle itself sits within rounding of the boundary
         near = (do.contact_dist - inc).abs() < 32 * eps * (1 + do.contact_dist.abs())
-        assert torch.equal(act_o | near, act_c | near), "active contact set differs"
+        # height fields: which of the exactly tied prism contacts lands in which slot is decided by rounding, in the oracle as well --
+        # the slot-wise active set is compared on the envs whose oracle answer is stable under few-ulp perturbations
+        rows = ~unstable if has_hfield else torch.ones(B, dtype=torch.bool)
+        assert torch.equal((act_o | near)[rows], (act_c | near)[rows]), "active contact set differs"
         check("contact.dist", dc.contact.dist, do.contact_dist)
         gt = torch.as_tensor(np.asarray(mj.geom_type))
         gs = torch.as_tensor(np.asarray(mj.geom_size))[:, 0]
