@@ -805,8 +805,17 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
       compute_mgrad();
       search = neg(Mgrad);
     }
+    // Who reads what the LAST body's _update_constraint produces (forces, J^T f, cost, gradient)?  The termination test -- unless the
+    // iteration budget ends the loop anyway --, the efc_force / qfrc_constraint outputs (absent from the state layout) and the
+    // integrator's velocity-implicit re-solve.  When none applies (Humanoid: 1 iteration, Euler without eulerdamp, state layout) the
+    // step only needs qacc, which the line search has just updated: that last evaluation is skipped.
+    const int integ_ = m.h(H_integrator);
+    const bool resolve = (mode & MJT_MODE_KIND) == MJT_MODE_STEP &&
+                         ((integ_ == INT_EULER && !(flags & DSBL_EULERDAMP)) || integ_ == INT_IMPLICITFAST);
+    const bool need_final = resolve || m.P(P_qfrc_constraint) >= 0 || m.D(D_efc_force) >= 0;
     while (run) {
       linesearch();
+      if (!need_final && niter + 1 >= iterations) { ++niter; break; }
       const V prev_grad = grad, prev_Mgrad = Mgrad;
       update_constraint(true);
       compute_grad();
