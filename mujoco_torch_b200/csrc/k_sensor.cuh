@@ -6,7 +6,8 @@
 #include "mjt_common.cuh"
 #include "k_smooth.cuh"
 
-enum { SENS_ACCELEROMETER = 1, SENS_VELOCIMETER = 2, SENS_GYRO = 3, SENS_MAGNETOMETER = 6, SENS_RANGEFINDER = 7, SENS_JOINTPOS = 9,
+enum { SENS_FORCE = 4, SENS_TORQUE = 5, SENS_TENDONACTFRC = 17, SENS_SUBTREELINVEL = 36, SENS_SUBTREEANGMOM = 37,
+       SENS_ACCELEROMETER = 1, SENS_VELOCIMETER = 2, SENS_GYRO = 3, SENS_MAGNETOMETER = 6, SENS_RANGEFINDER = 7, SENS_JOINTPOS = 9,
        SENS_JOINTVEL = 10, SENS_TENDONPOS = 11, SENS_TENDONVEL = 12, SENS_ACTUATORPOS = 13, SENS_ACTUATORVEL = 14, SENS_ACTUATORFRC = 15,
        SENS_JOINTACTFRC = 16, SENS_BALLQUAT = 18, SENS_BALLANGVEL = 19, SENS_FRAMEPOS = 26, SENS_FRAMEQUAT = 27, SENS_FRAMEXAXIS = 28,
        SENS_FRAMEYAXIS = 29, SENS_FRAMEZAXIS = 30, SENS_FRAMELINVEL = 31, SENS_FRAMEANGVEL = 32, SENS_SUBTREECOM = 35, SENS_CLOCK = 45 };
@@ -190,6 +191,19 @@ __device__ void sensor_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<
     else if (type == SENS_ACTUATORVEL) { val[0] = d.get(m.D(D_actuator_velocity) + obj); dim = 1; }
     else if (type == SENS_ACTUATORFRC) { val[0] = d.get(m.D(D_actuator_force) + obj); dim = 1; }
     else if (type == SENS_JOINTACTFRC) { val[0] = d.get(m.D(D_qfrc_actuator) + m.I(I_jnt_dofadr)[obj]); dim = 1; }
+    else if (type == SENS_TENDONACTFRC) {   // sensor.py:422-424: total force of the actuators acting on the tendon
+      T f = 0;
+      for (int u = 0; u < m.h(H_nu); ++u)
+        if (m.I(I_act_trntype)[u] == TRN_TENDON && m.I(I_act_trnid)[u] == obj) f += d.get(m.D(D_actuator_force) + u);
+      val[0] = f;
+      dim = 1;
+    } else if (type == SENS_SUBTREELINVEL || type == SENS_SUBTREEANGMOM || type == SENS_FORCE || type == SENS_TORQUE) {
+      // The reference reads d.subtree_linvel / subtree_angmom / cfrc_int here (sensor.py:260-265, 394-416), but nothing in it
+      // ever computes them (smooth.subtree_vel and smooth.rne_postconstraint do not exist: the hasattr guards at :223-225 and
+      // :356-363 skip them), so they hold make_data's zeros and these sensors read zero.  Same output here.
+      val[0] = val[1] = val[2] = T(0);
+      dim = 3;
+    }
     else if (type == SENS_MAGNETOMETER || type == SENS_VELOCIMETER || type == SENS_GYRO || type == SENS_ACCELEROMETER) {
       T R[9];
       for (int k = 0; k < 9; ++k) R[k] = d.get(m.D(D_site_xmat) + 9 * obj + k);

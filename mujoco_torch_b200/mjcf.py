@@ -1054,6 +1054,11 @@ class Compiler:
                 "framelinvel": (SensorType.FRAMELINVEL, 3, Stage.VEL, DataType.REAL),
                 "frameangvel": (SensorType.FRAMEANGVEL, 3, Stage.VEL, DataType.REAL),
                 "subtreecom": (SensorType.SUBTREECOM, 3, Stage.POS, DataType.REAL),
+                "subtreelinvel": (SensorType.SUBTREELINVEL, 3, Stage.VEL, DataType.REAL),
+                "subtreeangmom": (SensorType.SUBTREEANGMOM, 3, Stage.VEL, DataType.REAL),
+                "framelinacc": (SensorType.FRAMELINACC, 3, Stage.ACC, DataType.REAL),
+                "frameangacc": (SensorType.FRAMEANGACC, 3, Stage.ACC, DataType.REAL),
+                "tendonactuatorfrc": (SensorType.TENDONACTFRC, 1, Stage.ACC, DataType.REAL),
                 "clock": (SensorType.CLOCK, 1, Stage.POS, DataType.REAL),
             }
             objtypes = {"body": ObjType.BODY, "xbody": ObjType.XBODY, "geom": ObjType.GEOM, "site": ObjType.SITE, "camera": ObjType.CAMERA}

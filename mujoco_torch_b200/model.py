@@ -37,12 +37,9 @@ HFIELD_MAX_PRISMS = 32   # sub-grid prisms one (pair, env) thread walks; larger 
 LIVE_FRAC, LIVE_MIN_ROWS = 0.33, 64
 LIVE_FRAC_HALFWARP, LIVE_MIN_ROWS_HALFWARP = 0.15, 48
 
-_SUPPORTED_SENSORS = {SensorType.TOUCH, SensorType.ACCELEROMETER, SensorType.VELOCIMETER, SensorType.GYRO, SensorType.MAGNETOMETER,
-                      SensorType.RANGEFINDER, SensorType.JOINTPOS, SensorType.JOINTVEL, SensorType.ACTUATORPOS,
-                      SensorType.ACTUATORVEL, SensorType.ACTUATORFRC, SensorType.JOINTACTFRC, SensorType.TENDONPOS,
-                      SensorType.TENDONVEL, SensorType.BALLQUAT, SensorType.BALLANGVEL, SensorType.FRAMEPOS, SensorType.FRAMEQUAT,
-                      SensorType.FRAMEXAXIS, SensorType.FRAMEYAXIS, SensorType.FRAMEZAXIS, SensorType.FRAMELINVEL,
-                      SensorType.FRAMEANGVEL, SensorType.SUBTREECOM, SensorType.CLOCK}
+# Sensor types the reference has no branch for (TOUCH, FRAMELINACC, FRAMEANGACC, ... ) are not an error there: its stage loops
+# `continue` past them and their sensordata slots keep the caller's values (sensor.py:425-426).  k_sensor does the same, so no
+# sensor type is refused here.
 
 
 class Option:
@@ -353,10 +350,6 @@ class Model:
         self.body_dofmask = mask
         self.maskwords = mw
         self._row_supports(S)
-
-        for t in np.asarray(mj.sensor_type):
-            if int(t) not in _SUPPORTED_SENSORS:
-                raise NotImplementedError(f"sensor type {int(t)} not implemented.")
 
     def _row_supports(self, S):
         """Static column support of every constraint source (the dofs its Jacobian rows can touch).

@@ -19,6 +19,7 @@ S_JOINTPOS, S_JOINTVEL, S_ACTUATORPOS, S_ACTUATORVEL, S_ACTUATORFRC, S_JOINTACTF
 S_TENDONPOS, S_TENDONVEL, S_BALLQUAT, S_BALLANGVEL = 11, 12, 18, 19
 S_FRAMEPOS, S_FRAMEQUAT, S_FRAMEXAXIS, S_FRAMEYAXIS, S_FRAMEZAXIS, S_FRAMELINVEL, S_FRAMEANGVEL = 26, 27, 28, 29, 30, 31, 32
 S_SUBTREECOM, S_CLOCK = 35, 45
+S_FORCE, S_TORQUE, S_TENDONACTFRC, S_SUBTREELINVEL, S_SUBTREEANGMOM = 4, 5, 17, 36, 37
 O_UNKNOWN, O_BODY, O_XBODY, O_GEOM, O_SITE, O_CAMERA = 0, 1, 2, 5, 6, 7
 STAGE_POS, STAGE_VEL, STAGE_ACC = 1, 2, 3
 
@@ -282,6 +283,10 @@ def sensor_vel(m, d):
                 a = int(mj.jnt_dofadr[o])
                 vals.append(d.qvel[:, a : a + 3])
             _write(d, adr, 3, _cutoff(torch.stack(vals, 1), cutoff, dtp))
+        elif t in (S_SUBTREELINVEL, S_SUBTREEANGMOM):
+            # sensor.py:260-265 reads d.subtree_linvel / d.subtree_angmom, which nothing in the reference computes (the
+            # smooth.subtree_vel call at :223-225 is behind a hasattr that is False): make_data's zeros (io.py:184-185)
+            _write(d, adr, 3, _cutoff(torch.zeros(d.qpos.shape[0], len(idx), 3, dtype=d.qpos.dtype), cutoff, dtp))
         elif t in (S_FRAMELINVEL, S_FRAMEANGVEL):   # sensor.py:265-325
             vals = []
             for k, o in zip(idx, objid):
@@ -331,4 +336,14 @@ def sensor_acc(m, d):
         elif t == S_JOINTACTFRC:
             v = d.qfrc_actuator[:, torch.as_tensor(mj.jnt_dofadr[objid], dtype=torch.long)]
             _write(d, adr, 1, _cutoff(v, cutoff, dtp)[:, :, None])
+        elif t in (S_FORCE, S_TORQUE):
+            # sensor.py:394-416 rotates d.cfrc_int, which stays at make_data's zeros (io.py:182): there is no
+            # smooth.rne_postconstraint behind the hasattr at :362-363
+            _write(d, adr, 3, _cutoff(torch.zeros(d.qpos.shape[0], len(idx), 3, dtype=d.qpos.dtype), cutoff, dtp))
+        elif t == S_TENDONACTFRC:   # sensor.py:421-423, mask built in device.py:572-579
+            trn, tid = np.asarray(mj.actuator_trntype), np.asarray(mj.actuator_trnid)[:, 0]
+            mask = torch.as_tensor(np.stack([(trn == 3) & (tid == o) for o in objid]), dtype=d.actuator_force.dtype)
+            v = d.actuator_force @ mask.T
+            _write(d, adr, 1, _cutoff(v, cutoff, dtp)[:, :, None])
+        # every other type (TOUCH, FRAMELINACC, FRAMEANGACC, ...): `continue` at sensor.py:425-426, slots untouched
     return d

@@ -36,7 +36,7 @@ m.save_npz(os.path.join(OUT, "ant_zoo.npz"))
 print(f"ant_zoo: nq={m.nq} nv={m.nv} nu={m.nu} nbody={m.nbody} ngeom={m.ngeom}")
 
 # scenes authored for this repo (assets/xml)
-for name in ("shapes", "stack", "equality_bodies", "sink", "muscle", "capsules_topk", "terrain"):
+for name in ("shapes", "stack", "equality_bodies", "sink", "muscle", "capsules_topk", "terrain", "sensors_extra"):
     m = mjcf.from_xml_path(os.path.join(ROOT, "assets", "xml", name + ".xml"))
     m.save_npz(os.path.join(OUT, name + ".npz"))
     print(f"{name}: nq={m.nq} nv={m.nv} nu={m.nu} nbody={m.nbody} ngeom={m.ngeom}")

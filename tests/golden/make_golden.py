@@ -113,6 +113,9 @@ CASES = [
     # height-field narrowphase: sphere, capsule and box scattered over a bumpy 9 x 11 terrain (drop -5 = tests/util.terrain_state);
     # the reference walks the sub-grid in Python per env (collision_hfield.py), which is exactly how it is recorded here
     ("terrain", "terrain", {}, 32, -5.0, 1),
+    # sensors the reference accepts without feeding them: force / torque / subtreelinvel / subtreeangmom read make_data's zeros,
+    # touch / framelinacc / frameangacc have no branch and keep their slots, tendonactuatorfrc is computed (sensor.py:356-426)
+    ("sensors_extra", "sensors_extra", {}, 32, 0.5, 2),
 ]
 
 

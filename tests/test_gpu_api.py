@@ -511,6 +511,32 @@ def test_device_put_data_struct_steps_like_make_data():
         assert torch.equal(getattr(out, k), getattr(ref, k)[1]), k
 
 
+@pytest.mark.parametrize("outputs", ["full", "state"])
+def test_sensor_slots_without_a_reference_branch_keep_the_callers_values(outputs):
+    """reference sensor.py:425-426: a sensor type with no branch (touch, framelinacc, frameangacc) is skipped and its sensordata
+    slots pass through the step unchanged; force / torque / subtreelinvel / subtreeangmom overwrite theirs with zeros."""
+    from oracle import forward as of
+    from oracle import model as om
+
+    mt, mj, mx, d = _batch("sensors_extra", B=16, drop=0.5)
+    seed = torch.arange(1, mj.nsensordata + 1, dtype=torch.float64, device="cuda:0").expand(16, -1).contiguous()
+    out = mt.step(mx, d.replace(sensordata=seed), outputs=outputs)
+    m = om.OModel(mj, torch.float64)
+    od = of.make_data(m, 16)
+    od.qpos, od.qvel, od.ctrl, od.sensordata = d.qpos.cpu(), d.qvel.cpu(), d.ctrl.cpu(), seed.cpu()
+    od = of.step(m, od)
+    assert util.rel_err(out.sensordata, od.sensordata) < 1e-9
+    names = ("f_wrist", "cable_frc", "base_linvel", "t_wrist", "imu_linacc", "idle_frc", "link1_angmom", "pad_touch", "imu_angacc",
+             "imu_acc", "pull_a_frc", "imu_gyro")      # assets/xml/sensors_extra.xml, in order
+    by_name = {n: (int(a), int(dm)) for n, a, dm in zip(names, mj.sensor_adr, mj.sensor_dim)}
+    for name in ("imu_linacc", "pad_touch", "imu_angacc"):
+        a, dm = by_name[name]
+        assert torch.equal(out.sensordata[:, a:a + dm], seed[:, a:a + dm]), name
+    for name in ("f_wrist", "t_wrist", "base_linvel", "link1_angmom"):
+        a, dm = by_name[name]
+        assert float(out.sensordata[:, a:a + dm].abs().max()) == 0.0, name
+
+
 @pytest.mark.parametrize("name", ["humanoid", "ant", "halfcheetah", "hopper", "walker2d", "cartpole"])
 def test_env_layer_fused_epilogue_matches_the_reference_formulas(name):
     """zoo.BatchedEnv (reference mujoco_torch/zoo: base.py `_step` :300-340 + the per-env classes): FRAME_SKIP state-only physics

@@ -57,6 +57,9 @@ CASES = [
     ("muscle", {"integrator": 1}, -4.0),
     # drop -5: assets/xml/terrain.xml -- sphere, capsule and box on a height field
     ("terrain", {}, -5.0),
+    # sensors the reference accepts without feeding (zeros / untouched slots) and tendonactuatorfrc
+    ("sensors_extra", {}, 0.5),
+    ("sensors_extra", {"integrator": 1}, 0.5),
     # convex narrowphase (drop -1: loose pile of free bodies, drop -2: the model's own stack, squeezed)
     ("convex", {}, -1.0),
     ("shapes", {}, -1.0),
