@@ -41,7 +41,8 @@ import torch  # noqa: E402
 # reference README numbers, single H200, float64, torch.compile(vmap) tuned, XML-default options
 L2_BYTES = 126 * 1000 * 1000   # B200 L2; batches whose per-step working set is smaller get a flush between timed steps
 PUBLISHED = {("humanoid", "f64", 65536): 2333178.0, ("humanoid", "f64", 131072): 2490457.0, ("humanoid", "f64", 32768): 2054194.0,
-             ("humanoid", "f64", 4096): 750288.0, ("humanoid", "f64", 1024): 202922.0,
+             ("humanoid", "f64", 4096): 750288.0, ("humanoid", "f64", 1024): 202922.0, ("humanoid", "f64", 128): 26560.0,
+             ("humanoid", "f64", 1): 232.0,
              ("halfcheetah", "f64", 4096): 745732.0, ("halfcheetah", "f64", 32768): 3584003.0, ("halfcheetah", "f64", 65536): 4122131.0,
              ("halfcheetah", "f64", 131072): 4479824.0, ("ant", "f64", 32768): 981050.0, ("ant", "f64", 65536): 1341747.0,
              ("ant", "f64", 131072): 1638131.0, ("walker2d", "f64", 32768): 537248.0, ("hopper", "f64", 131072): 4893648.0}
@@ -236,6 +237,8 @@ def main():
                          "on by default when the job has more than one rank")
     ap.add_argument("--no-gather-obs", action="store_true")
     ap.add_argument("--no-other-mode", action="store_true", help="skip the second timed loop with the other --outputs mode")
+    ap.add_argument("--graph", action="store_true",
+                    help="time the rollout through mujoco_torch_b200.GraphedStep (one CUDA-graph replay per step) instead of step() calls")
     ap.add_argument("--no-variants", action="store_true", help="skip the f32 / ImplicitFast variants of the Humanoid workload")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -295,6 +298,26 @@ def main():
     def rollout(d, steps, outputs, gather=None, zeros_b=None, fixed=False):
         """`steps` steps from Data `d` with the resident ctrl sequence; returns (device ms between the two events, last Data)."""
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if args.graph and outputs == args.outputs and gather is None and not fixed:
+            graphed.reset(d)
+            barrier()
+            if l2_flush is not None:
+                total = 0.0
+                for i in range(steps):
+                    l2_flush.add_(1)
+                    ev0.record()
+                    d = graphed(ctrls[i % 4])
+                    ev1.record()
+                    ev1.synchronize()
+                    total += ev0.elapsed_time(ev1)
+                barrier()
+                return total, d
+            ev0.record()
+            for i in range(steps):
+                d = graphed(ctrls[i % 4])
+            ev1.record()
+            barrier()
+            return ev0.elapsed_time(ev1), d
         barrier()
         if l2_flush is not None:
             # working set smaller than L2: every step is timed on its own, with a write larger than L2 between the brackets
@@ -324,6 +347,7 @@ def main():
         barrier()
         return ev0.elapsed_time(ev1), d
 
+    graphed = mt.GraphedStep(mx, d0, 1, outputs=args.outputs) if args.graph else None
     # ---- device-resident throughput (the headline): W untimed warm-up steps, then exactly K timed steps
     d = d0
     for i in range(args.warmup):
@@ -519,7 +543,8 @@ def main():
         "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": (value / pub) if pub else None, "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": workload_name(args, mj), "batch_per_gpu": B, "parallelism": f"dp{world} (envs sharded, no collective)",
+        "config": {"workload": workload_name(args, mj), "batch_per_gpu": B,
+                   "call": "GraphedStep: one CUDA-graph replay per step (same kernels as step())" if args.graph else "step() per step", "parallelism": f"dp{world} (envs sharded, no collective)",
                    "outputs": ("state: every step returns qpos, qvel, act, time, qacc, qacc_warmstart, act_dot, sensordata (bit-identical to the "
                                "full-Data step, tests/test_gpu_api.py); the full-Data number is in other_output_mode") if args.outputs == "state"
                    else "full: every field of Data materialised each step, like the reference",

@@ -15,6 +15,7 @@ from .api import (  # noqa: F401
 )
 from .data import Contact, Data  # noqa: F401
 from .devget import device_get_into  # noqa: F401
+from .graph import GraphedStep  # noqa: F401
 from .hostio import HostPipeline  # noqa: F401
 from .mjmodel import (  # noqa: F401
     BiasType, ConeType, DisableBit, DynType, EnableBit, EqType, GainType, GeomType, IntegratorType, JacobianType, JointType,

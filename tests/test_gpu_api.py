@@ -511,6 +511,39 @@ def test_device_put_data_struct_steps_like_make_data():
         assert torch.equal(getattr(out, k), getattr(ref, k)[1]), k
 
 
+@pytest.mark.parametrize("name,outputs,nsteps", [("humanoid", "state", 1), ("humanoid", "state", 5), ("humanoid", "full", 2),
+                                                 ("sink", "state", 3), ("walker2d", "state", 2)])
+def test_graphed_step_equals_the_step_loop(name, outputs, nsteps):
+    """GraphedStep replays the captured step() calls: bit-identical to the Python loop, over several replays, with ctrl changing
+    between replays and held over the nsteps of one replay (frame skip)."""
+    mt, mj, mx, d = _batch(name, B=48, drop=0.4 if name != "sink" else 0.0)
+    if name == "walker2d":
+        mj.opt.integrator = 1   # RK4: 20 launches per step
+        mx = mt.device_put(mj, dtype=torch.float64).to("cuda:0")
+    g = mt.GraphedStep(mx, d, nsteps, outputs=outputs)
+    gen = torch.Generator(device="cuda:0").manual_seed(5)
+    ref = d
+    for t in range(4):
+        ctrl = torch.rand(48, mj.nu, generator=gen, device="cuda:0", dtype=torch.float64) * 2 - 1
+        out = g(ctrl)
+        ref = ref.replace(ctrl=ctrl)
+        for _ in range(nsteps):
+            ref = mt.step(mx, ref, outputs=outputs)
+        for k in ("qpos", "qvel", "act", "time", "qacc", "qacc_warmstart", "sensordata"):
+            assert torch.equal(getattr(out, k), getattr(ref, k)), (k, t)
+        for k in ("qpos", "qvel", "qacc_warmstart"):
+            assert torch.equal(getattr(g.state, k), getattr(ref, k)), (k, t)
+    if outputs == "full":
+        assert torch.equal(out.efc_J, ref.efc_J) and torch.equal(out.contact.dist, ref.contact.dist)
+    # reset() loads a new state into the static buffers; the graph is reused
+    g.reset(d)
+    out = g(d.ctrl)
+    ref = d
+    for _ in range(nsteps):
+        ref = mt.step(mx, ref, outputs=outputs)
+    assert torch.equal(out.qpos, ref.qpos) and torch.equal(out.qacc, ref.qacc)
+
+
 @pytest.mark.parametrize("outputs", ["full", "state"])
 def test_sensor_slots_without_a_reference_branch_keep_the_callers_values(outputs):
     """reference sensor.py:425-426: a sensor type with no branch (touch, framelinacc, frameangacc) is skipped and its sensordata
