@@ -164,6 +164,12 @@ class _TensorBag:
             if isinstance(v, _TensorBag):
                 v[idx] = o
             else:
+                # model-constant fields come back from step() as stride-0 expansions of one per-model tensor (Contact.friction,
+                # geom ids ...): a write must neither alias across envs nor reach the other Data objects, so such a field is
+                # materialised on its first write (the reference's tensorclass owns all of its memory, types.py:1091)
+                if any(st == 0 and sz > 1 for st, sz in zip(v.stride(), v.shape)):
+                    v = v.clone(memory_format=torch.contiguous_format)
+                    self._fields[k] = v
                 v[idx] = o
 
     def __len__(self):

@@ -108,6 +108,23 @@ def test_data_container_api():
     assert f32.qpos.dtype == torch.float32 and f32.contact.geom1.dtype == torch.int64
 
 
+def test_masked_assignment_materialises_expanded_fields():
+    """The RL reset pattern `d[mask] = fresh` on a Data whose fields are stride-0 expansions (an un-cloned expand(); the
+    model-constant Contact fields of every step output): the write lands in the selected envs only and never in the shared source."""
+    mx = mt.device_put(util.load_model("humanoid"), dtype=torch.float64)
+    one = mt.make_data(mx)
+    b = one.expand(4)
+    assert b.qvel.stride()[0] == 0
+    fresh = mt.make_data(mx).expand(2).clone().replace(qvel=torch.full((2, 27), 3.0, dtype=torch.float64))
+    fresh.contact.friction.fill_(0.25)
+    b[torch.tensor([False, True, False, True])] = fresh
+    assert b.qvel[:, 0].tolist() == [0.0, 3.0, 0.0, 3.0] and float(one.qvel.abs().max()) == 0.0
+    assert float(b.contact.friction[1].min()) == 0.25 and float(b.contact.friction[0].max()) != 0.25
+    assert float(one.contact.friction.max()) != 0.25
+    b[0:2] = fresh
+    assert b.qvel[:, 0].tolist() == [3.0, 3.0, 0.0, 3.0]
+
+
 def test_data_is_a_pytree_for_vmap():
     mx = mt.device_put(util.load_model("cartpole"), dtype=torch.float64)
     d = mt.make_data(mx).expand(5).clone()
