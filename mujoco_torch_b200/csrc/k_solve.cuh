@@ -70,7 +70,7 @@ template <int G> __device__ __forceinline__ bool unib(bool v) { return G == 32 ?
 #define MJT_CHOL_INLINE __forceinline__
 #endif
 template <typename T, int G>
-__device__ MJT_CHOL_INLINE void cholesky_rows_fn(T* A, T* di, int n, int lane, unsigned gm) {
+__device__ MJT_CHOL_INLINE void cholesky_rows_fn(T* A, T* di, int n, int lane, unsigned gm, const T* idle) {
   const bool big = n > 16;
   T r[G];
   const bool mine = lane < n;
@@ -79,9 +79,11 @@ __device__ MJT_CHOL_INLINE void cholesky_rows_fn(T* A, T* di, int n, int lane, u
   for (int j = 0; j < G; ++j) {
     if (j < n) {
       const T* rowj = A + tri(j);
-      // unconditional load (a conditional one compiles to a branch): lanes above the diagonal or beyond n read some other
-      // in-bounds word of the tile; whatever they compute is discarded by the selects below and never stored
-      T acc = rowi[j], acc2 = T(0);
+      // unconditional load (a conditional one compiles to a branch): lanes above the diagonal or beyond n read `idle`, a word of
+      // the env's region that nobody writes during the factorisation (racecheck-clean); whatever they compute from it is
+      // discarded by the selects below and never stored
+      const T* src = (mine && lane >= j) ? rowi + j : idle;
+      T acc = *src, acc2 = T(0);
 #pragma unroll
       for (int k = 0; k + 1 < j; k += 2) {
         acc -= r[k] * rowj[k];
@@ -342,7 +344,7 @@ struct SolveCtx {
     }
     return out;
   }
-  __device__ __forceinline__ void cholesky_rows(T* A) const { cholesky_rows_fn<T, G>(A, dinv(), nv, lane, gmask()); }
+  __device__ __forceinline__ void cholesky_rows(T* A) const { cholesky_rows_fn<T, G>(A, dinv(), nv, lane, gmask(), xs()); }
   __device__ __forceinline__ void cholesky(T* A) const {
     if (DPL == 1 && MJT_CHOL_ROWS) { cholesky_rows(A); return; }
     const int n = nv;
