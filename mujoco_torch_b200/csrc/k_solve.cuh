@@ -451,7 +451,7 @@ struct SolveCtx {
     for (int p = lane; p < L.nP; p += G) H[p] = M0[p];
     __syncwarp(gmask());
     // sources that touch a single dof (joint limits, dof friction): one lane per dof adds their diagonal terms
-    for (int i = lane; i < nv; i += G) {
+    for (int i = lane; i < (m.h(H_nsrc1) ? nv : 0); i += G) {
       T acc = T(0);
       for (int q = dof_sadr[i], qe = dof_sadr[i + 1]; q < qe; ++q) {
         const int sidx = dof_sent[q] & 0xffff;
@@ -468,11 +468,26 @@ struct SolveCtx {
     }
     __syncwarp(gmask());
     const int nsrc = m.h(H_nsrc);
+    // Multi-dof sources, in ascending order.  A full warp per env picks the candidates 32 at a time (one lane per source tests
+    // "more than one dof, and live", one ballot) instead of walking every source through a dependent chain of table loads: in a
+    // contact-rich scene most of the candidate contacts are dead in any given step.
+    unsigned pick = 0;
     for (int sidx = 0; sidx < nsrc; ++sidx) {
-      if (src_nsup[sidx] == 1) continue;
+      if (G == 32 && compact) {   // (few-row models keep the plain loop: measured 2 % faster on Humanoid)
+        if ((sidx & 31) == 0) {
+          const int mine_s = sidx + lane;
+          const bool ok = mine_s < nsrc && src_nsup[mine_s] != 1 && (!compact || spos()[mine_s] >= 0);
+          pick = __ballot_sync(0xffffffffu, ok);
+        }
+        const unsigned rest = pick >> (sidx & 31);
+        if (!rest) { sidx |= 31; continue; }          // nothing left in this group of 32
+        sidx += __ffs(rest) - 1;                        // next picked source (warp-uniform: pick is a ballot)
+      } else {
+        if (src_nsup[sidx] == 1) continue;
+      }
       const int r0 = src_row[sidx], nr = src_nrows[sidx];
       const int cs = compact ? spos()[sidx] : r0;
-      if (cs < 0) continue;
+      if (!(G == 32 && compact) && cs < 0) continue;
       unsigned act = 0;
       if (nr <= 32) act = active_bits(cs, nr);
       else for (int e = 0; e < nr; ++e) act |= slot_active(cs + e) ? 1u : 0u;

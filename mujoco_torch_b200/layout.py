@@ -22,7 +22,7 @@ disableflags solver cone integrator iterations ls_iterations
 data_words has_gravcomp has_fluid nv_pad nlim_sh nlim_ball nfric_dof nfric_ten nlim_ten
 ne_connect ne_weld ne_joint maskwords nsens_pos nsens_vel nsens_acc
 nconvex nrfgeom jc_words solve_blob_words live_rcap live_jcap
-layout_state pub_words n_mnz topk ncand
+layout_state pub_words n_mnz topk ncand nsrc1
 """.split()
 
 # ---- int arrays ---------------------------------------------------------------------------

@@ -679,7 +679,8 @@ class Model:
                  nfric_dof=cnt("FRIC_DOF"), nfric_ten=cnt("FRIC_TEN"), nlim_ten=cnt("LIM_TEN"), ne_connect=cnt("EQ_CONNECT"),
                  ne_weld=cnt("EQ_WELD"), ne_joint=cnt("EQ_JOINT"), maskwords=self.maskwords, nsens_pos=int((st == 1).sum()),
                  nsens_vel=int((st == 2).sum()), nsens_acc=int((st == 3).sum()), nconvex=len(cv), nrfgeom=len(rf), jc_words=self.sup["jc_words"],
-                 live_rcap=self.live_caps[0], live_jcap=self.live_caps[1], n_mnz=len(m_nz), topk=self.topk, ncand=self.ncand)
+                 live_rcap=self.live_caps[0], live_jcap=self.live_caps[1], n_mnz=len(m_nz), topk=self.topk, ncand=self.ncand,
+                 nsrc1=sum(1 for n in self.sup["src_nsup"] if n == 1))
         nH, nI, nF, nD, nPf = len(L.H_SCALARS), len(L.I_ARRAYS), len(L.F_ARRAYS), len(L.D_FIELDS), len(L.P_FIELDS)
         def assemble(keep=None, extra=None, state=False):
             """One blob; with ``keep`` only the named arrays carry data (the others get length 0)."""
