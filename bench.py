@@ -197,7 +197,7 @@ def run_reference(args):
     v = float(np.median(rates))
     sample = f"oracle port, B={B} envs x 2 steps per sample, {len(rates)} samples, {cores} torch threads, float64"
     print(json.dumps({
-        "impl": "reference", "metric": "env-steps/sec", "value": v, "unit": "env-steps/s", "n_gpus": 0, "steps": args.steps,
+        "impl": "reference", "metric": "env-steps/sec", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus, "gpus_used": 0, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": float(np.median(per)) * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args, mj), "batch": B},
