@@ -377,9 +377,12 @@ def main():
     tile_overflow = None
     if args.outputs == "full" and getattr(mx, "live_caps", (0, 0))[0] > 0 and os.environ.get("MJT_LIVE_TILE", "1") != "0":
         try:
-            root = dd.qpos._base if dd.qpos._base is not None else dd.qpos
+            # the full layout is one (data_words, B) env-minor buffer that starts with qpos; RK4 runs its forward passes in
+            # stage buffers, so the flag of the last pass is only in the step's output for the one-pass integrators
+            if int(mj.opt.integrator) == 1 or dd.qpos.stride() != (1, B):
+                raise ValueError("no flag in this output")
             off = mx.field_off["scr_ovf"]
-            flags = root[:, off] if (root.dim() == 2 and root.shape[0] == B and root.shape[1] == mx.data_words) else root.reshape(-1)[off * B:(off + 1) * B]
+            flags = torch.as_strided(dd.qpos, (B,), (1,), dd.qpos.storage_offset() + off * B)
             tile_overflow = float((flags != 0).double().mean())
         except Exception:  # noqa: BLE001
             tile_overflow = None
