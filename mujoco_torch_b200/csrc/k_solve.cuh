@@ -642,17 +642,20 @@ __device__ void solve_env(const ModelView<T>& m, const MjtIn& in, const EnvBuf<T
       for (int k = 0; k < DPL; ++k) grad.v[k] = Ma.v[k] - qfrc_smooth.v[k] - qfrc_con.v[k];
     };
     // reference _update_gradient :359-376 (the M^-1 / H^-1 application)
-    bool lm_is_m = true;   // Lm holds chol(M) (from the factor_m prologue) until a Hessian is factorised over it
+    // The Hessian M + sum over active rows of D_r J_r^T J_r is a function of the active set alone (D and J are fixed during the
+    // solve), so its factor in Lm stays valid for as long as the set does not change: lane k remembers word k of the mask the factor
+    // was built from.  Lm starts as chol(M) from the factor_m prologue, i.e. the factor of the empty set.  Once the active set has
+    // settled -- typically after a few Newton iterations of a resting contact scene -- the assembly and the factorisation are skipped.
+    unsigned fmask = 0;
+    const bool track = c.L.nchunk <= G;   // one mask word per lane; larger tiles always refactorise
     auto compute_mgrad = [&]() {
       if (newton) {
-        unsigned any = 0;
-        for (int ch = 0; (ch * G) < nlive; ++ch) any |= c.amask()[ch];
-        any = (unsigned)uni<G>((int)any);
-        // no active row: H = M exactly, and chol(M) is already in Lm -- skip the assembly and the factorisation
-        if (any || !lm_is_m) {
+        const unsigned cur = lane < c.L.nchunk && (lane * G) < nlive ? c.amask()[lane] : 0u;
+        const bool changed = !track || group_sum<int, G>(cur != fmask ? 1 : 0, gm) != 0;
+        if (unib<G>(changed)) {
           c.hessian(D);
           c.cholesky(Lm);
-          lm_is_m = !any;
+          fmask = cur;
         }
       }
       Mgrad = c.cho_solve(Lm, grad);  // CG: Lm still holds chol(M)
