@@ -408,26 +408,41 @@ struct SolveCtx {
       x.v[0] = xv;
       return x;
     } else {
-    for (int i = 0; i < n; ++i) {
-      const T xi = vec_bcast<T, G>(x, i, gmask()) * di[i];
-#pragma unroll
-      for (int k = 0; k < DPL; ++k) {
-        const int j = lane + G * k;
-        if (j == i) x.v[k] = xi;
-        else if (j > i && j < n) x.v[k] -= Lm[tri(j) + i] * xi;
+      // Two dofs per lane (j = lane and lane + G): the same unscaled-owner scheme, with the sweep split at i = G so that the
+      // broadcasting slot is known at compile time.  Step i costs a multiply, a shuffle and one predicated load + FMA per slot.
+      static_assert(DPL == 2, "cho_solve handles one or two dofs per lane");
+      const bool m0 = lane < n, m1 = lane + G < n;
+      const T d0 = m0 ? di[lane] : T(0), d1 = m1 ? di[lane + G] : T(0);
+      T x0 = x.v[0], x1 = x.v[1];
+      const T* row0 = Lm + tri(m0 ? lane : 0);
+      const T* row1 = Lm + tri(m1 ? lane + G : 0);
+      const int nlo = n < G ? n : G;
+#pragma unroll 4
+      for (int i = 0; i < nlo; ++i) {            // forward, pivots in slot 0
+        const T yi = __shfl_sync(gmask(), x0 * d0, i, G);
+        if (m0 && lane > i) x0 -= row0[i] * yi;
+        if (m1) x1 -= row1[i] * yi;
       }
-    }
-    for (int i = n - 1; i >= 0; --i) {
-      const T xi = vec_bcast<T, G>(x, i, gmask()) * di[i];
-      const T* rowi = Lm + tri(i);
-#pragma unroll
-      for (int k = 0; k < DPL; ++k) {
-        const int j = lane + G * k;
-        if (j == i) x.v[k] = xi;
-        else if (j < i) x.v[k] -= rowi[j] * xi;
+      for (int i = G; i < n; ++i) {               // forward, pivots in slot 1
+        const T yi = __shfl_sync(gmask(), x1 * d1, i - G, G);
+        if (m1 && lane + G > i) x1 -= row1[i] * yi;
       }
-    }
-    return x;
+      x0 *= d0;
+      x1 *= d1;
+      for (int i = n - 1; i >= G; --i) {          // backward, pivots in slot 1
+        const T zi = __shfl_sync(gmask(), x1 * d1, i - G, G);
+        const T* rowi = Lm + tri(i);
+        if (m0) x0 -= rowi[lane] * zi;
+        if (lane + G < i) x1 -= rowi[lane + G] * zi;
+      }
+#pragma unroll 4
+      for (int i = nlo - 1; i >= 0; --i) {        // backward, pivots in slot 0
+        const T zi = __shfl_sync(gmask(), x0 * d0, i, G);
+        if (lane < i) x0 -= Lm[tri(i) + lane] * zi;
+      }
+      x.v[0] = x0 * d0;
+      x.v[1] = x1 * d1;
+      return x;
     }
   }
   // bits k0 .. k0+nr-1 (nr <= 32) of the active-slot mask (one mask word per G slots)
