@@ -42,10 +42,10 @@ class GraphedStep:
             raise TypeError("first argument must be a mujoco_torch_b200 Model (see device_put)")
         if d.qpos.dim() != 2:
             raise ValueError("GraphedStep needs a Data with one batch dimension")
-        if not d.qpos.is_cuda:
-            raise RuntimeError("GraphedStep is CUDA-only (no CPU fallback exists)")
         if nsteps < 1:
             raise ValueError("nsteps must be >= 1")
+        if not d.qpos.is_cuda:
+            raise RuntimeError("GraphedStep is CUDA-only (no CPU fallback exists)")
         self.m, self.nsteps, self.outputs, self.fixed = m, int(nsteps), outputs, bool(fixed_iterations)
         dev, B = d.qpos.device, d.qpos.shape[0]
         sizes = [int(np.prod(m.field_shape[k])) if m.field_shape[k] else 1 for k in _CARRIED]

@@ -108,6 +108,20 @@ def test_data_container_api():
     assert f32.qpos.dtype == torch.float32 and f32.contact.geom1.dtype == torch.int64
 
 
+def test_graphed_step_refuses_what_it_cannot_capture():
+    """GraphedStep is CUDA-only like step(): wrong model type, unbatched or CPU Data and nsteps < 1 fail at construction."""
+    mx = mt.device_put(util.load_model("cartpole"), dtype=torch.float64)
+    d = mt.make_data(mx).expand(4).clone()
+    with pytest.raises(TypeError):
+        mt.GraphedStep(object(), d)
+    with pytest.raises(ValueError):
+        mt.GraphedStep(mx, mt.make_data(mx))
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        mt.GraphedStep(mx, d)
+    with pytest.raises(ValueError):
+        mt.GraphedStep(mx, d, 0)
+
+
 def test_masked_assignment_materialises_expanded_fields():
     """The RL reset pattern `d[mask] = fresh` on a Data whose fields are stride-0 expansions (an un-cloned expand(); the
     model-constant Contact fields of every step output): the write lands in the selected envs only and never in the shared source."""
