@@ -116,6 +116,19 @@ CASES = [
     # sensors the reference accepts without feeding them: force / torque / subtreelinvel / subtreeangmom read make_data's zeros,
     # touch / framelinacc / frameangacc have no branch and keep their slots, tendonactuatorfrc is computed (sensor.py:356-426)
     ("sensors_extra", "sensors_extra", {}, 32, 0.5, 2),
+    # mjtDisableBit handling (opt.disableflags): every bit the reference tests somewhere on the path, on the scene that has the
+    # feature -- contacts / limits + friction loss / gravity + warm start + ctrl clamping / springs + dampers + actuation /
+    # the whole constraint stage / sensors + refsafe (sink), equalities (equality_bodies), parent-child filtering (raw ant: more
+    # candidate pairs), and Humanoid with its XML's eulerdamp="disable" cleared (the implicit damping re-solve of _euler)
+    ("sink_nocontact", "sink", {"disableflags": 16}, 32, -3.0, 2),
+    ("sink_nolimit_nofrictionloss", "sink", {"disableflags": 12}, 32, -3.0, 2),
+    ("sink_nogravity_nowarmstart_noclamp", "sink", {"disableflags": 896}, 32, -3.0, 2),
+    ("sink_nospring_nodamper_noactuation", "sink", {"disableflags": 2144}, 32, -3.0, 2),
+    ("sink_noconstraint", "sink", {"disableflags": 1}, 32, -3.0, 2),
+    ("sink_nosensor_norefsafe", "sink", {"disableflags": 12288}, 32, -3.0, 2),
+    ("equality_bodies_noequality", "equality_bodies", {"disableflags": 2}, 32, 0.0, 2),
+    ("ant_nofilterparent", "ant", {"disableflags": 1024}, 32, 0.0, 1),
+    ("humanoid_eulerdamp", "humanoid", {"disableflags": 0}, 32, 0.4, 1),
 ]
 
 
