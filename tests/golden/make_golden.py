@@ -129,7 +129,34 @@ CASES = [
     ("equality_bodies_noequality", "equality_bodies", {"disableflags": 2}, 32, 0.0, 2),
     ("ant_nofilterparent", "ant", {"disableflags": 1024}, 32, 0.0, 1),
     ("humanoid_eulerdamp", "humanoid", {"disableflags": 0}, 32, 0.4, 1),
+    # step inputs beyond qpos / qvel / ctrl (EXTRA below): Cartesian and joint-space applied forces (support.xfrc_accumulate
+    # :184-194, forward.py:222-228), equalities switched per env through eq_active (constraint.py:195-200), mocap poses driving
+    # kinematics (smooth.py:105-113)
+    ("humanoid_applied", "humanoid", {"iterations": 100, "ls_iterations": 50}, 32, 0.4, 2),   # converged: the 1-iteration XML solver is discontinuous at most of these states
+    ("equality_bodies_toggled", "equality_bodies", {}, 32, 0.0, 2),
+    ("equality_sites_toggled", "equality", {}, 32, 0.3, 2),
+    ("pendula_mocap", "pendula", {}, 32, 0.0, 2),
 ]
+
+
+def extra_inputs(name, lite, B):
+    """Seeded extra step inputs of the fixtures named *_applied / *_toggled / *_mocap (recorded as in_<field>)."""
+    rng = np.random.RandomState(sum(map(ord, name)))
+    out = {}
+    if name.endswith("_applied") or name.endswith("_mocap"):
+        x = 20.0 * rng.randn(B, lite.nbody, 6)
+        x[:, 0] = 0.0
+        x *= (rng.rand(B, lite.nbody, 1) < 0.35)      # most bodies carry exactly zero wrench (the skip path)
+        out["xfrc_applied"] = x
+        out["qfrc_applied"] = 2.0 * rng.randn(B, lite.nv)
+    if name.endswith("_toggled"):
+        out["eq_active"] = (rng.rand(B, lite.neq) < 0.6).astype(np.uint8)
+    if name.endswith("_mocap"):
+        ids = [b for b in range(lite.nbody) if int(lite.body_mocapid[b]) >= 0]
+        pos = np.stack([np.asarray(lite.body_pos[b]) for b in ids])[None] + 0.2 * rng.randn(B, len(ids), 3)
+        quat = rng.randn(B, len(ids), 4)
+        out["mocap_pos"], out["mocap_quat"] = pos, quat / np.linalg.norm(quat, axis=-1, keepdims=True) * rng.uniform(0.5, 2.0, (B, len(ids), 1))
+    return out
 
 
 # every fixture records at least this many envs (the per-fixture counts in CASES are the historical minimum)
@@ -151,6 +178,7 @@ def run_case(name, model, opt, B, drop, nsteps):
         qpos, qvel, ctrl, act = util.sink_state(lite, B)
     elif drop < 0:  # pile-up state: every free body lowered and tilted so that convex pairs interpenetrate
         qpos, qvel, ctrl = util.pile_state(lite, B) if drop > -1.5 else util.stack_state(lite, B)
+    extra = extra_inputs(name, lite, B)
     mx = ref_device.device_put(mujoco.MjModel(lite))
     dx0 = ref_io.make_data(mx)
     outs = {k: [] for k in OUT_FIELDS}
@@ -159,13 +187,16 @@ def run_case(name, model, opt, B, drop, nsteps):
         d = dx0.replace(qpos=torch.as_tensor(qpos[b]), qvel=torch.as_tensor(qvel[b]), ctrl=torch.as_tensor(ctrl[b]))
         if act is not None:
             d = d.replace(act=torch.as_tensor(act[b]))
+        for k, v in extra.items():
+            d = d.replace(**{k: torch.as_tensor(v[b]).to(getattr(dx0, k).dtype)})
         for _ in range(nsteps):
             d = ref_forward.step(mx, d, fixed_iterations=fixed)
         for k in OUT_FIELDS:
             outs[k].append(np.asarray(getattr(d, k)))
         for k in CONTACT_FIELDS:
             cons[k].append(np.asarray(getattr(d.contact, k)))
-    save = {"in_qpos": qpos, "in_qvel": qvel, "in_ctrl": ctrl, **({"in_act": act} if act is not None else {}), "nsteps": np.int64(nsteps),
+    save = {"in_qpos": qpos, "in_qvel": qvel, "in_ctrl": ctrl, **({"in_act": act} if act is not None else {}),
+            **{"in_" + k: v for k, v in extra.items()}, "nsteps": np.int64(nsteps),
             "opt_keys": np.array(list(opt.keys()), dtype="U32"), "opt_vals": np.array(list(opt.values()), dtype=np.float64),
             "model": np.array(model), "torch_version": np.array(torch.__version__)}
     for k, v in outs.items():

@@ -34,6 +34,11 @@ def _load(path):
     return z, mj
 
 
+def _extra(z):
+    """Recorded step inputs beyond qpos / qvel / ctrl / act (applied forces, equality switches, mocap poses)."""
+    return {k: z["in_" + k] for k in util.EXTRA_INPUTS if "in_" + k in z.files}
+
+
 def _fixed(z):
     return bool(dict(zip((str(k) for k in z["opt_keys"]), z["opt_vals"])).get("fixed_iterations", 0))
 
@@ -104,7 +109,7 @@ def _oracle_unstable(path, z, mj):
     B = z["in_qpos"].shape[0]
     unstable = np.zeros(B, dtype=bool)
     if z["out_efc_J"].shape[1]:
-        kw = dict(nsteps=int(z["nsteps"]), act=z["in_act"] if "in_act" in z.files else None, fixed_iterations=_fixed(z))
+        kw = dict(nsteps=int(z["nsteps"]), act=z["in_act"] if "in_act" in z.files else None, fixed_iterations=_fixed(z), extra=_extra(z))
         base = util.run_oracle(mj, z["in_qpos"], z["in_qvel"], z["in_ctrl"], torch.float64, **kw)[1].qacc.numpy()
         rng = np.random.RandomState(17)
         scale = max(np.abs(base).max(), 1e-6)
@@ -174,7 +179,7 @@ def _recorded_branch(z, mj, get_contact, get):
 def test_oracle_matches_reference(path):
     z, mj = _load(path)
     mo, do = util.run_oracle(mj, z["in_qpos"], z["in_qvel"], z["in_ctrl"], torch.float64, nsteps=int(z["nsteps"]),
-                             act=z["in_act"] if "in_act" in z.files else None, fixed_iterations=_fixed(z))
+                             act=z["in_act"] if "in_act" in z.files else None, fixed_iterations=_fixed(z), extra=_extra(z))
     ocon = {"dist": "contact_dist", "pos": "contact_pos", "frame": "contact_frame"}
 
     def get_contact(k):
@@ -201,7 +206,7 @@ def test_oracle_matches_reference(path):
 def test_cuda_matches_reference(path):
     z, mj = _load(path)
     mx, dc = util.run_cuda(mj, z["in_qpos"], z["in_qvel"], z["in_ctrl"], torch.float64, nsteps=int(z["nsteps"]),
-                           act=z["in_act"] if "in_act" in z.files else None, fixed_iterations=_fixed(z))
+                           act=z["in_act"] if "in_act" in z.files else None, fixed_iterations=_fixed(z), extra=_extra(z))
     sel, zs = _recorded_branch(z, mj, lambda k: getattr(dc.contact, k).cpu().numpy(), lambda k: getattr(dc, k).cpu().numpy())
     _check_excluding_discontinuities(path, z, mj, zs, sel, lambda k: getattr(dc, k).cpu().numpy()[sel],
                                      lambda k: getattr(dc.contact, k).cpu().numpy()[sel], "cuda")

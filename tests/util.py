@@ -124,7 +124,11 @@ def terrain_state(mj, B, seed=31):
     return qpos, 0.3 * rng.randn(B, mj.nv), np.zeros((B, mj.nu))
 
 
-def run_oracle(mj, qpos, qvel, ctrl, dtype=torch.float64, nsteps=1, warm=None, act=None, fixed_iterations=False):
+# step inputs beyond qpos / qvel / ctrl / act that a fixture may record (tests/golden/make_golden.py: "in_" + name)
+EXTRA_INPUTS = ("xfrc_applied", "qfrc_applied", "eq_active", "mocap_pos", "mocap_quat")
+
+
+def run_oracle(mj, qpos, qvel, ctrl, dtype=torch.float64, nsteps=1, warm=None, act=None, fixed_iterations=False, extra=None):
     from oracle import forward as of
     from oracle import model as om
 
@@ -135,13 +139,15 @@ def run_oracle(mj, qpos, qvel, ctrl, dtype=torch.float64, nsteps=1, warm=None, a
         d.qacc_warmstart = torch.as_tensor(warm).to(dtype)
     if act is not None:
         d.act = torch.as_tensor(act).to(dtype)
+    for k, v in (extra or {}).items():
+        setattr(d, k, torch.as_tensor(v).to(torch.int32 if k == "eq_active" else dtype))
     for _ in range(nsteps):
         d = of.step(m, d, fixed_iterations=fixed_iterations)
     return m, d
 
 
 def run_cuda(mj, qpos, qvel, ctrl, dtype=torch.float64, nsteps=1, warm=None, device="cuda:0", act=None, fixed_iterations=False,
-             outputs="full"):
+             outputs="full", extra=None):
     import mujoco_torch_b200 as mt
 
     mx = mt.device_put(mj, dtype=dtype).to(device)
@@ -152,6 +158,8 @@ def run_cuda(mj, qpos, qvel, ctrl, dtype=torch.float64, nsteps=1, warm=None, dev
         kw["qacc_warmstart"] = torch.as_tensor(warm, device=device).to(dtype)
     if act is not None:
         kw["act"] = torch.as_tensor(act, device=device).to(dtype)
+    for k, v in (extra or {}).items():
+        kw[k] = torch.as_tensor(v, device=device).to(getattr(d, k).dtype if k == "eq_active" else dtype)
     d = d.replace(**kw)
     for _ in range(nsteps):
         d = mt.step(mx, d, fixed_iterations=fixed_iterations, outputs=outputs)
