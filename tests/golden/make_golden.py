@@ -136,6 +136,14 @@ CASES = [
     ("equality_bodies_toggled", "equality_bodies", {}, 32, 0.0, 2),
     ("equality_sites_toggled", "equality", {}, 32, 0.3, 2),
     ("pendula_mocap", "pendula", {}, 32, 0.0, 2),
+    # solver / option combinations not recorded above: CG with the pyramidal cone, CG run to convergence on Humanoid, impratio != 1
+    # in both cones (constraint.py:487, 549), the zoo Ant with its default Newton / pyramidal options, Walker2d with Euler
+    ("halfcheetah_cg", "halfcheetah", {"solver": 1}, 32, 0.6, 2),
+    ("humanoid_cg_converged", "humanoid", {"solver": 1, "iterations": 100, "ls_iterations": 50}, 32, 0.4, 1),
+    ("sink_impratio", "sink", {"impratio": 5.0}, 32, -3.0, 2),
+    ("sink_elliptic_impratio", "sink", {"cone": 1, "impratio": 0.5}, 32, -3.0, 2),
+    ("ant_zoo_default", "ant_zoo", {}, 32, 0.5, 2),
+    ("walker2d", "walker2d", {}, 32, 0.8, 2),
 ]
 
 
