@@ -144,6 +144,14 @@ CASES = [
     ("sink_elliptic_impratio", "sink", {"cone": 1, "impratio": 0.5}, 32, -3.0, 2),
     ("ant_zoo_default", "ant_zoo", {}, 32, 0.5, 2),
     ("walker2d", "walker2d", {}, 32, 0.8, 2),
+    # ctrl three times its range: clamping active in most envs (forward.py:117-126), and the same with DSBL_CLAMPCTRL;
+    # sink at three times ctrl also drives its position actuator into its forcerange
+    ("halfcheetah_bigctrl", "halfcheetah", {}, 32, 0.6, 2),
+    ("halfcheetah_bigctrl_noclamp", "halfcheetah", {"disableflags": 256}, 32, 0.6, 2),
+    ("sink_bigctrl", "sink", {}, 32, -3.0, 2),
+    # vector options: tilted gravity (converged solver), wind + viscosity on top of the swimmer's density (inertia-box fluid model)
+    ("humanoid_gravity_tilted", "humanoid", {"iterations": 100, "ls_iterations": 50, "gravity[0]": 3.0, "gravity[2]": -7.0}, 32, 0.4, 2),
+    ("swimmer_wind_viscosity", "swimmer", {"wind[0]": 0.7, "wind[1]": -0.4, "viscosity": 0.05}, 32, 0.0, 2),
 ]
 
 
@@ -186,6 +194,8 @@ def run_case(name, model, opt, B, drop, nsteps):
         qpos, qvel, ctrl, act = util.sink_state(lite, B)
     elif drop < 0:  # pile-up state: every free body lowered and tilted so that convex pairs interpenetrate
         qpos, qvel, ctrl = util.pile_state(lite, B) if drop > -1.5 else util.stack_state(lite, B)
+    if "_bigctrl" in name:
+        ctrl = 3.0 * ctrl
     extra = extra_inputs(name, lite, B)
     mx = ref_device.device_put(mujoco.MjModel(lite))
     dx0 = ref_io.make_data(mx)

@@ -14,7 +14,13 @@ def load_model(name, **opt_overrides):
 
     mj = MjModelLite.load_npz(os.path.join(MODELS, name + ".npz"))
     for k, v in opt_overrides.items():
-        setattr(mj.opt, k, v)
+        if k.endswith("]"):      # one component of a vector option: "gravity[0]", "wind[2]"
+            name, idx = k[:-1].split("[")
+            vec = np.array(getattr(mj.opt, name), dtype=np.float64)
+            vec[int(idx)] = v
+            setattr(mj.opt, name, vec)
+        else:
+            setattr(mj.opt, k, v)
     return mj
 
 
