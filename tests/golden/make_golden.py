@@ -152,6 +152,14 @@ CASES = [
     # vector options: tilted gravity (converged solver), wind + viscosity on top of the swimmer's density (inertia-box fluid model)
     ("humanoid_gravity_tilted", "humanoid", {"iterations": 100, "ls_iterations": 50, "gravity[0]": 3.0, "gravity[2]": -7.0}, 32, 0.4, 2),
     ("swimmer_wind_viscosity", "swimmer", {"wind[0]": 0.7, "wind[1]": -0.4, "viscosity": 0.05}, 32, 0.0, 2),
+    # integrator x feature and cone x solver x model combinations that only appeared separately above
+    ("muscle_rk4", "muscle", {"integrator": 1}, 32, -4.0, 2),
+    ("sink_rk4", "sink", {"integrator": 1}, 32, -3.0, 1),
+    ("satellite_small_rk4", "satellite_small", {"integrator": 1}, 32, 0.0, 2),
+    # (a CG run that stops at `tolerance` is not usable as a pin: hopper + CG + elliptic lands 2e-8 from the recording in the
+    # oracle itself -- one iteration more or less at the threshold; the CG recordings above use fixed_iterations or stay far from it)
+    ("walker2d_elliptic", "walker2d", {"cone": 1, "iterations": 100, "ls_iterations": 50}, 32, 0.8, 2),
+    ("humanoid_elliptic_converged", "humanoid", {"cone": 1, "iterations": 100, "ls_iterations": 50}, 32, 0.4, 1),
 ]
 
 
