@@ -235,3 +235,23 @@ def test_g10_rows_per_contact(cone, condim, rows):
     assert m.ncon == 1 and m.nefc == rows
     d = of.step(m, of.make_data(m, 2))
     assert d.efc_J.shape == (2, rows, 6) and torch.isfinite(d.qpos).all()
+
+
+def test_every_recording_has_a_recipe_and_every_recipe_a_recording():
+    """tests/golden/*.npz and the CASES list of tests/golden/make_golden.py (the committed generating script) name the same
+    fixtures, and every recording says which model / options / step count it was made with."""
+    import ast
+    import glob
+    import os
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    src = open(os.path.join(here, "golden", "make_golden.py")).read()
+    tree = ast.parse(src)
+    cases = next(n.value for n in tree.body if isinstance(n, ast.Assign) and getattr(n.targets[0], "id", "") == "CASES")
+    names = sorted(ast.literal_eval(e.elts[0]) for e in cases.elts)
+    files = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(here, "golden", "*.npz")))
+    assert names == files, (set(names) ^ set(files))
+    for f in files:
+        z = np.load(os.path.join(here, "golden", f + ".npz"))
+        assert {"in_qpos", "in_qvel", "in_ctrl", "nsteps", "opt_keys", "opt_vals", "model", "out_qpos", "out_qacc"} <= set(z.files), f
+        assert z["in_qpos"].shape[0] >= 32 and z["out_qpos"].shape == z["in_qpos"].shape, f
